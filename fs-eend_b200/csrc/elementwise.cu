@@ -1,0 +1,216 @@
+// Bandwidth-bound kernels of the FS-EEND hot path: input BatchNorm+cast, speaker-axis attention, logits head.
+#include "elementwise.cuh"
+
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace fseend {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// x (packed fp32 rows, cu_seqlens) -> BN(eval) -> fp16 [B][Tmax][Kpad]; rows t >= len take x = -1
+// (the reference pads with -1 BEFORE BatchNorm, FS:model:165-166); columns >= Din are zero.
+__global__ void prep_input_kernel(const float* __restrict__ x, const int* __restrict__ cu, int Tmax, int Din,
+                                  int Kpad, const float* __restrict__ sc, const float* __restrict__ sh,
+                                  __half* __restrict__ out) {
+  const int row = blockIdx.x;  // b * Tmax + t
+  const int b = row / Tmax, t = row - b * Tmax;
+  const int start = cu[b], len = cu[b + 1] - start;
+  const float* src = (t < len) ? x + static_cast<size_t>(start + t) * Din : nullptr;
+  __half2* dst = reinterpret_cast<__half2*>(out + static_cast<size_t>(row) * Kpad);
+  for (int i = threadIdx.x; i < Kpad / 2; i += blockDim.x) {
+    const int c0 = 2 * i, c1 = 2 * i + 1;
+    float v0 = 0.f, v1 = 0.f;
+    if (c0 < Din) v0 = fmaf(src ? __ldg(src + c0) : -1.f, sc[c0], sh[c0]);
+    if (c1 < Din) v1 = fmaf(src ? __ldg(src + c1) : -1.f, sc[c1], sh[c1]);
+    dst[i] = __floats2half2_rn(v0, v1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Speaker-axis attention (FS:fusion:390, no mask): for every frame, S x S attention per head over the
+// S attractor rows.  qkv: [frames][S][768] fp16, out: [frames][S][256] fp16.
+// One thread = (frame, head, query slot); K/V of the block's frames are staged in shared memory.
+constexpr int kMaxS = 16;
+
+__global__ void __launch_bounds__(128)
+spk_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n_frames, int S, float scale,
+                int frames_per_block) {
+  extern __shared__ uint4 kv_smem[];  // [F][S][64 uint4] : K (32 uint4) then V (32 uint4) per row
+  const int f0 = blockIdx.x * frames_per_block;
+  const int nf = min(frames_per_block, n_frames - f0);
+  const int rows = nf * S;
+  for (int i = threadIdx.x; i < rows * 64; i += blockDim.x) {
+    const int rr = i >> 6, cc = i & 63;
+    kv_smem[i] = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<size_t>(f0) * S + rr) * 768 + 256) + cc);
+  }
+  __syncthreads();
+  const int tpf = 4 * S;
+  const int f = threadIdx.x / tpf;
+  if (f >= nf) return;
+  const int rem = threadIdx.x - f * tpf;
+  const int a = rem >> 2, h = rem & 3;   // heads fastest: 4 consecutive threads read 512 contiguous bytes of q
+
+  float q[64];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(qkv + (static_cast<size_t>(f0 + f) * S + a) * 768 + h * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint4 u = __ldg(qp + i);
+      const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 t = __half22float2(hh[j]);
+        q[i * 8 + 2 * j] = t.x * scale;
+        q[i * 8 + 2 * j + 1] = t.y * scale;
+      }
+    }
+  }
+  float sc[kMaxS];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int bb = 0; bb < kMaxS; ++bb) {
+    sc[bb] = -INFINITY;
+    if (bb < S) {
+      const uint4* kp = kv_smem + (f * S + bb) * 64 + h * 8;
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 u = kp[i];
+        const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 t = __half22float2(hh[j]);
+          d = fmaf(q[i * 8 + 2 * j], t.x, d);
+          d = fmaf(q[i * 8 + 2 * j + 1], t.y, d);
+        }
+      }
+      sc[bb] = d;
+      mx = fmaxf(mx, d);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int bb = 0; bb < kMaxS; ++bb) {
+    if (bb < S) {
+      sc[bb] = __expf(sc[bb] - mx);
+      sum += sc[bb];
+    }
+  }
+  const float inv = 1.f / sum;
+  float o[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int bb = 0; bb < kMaxS; ++bb) {
+    if (bb < S) {
+      // the reference multiplies fp32 probabilities with V; keep P in fp32 (no tensor core here)
+      const float pw = sc[bb] * inv;
+      const uint4* vp = kv_smem + (f * S + bb) * 64 + 32 + h * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 u = vp[i];
+        const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 t = __half22float2(hh[j]);
+          o[i * 8 + 2 * j] = fmaf(pw, t.x, o[i * 8 + 2 * j]);
+          o[i * 8 + 2 * j + 1] = fmaf(pw, t.y, o[i * 8 + 2 * j + 1]);
+        }
+      }
+    }
+  }
+  uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(f0 + f) * S + a) * 256 + h * 64);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 u;
+    __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hh[j] = __floats2half2_rn(o[i * 8 + 2 * j], o[i * 8 + 2 * j + 1]);
+    op[i] = u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Logits head (FS:model:43,60): att_n = att / ||att||, y[frame][s] = emb[frame] . att_n[frame][s].
+// One warp per frame; each lane owns 8 of the 256 channels.
+__global__ void __launch_bounds__(256)
+head_kernel(const __half* __restrict__ emb, const __half* __restrict__ att, int n_frames, int S,
+            float* __restrict__ logits, float* __restrict__ emb_f32, float* __restrict__ att_f32) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_frames) return;
+  float e[8];
+  {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(emb + static_cast<size_t>(warp) * 256) + lane);
+    const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 t = __half22float2(hh[j]);
+      e[2 * j] = t.x;
+      e[2 * j + 1] = t.y;
+    }
+    if (emb_f32) {
+      float4* ep = reinterpret_cast<float4*>(emb_f32 + static_cast<size_t>(warp) * 256 + lane * 8);
+      ep[0] = make_float4(e[0], e[1], e[2], e[3]);
+      ep[1] = make_float4(e[4], e[5], e[6], e[7]);
+    }
+  }
+  for (int s = 0; s < S; ++s) {
+    const size_t row = static_cast<size_t>(warp) * S + s;
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(att + row * 256) + lane);
+    const __half2* hh = reinterpret_cast<const __half2*>(&u);
+    float a[8];
+    float ss = 0.f, dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 t = __half22float2(hh[j]);
+      a[2 * j] = t.x;
+      a[2 * j + 1] = t.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ss = fmaf(a[j], a[j], ss);
+      dot = fmaf(a[j], e[j], dot);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, off);
+      dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    }
+    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+    if (lane == 0) logits[row] = dot * inv;
+    if (att_f32) {
+      float4* ap = reinterpret_cast<float4*>(att_f32 + row * 256 + lane * 8);
+      ap[0] = make_float4(a[0] * inv, a[1] * inv, a[2] * inv, a[3] * inv);
+      ap[1] = make_float4(a[4] * inv, a[5] * inv, a[6] * inv, a[7] * inv);
+    }
+  }
+}
+
+}  // namespace
+
+void launch_prep_input(const float* x, const int* cu_seqlens, int B, int Tmax, int Din, int Kpad, const float* sc,
+                       const float* sh, __half* out, cudaStream_t stream) {
+  prep_input_kernel<<<B * Tmax, 192, 0, stream>>>(x, cu_seqlens, Tmax, Din, Kpad, sc, sh, out);
+}
+
+int launch_spk_attn(const __half* qkv, __half* out, int n_frames, int S, float scale, cudaStream_t stream) {
+  if (S < 1 || S > kMaxS) return -1;
+  const int fpb = 128 / (4 * S);
+  const int smem = fpb * S * 64 * 16;
+  const int grid = (n_frames + fpb - 1) / fpb;
+  spk_attn_kernel<<<grid, 128, smem, stream>>>(qkv, out, n_frames, S, scale, fpb);
+  return 0;
+}
+
+void launch_head(const __half* emb, const __half* att, int n_frames, int S, float* logits, float* emb_f32,
+                 float* att_f32, cudaStream_t stream) {
+  const int warps_per_block = 8;
+  const int grid = (n_frames + warps_per_block - 1) / warps_per_block;
+  head_kernel<<<grid, warps_per_block * 32, 0, stream>>>(emb, att, n_frames, S, logits, emb_f32, att_f32);
+}
+
+}  // namespace fseend

@@ -1,0 +1,21 @@
+// Bandwidth-bound kernels of the FS-EEND hot path (see elementwise.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace fseend {
+
+// x: packed fp32 rows [sum(len)][Din]; cu_seqlens: device int[B+1]; out: fp16 [B][Tmax][Kpad].
+// out = x * sc + sh (BatchNorm eval folded into per-channel scale/shift), rows t >= len use x = -1.
+void launch_prep_input(const float* x, const int* cu_seqlens, int B, int Tmax, int Din, int Kpad, const float* sc,
+                       const float* sh, __half* out, cudaStream_t stream);
+
+// qkv: [n_frames][S][768] fp16 -> out [n_frames][S][256] fp16; S <= 16.  Returns -1 on unsupported S.
+int launch_spk_attn(const __half* qkv, __half* out, int n_frames, int S, float scale, cudaStream_t stream);
+
+// emb: [n_frames][256], att: [n_frames][S][256] (un-normalised) -> logits [n_frames][S] fp32;
+// optional fp32 copies of emb and of the L2-normalised attractors.
+void launch_head(const __half* emb, const __half* att, int n_frames, int S, float* logits, float* emb_f32,
+                 float* att_f32, cudaStream_t stream);
+
+}  // namespace fseend

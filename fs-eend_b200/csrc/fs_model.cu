@@ -1,0 +1,798 @@
+// FS-EEND model object behind the C ABI (include/fseend_b200.h): weight conversion, workspace/TMA-descriptor
+// plan per (B, Tmax, S), and the launch sequence of the forward pass.
+//
+// Reference path restated here (file:line relative to /root/reference/FS-EEND/nnet):
+//   model/onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm.py:67-84   test()
+//   ...:162-188  encoder  | :38-41 conv + L2 | :112-118 decoder | modules/merge_tfm_encoder.py:356-376 fusion layer
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fseend_b200.h"
+#include "attn.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "tmap.h"
+
+namespace fseend {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+
+#define CUDA_CHECK(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      throw std::runtime_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e));        \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void alloc(size_t n) {
+    free();
+    CUDA_CHECK(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  ~DevBuf() { free(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// fp16 weight matrix [rows][K] on the device + its TMA descriptor (box 64 x 256 rows)
+struct WMat {
+  DevBuf buf;
+  int rows = 0, K = 0;
+  CUtensorMap tm;
+  void upload(const std::vector<__half>& h, int rows_, int K_) {
+    rows = rows_;
+    K = K_;
+    buf.alloc(h.size() * sizeof(__half));
+    CUDA_CHECK(cudaMemcpy(buf.p, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows)};
+    uint64_t str[1] = {static_cast<uint64_t>(K)};
+    uint32_t box[2] = {64, 256};
+    tm = make_tmap_f16(buf.p, 2, dims, str, box);
+  }
+};
+
+struct FVec {
+  DevBuf buf;
+  void upload(const std::vector<float>& h) {
+    buf.alloc(h.size() * sizeof(float));
+    CUDA_CHECK(cudaMemcpy(buf.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  const float* f() const { return static_cast<const float*>(buf.p); }
+};
+
+struct EncLayer {
+  WMat wqkv, wo, w1, w2;
+  FVec bqkv, bo, b1, b2, g1, be1, g2, be2;
+};
+struct DecLayer {
+  WMat wqkv1, wo1, wqkv2, wo2, w1, w2;
+  FVec bqkv1, bo1, bqkv2, bo2, b1, b2, g11, be11, g21, be21, g22, be22;
+};
+
+struct ProfEntry {
+  std::string name;
+  cudaEvent_t a, b;
+};
+
+}  // namespace
+}  // namespace fseend
+
+using namespace fseend;
+
+struct fseend_fs_model {
+  fseend_fs_config cfg;
+  int Kin = 0;  // in_size padded to a multiple of 64
+  FVec bn_scale, bn_shift;
+  WMat w_in;
+  FVec b_in, g_in, be_in;
+  std::vector<std::unique_ptr<EncLayer>> enc;
+  WMat w_conv;
+  FVec b_conv;
+  WMat w_cvt;
+  FVec pe_proj;  // [kMaxSlots][256]
+  std::vector<std::unique_ptr<DecLayer>> dec;
+
+  // ---- plan (workspace + descriptors) for the current (B, T, S)
+  int pB = 0, pT = 0, pS = 0;
+  size_t ws_bytes = 0;
+  DevBuf x16, hA, hB, qkv_e, ao_e, f_e, emb16, aX, aY, aZ, qkv_d, ao_d, f_d, cu_dev, len_dev, x_stage, logits_stage;
+  int* cu_host = nullptr;  // pinned [B+1] + [B]
+  // descriptors
+  CUtensorMap tm_x16, tm_hA, tm_hB, tm_qkv_e_out, tm_qkv_e_attn, tm_ao_e_attn, tm_ao_e, tm_f_e_out, tm_f_e_in;
+  CUtensorMap tm_hconv_in, tm_emb_out, tm_emb_in, tm_cvt_out;
+  CUtensorMap tm_aX, tm_aY, tm_aZ, tm_qkv_d_out, tm_qkv_d_attn, tm_ao_d_attn, tm_ao_d, tm_f_d_out, tm_f_d_in;
+
+  bool profiling = false;
+  std::vector<ProfEntry> prof_pending;
+  std::map<std::string, std::pair<double, int>> prof_acc;
+  int launches_last = 0;
+
+  ~fseend_fs_model() {
+    if (cu_host) cudaFreeHost(cu_host);
+  }
+};
+
+namespace fseend {
+namespace {
+
+constexpr int kMaxSlots = 16;
+
+struct TensorTable {
+  std::map<std::string, std::pair<const float*, long long>> t;
+  const float* get(const std::string& name, long long numel) const {
+    auto it = t.find(name);
+    if (it == t.end()) throw std::invalid_argument("missing state_dict tensor: " + name);
+    if (it->second.second != numel)
+      throw std::invalid_argument("state_dict tensor " + name + " has " + std::to_string(it->second.second) +
+                                  " elements, expected " + std::to_string(numel));
+    return it->second.first;
+  }
+  // positional-encoding buffer may be longer than needed
+  const float* get_atleast(const std::string& name, long long numel) const {
+    auto it = t.find(name);
+    if (it == t.end()) throw std::invalid_argument("missing state_dict tensor: " + name);
+    if (it->second.second < numel) throw std::invalid_argument("state_dict tensor " + name + " too small");
+    return it->second.first;
+  }
+};
+
+std::vector<__half> to_half(const float* w, size_t n) {
+  std::vector<__half> h(n);
+  for (size_t i = 0; i < n; ++i) h[i] = __float2half_rn(w[i]);
+  return h;
+}
+std::vector<float> to_vec(const float* w, size_t n) { return std::vector<float>(w, w + n); }
+
+void load_linear(const TensorTable& tt, const std::string& name, int out_f, int in_f, WMat& w, FVec& b) {
+  w.upload(to_half(tt.get(name + ".weight", 1ll * out_f * in_f), 1ull * out_f * in_f), out_f, in_f);
+  b.upload(to_vec(tt.get(name + ".bias", out_f), out_f));
+}
+void load_ln(const TensorTable& tt, const std::string& name, int n, FVec& g, FVec& b) {
+  g.upload(to_vec(tt.get(name + ".weight", n), n));
+  b.upload(to_vec(tt.get(name + ".bias", n), n));
+}
+void load_attn(const TensorTable& tt, const std::string& name, int D, WMat& wqkv, FVec& bqkv, WMat& wo, FVec& bo) {
+  wqkv.upload(to_half(tt.get(name + ".in_proj_weight", 3ll * D * D), 3ull * D * D), 3 * D, D);
+  bqkv.upload(to_vec(tt.get(name + ".in_proj_bias", 3 * D), 3 * D));
+  load_linear(tt, name + ".out_proj", D, D, wo, bo);
+}
+
+void build_model(fseend_fs_model* m, const TensorTable& tt) {
+  const fseend_fs_config& c = m->cfg;
+  const int D = c.n_units, Din = c.in_size;
+  m->Kin = (Din + 63) / 64 * 64;
+  // BatchNorm1d (eval) -> per-channel affine applied in fp32 before the fp16 cast (FS:model:166)
+  {
+    const float* w = tt.get("enc.bn.weight", Din);
+    const float* b = tt.get("enc.bn.bias", Din);
+    const float* mu = tt.get("enc.bn.running_mean", Din);
+    const float* var = tt.get("enc.bn.running_var", Din);
+    std::vector<float> sc(Din), sh(Din);
+    for (int i = 0; i < Din; ++i) {
+      sc[i] = w[i] / sqrtf(var[i] + c.bn_eps);
+      sh[i] = b[i] - mu[i] * sc[i];
+    }
+    m->bn_scale.upload(sc);
+    m->bn_shift.upload(sh);
+  }
+  {  // input projection, K zero-padded to Kin (FS:model:173-174)
+    const float* w = tt.get("enc.encoder.weight", 1ll * D * Din);
+    std::vector<__half> h(1ull * D * m->Kin, __float2half_rn(0.f));
+    for (int o = 0; o < D; ++o)
+      for (int i = 0; i < Din; ++i) h[1ull * o * m->Kin + i] = __float2half_rn(w[1ull * o * Din + i]);
+    m->w_in.upload(h, D, m->Kin);
+    m->b_in.upload(to_vec(tt.get("enc.encoder.bias", D), D));
+    load_ln(tt, "enc.encoder_norm", D, m->g_in, m->be_in);
+  }
+  for (int l = 0; l < c.enc_n_layers; ++l) {
+    auto L = std::make_unique<EncLayer>();
+    const std::string p = "enc.transformer_encoder.layers." + std::to_string(l);
+    load_attn(tt, p + ".self_attn", D, L->wqkv, L->bqkv, L->wo, L->bo);
+    load_linear(tt, p + ".linear1", c.enc_dim_feedforward, D, L->w1, L->b1);
+    load_linear(tt, p + ".linear2", D, c.enc_dim_feedforward, L->w2, L->b2);
+    load_ln(tt, p + ".norm1", D, L->g1, L->be1);
+    load_ln(tt, p + ".norm2", D, L->g2, L->be2);
+    m->enc.push_back(std::move(L));
+  }
+  {  // Conv1d weight (Dout, Din, K) -> K tap matrices [tap][Dout][Din] (FS:model:30,40)
+    const int Kc = c.conv_kernel;
+    const float* w = tt.get("cnn.weight", 1ll * D * D * Kc);
+    std::vector<__half> h(1ull * Kc * D * D);
+    for (int k = 0; k < Kc; ++k)
+      for (int o = 0; o < D; ++o)
+        for (int i = 0; i < D; ++i)
+          h[(1ull * k * D + o) * D + i] = __float2half_rn(w[(1ull * o * D + i) * Kc + k]);
+    m->w_conv.upload(h, Kc * D, D);
+    m->b_conv.upload(to_vec(tt.get("cnn.bias", D), D));
+  }
+  {  // attractor init: convert(cat[emb, pe_s]) = Wc[:, :D] emb + (Wc[:, D:] pe_s + bc)  (FS:model:113-114)
+    const float* w = tt.get("dec.convert.weight", 2ll * D * D);
+    const float* b = tt.get("dec.convert.bias", D);
+    const float* pe = tt.get_atleast("dec.pos_enc.pe", 1ll * kMaxSlots * D);
+    std::vector<__half> h(1ull * D * D);
+    for (int o = 0; o < D; ++o)
+      for (int i = 0; i < D; ++i) h[1ull * o * D + i] = __float2half_rn(w[1ull * o * 2 * D + i]);
+    m->w_cvt.upload(h, D, D);
+    std::vector<float> pp(1ull * kMaxSlots * D);
+    for (int s = 0; s < kMaxSlots; ++s)
+      for (int o = 0; o < D; ++o) {
+        double acc = b[o];
+        for (int i = 0; i < D; ++i) acc += static_cast<double>(w[1ull * o * 2 * D + D + i]) * pe[1ull * s * D + i];
+        pp[1ull * s * D + o] = static_cast<float>(acc);
+      }
+    m->pe_proj.upload(pp);
+  }
+  for (int l = 0; l < c.dec_n_layers; ++l) {
+    auto L = std::make_unique<DecLayer>();
+    const std::string p = "dec.attractor_decoder.layers." + std::to_string(l);
+    load_attn(tt, p + ".self_attn1", D, L->wqkv1, L->bqkv1, L->wo1, L->bo1);
+    load_attn(tt, p + ".self_attn2", D, L->wqkv2, L->bqkv2, L->wo2, L->bo2);
+    load_linear(tt, p + ".linear1", c.dec_dim_feedforward, D, L->w1, L->b1);
+    load_linear(tt, p + ".linear2", D, c.dec_dim_feedforward, L->w2, L->b2);
+    load_ln(tt, p + ".norm11", D, L->g11, L->be11);
+    load_ln(tt, p + ".norm21", D, L->g21, L->be21);
+    load_ln(tt, p + ".norm22", D, L->g22, L->be22);
+    m->dec.push_back(std::move(L));
+  }
+}
+
+CUtensorMap rows_map(const DevBuf& buf, uint64_t cols, uint64_t rows_per_seq, uint64_t n_seq) {
+  return make_tmap_rows3d(buf.p, cols, cols, rows_per_seq, n_seq, 128);
+}
+CUtensorMap attn_map(const DevBuf& buf, uint64_t cols, int S, int T, int B) {
+  uint64_t dims[4] = {cols, static_cast<uint64_t>(S), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+  uint64_t str[3] = {cols, cols * S, cols * S * T};
+  uint32_t box[4] = {64, 1, 128, 1};
+  return make_tmap_f16(buf.p, 4, dims, str, box);
+}
+
+void make_plan(fseend_fs_model* m, int B, int T, int S) {
+  if (m->pB == B && m->pT == T && m->pS == S) return;
+  const fseend_fs_config& c = m->cfg;
+  const int D = c.n_units;
+  const size_t Me = 1ull * B * T, Md = Me * S;
+  size_t total = 0;
+  auto A = [&](DevBuf& b, size_t bytes) {
+    b.alloc(bytes);
+    total += bytes;
+  };
+  A(m->x16, Me * m->Kin * 2);
+  A(m->hA, Me * D * 2);
+  A(m->hB, Me * D * 2);
+  A(m->qkv_e, Me * 3 * D * 2);
+  A(m->ao_e, Me * D * 2);
+  A(m->f_e, Me * c.enc_dim_feedforward * 2);
+  A(m->emb16, Me * D * 2);
+  A(m->aX, Md * D * 2);
+  A(m->aY, Md * D * 2);
+  A(m->aZ, Md * D * 2);
+  A(m->qkv_d, Md * 3 * D * 2);
+  A(m->ao_d, Md * D * 2);
+  A(m->f_d, Md * c.dec_dim_feedforward * 2);
+  A(m->cu_dev, (B + 1) * sizeof(int));
+  A(m->len_dev, B * sizeof(int));
+  m->x_stage.free();
+  m->logits_stage.free();
+  if (m->cu_host) cudaFreeHost(m->cu_host);
+  CUDA_CHECK(cudaMallocHost(&m->cu_host, (2 * B + 1) * sizeof(int)));
+  m->ws_bytes = total;
+
+  m->tm_x16 = rows_map(m->x16, m->Kin, Me, 1);
+  m->tm_hA = rows_map(m->hA, D, Me, 1);
+  m->tm_hB = rows_map(m->hB, D, Me, 1);
+  m->tm_qkv_e_out = rows_map(m->qkv_e, 3 * D, Me, 1);
+  m->tm_qkv_e_attn = attn_map(m->qkv_e, 3 * D, 1, T, B);
+  m->tm_ao_e_attn = attn_map(m->ao_e, D, 1, T, B);
+  m->tm_ao_e = rows_map(m->ao_e, D, Me, 1);
+  m->tm_f_e_out = rows_map(m->f_e, c.enc_dim_feedforward, Me, 1);
+  m->tm_f_e_in = m->tm_f_e_out;
+  // conv: per-sequence tiles so that shifted taps zero-fill across sequence ends
+  m->tm_hconv_in = rows_map(m->hA, D, T, B);   // encoder output always ends in hA (see forward)
+  m->tm_emb_out = rows_map(m->emb16, D, T, B);
+  m->tm_emb_in = rows_map(m->emb16, D, Me, 1);
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(S), Me};
+    uint64_t str[2] = {static_cast<uint64_t>(D), static_cast<uint64_t>(D) * S};
+    uint32_t box[3] = {64, 1, 128};
+    m->tm_cvt_out = make_tmap_f16(m->aX.p, 3, dims, str, box);
+  }
+  m->tm_aX = rows_map(m->aX, D, Md, 1);
+  m->tm_aY = rows_map(m->aY, D, Md, 1);
+  m->tm_aZ = rows_map(m->aZ, D, Md, 1);
+  m->tm_qkv_d_out = rows_map(m->qkv_d, 3 * D, Md, 1);
+  m->tm_qkv_d_attn = attn_map(m->qkv_d, 3 * D, S, T, B);
+  m->tm_ao_d_attn = attn_map(m->ao_d, D, S, T, B);
+  m->tm_ao_d = rows_map(m->ao_d, D, Md, 1);
+  m->tm_f_d_out = rows_map(m->f_d, c.dec_dim_feedforward, Md, 1);
+  m->tm_f_d_in = m->tm_f_d_out;
+  m->pB = B;
+  m->pT = T;
+  m->pS = S;
+}
+
+struct Launcher {
+  fseend_fs_model* m;
+  cudaStream_t st;
+  int count = 0;
+  template <class F>
+  void run(const char* name, F&& f) {
+    ProfEntry e;
+    if (m->profiling) {
+      e.name = name;
+      CUDA_CHECK(cudaEventCreate(&e.a));
+      CUDA_CHECK(cudaEventCreate(&e.b));
+      CUDA_CHECK(cudaEventRecord(e.a, st));
+    }
+    f();
+    ++count;
+    if (m->profiling) {
+      CUDA_CHECK(cudaEventRecord(e.b, st));
+      m->prof_pending.push_back(e);
+    }
+  }
+};
+
+GemmParams flat_params(size_t rows, int N, int K, int mode) {
+  GemmParams p{};
+  p.rows_per_seq = static_cast<int>(rows);
+  p.n_seq = 1;
+  p.tiles_per_seq = static_cast<int>((rows + 127) / 128);
+  p.n_tiles = N / 256;
+  p.k_blocks = K / 64;
+  p.taps = 1;
+  p.tap_shift = 0;
+  p.mode = mode;
+  p.ln_eps = 1e-5f;
+  return p;
+}
+
+void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, int B, int S, float* logits,
+                  float* emb_out, float* att_out, cudaStream_t st) {
+  const fseend_fs_config& c = m->cfg;
+  const int D = c.n_units;
+  if (B < 1) throw std::invalid_argument("B must be >= 1");
+  if (S < 1 || S > kMaxSlots) throw std::invalid_argument("max_nspks must be in [1,16]");
+  int T = 0;
+  long long total = 0;
+  for (int b = 0; b < B; ++b) {
+    if (ilens[b] < 1) throw std::invalid_argument("ilens must be >= 1");
+    T = ilens[b] > T ? ilens[b] : T;
+    total += ilens[b];
+  }
+  if (1ll * B * T * S * 768 >= (1ll << 31) * 8) throw std::invalid_argument("batch too large for one call");
+  make_plan(m, B, T, S);
+  const size_t Me = 1ull * B * T, Md = Me * S;
+
+  // cu_seqlens + lens: pinned staging -> device (async on the same stream)
+  m->cu_host[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    m->cu_host[b + 1] = m->cu_host[b] + ilens[b];
+    m->cu_host[B + 1 + b] = ilens[b];
+  }
+  CUDA_CHECK(cudaMemcpyAsync(m->cu_dev.p, m->cu_host, (B + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(m->len_dev.p, m->cu_host + B + 1, B * sizeof(int), cudaMemcpyHostToDevice, st));
+
+  Launcher L{m, st};
+  CUtensorMap none = m->tm_hA;  // placeholder for unused descriptor arguments
+
+  L.run("prep_input", [&] {
+    launch_prep_input(x_packed, static_cast<const int*>(m->cu_dev.p), B, T, c.in_size, m->Kin, m->bn_scale.f(),
+                      m->bn_shift.f(), static_cast<__half*>(m->x16.p), st);
+  });
+  // input projection + LN -> hA
+  {
+    GemmParams p = flat_params(Me, D, m->Kin, EPI_LN);
+    p.bias = m->b_in.f();
+    p.ln_g = m->g_in.f();
+    p.ln_b = m->be_in.f();
+    p.ln_eps = c.ln_eps;
+    L.run("gemm_in_ln", [&] { launch_gemm(m->tm_x16, m->w_in.tm, none, m->tm_hA, p, st); });
+  }
+  // encoder layers: hA -> (attn) -> hB -> (ffn) -> hA
+  for (int l = 0; l < c.enc_n_layers; ++l) {
+    EncLayer& E = *m->enc[l];
+    {
+      GemmParams p = flat_params(Me, 3 * D, D, EPI_BIAS);
+      p.bias = E.bqkv.f();
+      L.run("gemm_qkv", [&] { launch_gemm(m->tm_hA, E.wqkv.tm, none, m->tm_qkv_e_out, p, st); });
+    }
+    {
+      AttnParams a{B, 1, T, c.n_heads, c.has_mask ? c.mask_delay : (1 << 28), 1.f / sqrtf(64.f)};
+      L.run("attn_causal", [&] { launch_causal_attn(m->tm_qkv_e_attn, m->tm_ao_e_attn, a, st); });
+    }
+    {
+      GemmParams p = flat_params(Me, D, D, EPI_LN);
+      p.bias = E.bo.f();
+      p.has_residual = 1;
+      p.ln_g = E.g1.f();
+      p.ln_b = E.be1.f();
+      p.ln_eps = c.ln_eps;
+      L.run("gemm_out_ln", [&] { launch_gemm(m->tm_ao_e, E.wo.tm, m->tm_hA, m->tm_hB, p, st); });
+    }
+    {
+      GemmParams p = flat_params(Me, c.enc_dim_feedforward, D, EPI_BIAS);
+      p.bias = E.b1.f();
+      p.relu = 1;
+      L.run("gemm_ffn1", [&] { launch_gemm(m->tm_hB, E.w1.tm, none, m->tm_f_e_out, p, st); });
+    }
+    {
+      GemmParams p = flat_params(Me, D, c.enc_dim_feedforward, EPI_LN);
+      p.bias = E.b2.f();
+      p.has_residual = 1;
+      p.ln_g = E.g2.f();
+      p.ln_b = E.be2.f();
+      p.ln_eps = c.ln_eps;
+      // last layer: rows t >= ilens[b] become zeros = the reference's truncate + re-pad(0) (FS:model:38-39)
+      if (l == c.enc_n_layers - 1) {
+        p.rows_per_seq = T;
+        p.n_seq = B;
+        p.tiles_per_seq = (T + 127) / 128;
+        p.seq_len = static_cast<const int*>(m->len_dev.p);
+        CUtensorMap tmA = make_tmap_rows3d(m->f_e.p, c.enc_dim_feedforward, c.enc_dim_feedforward, T, B, 128);
+        CUtensorMap tmR = make_tmap_rows3d(m->hB.p, D, D, T, B, 128);
+        L.run("gemm_ffn2_ln", [&] { launch_gemm(tmA, E.w2.tm, tmR, m->tm_hconv_in, p, st); });
+      } else {
+        L.run("gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_e_in, E.w2.tm, m->tm_hB, m->tm_hA, p, st); });
+      }
+    }
+  }
+  if (c.enc_n_layers == 0) throw std::invalid_argument("enc_n_layers must be >= 1");
+  // look-ahead Conv1d as 19 shifted GEMMs + bias + L2 norm -> emb16
+  {
+    GemmParams p{};
+    p.rows_per_seq = T;
+    p.n_seq = B;
+    p.tiles_per_seq = (T + 127) / 128;
+    p.n_tiles = 1;
+    p.k_blocks = D / 64;
+    p.taps = c.conv_kernel;
+    p.tap_shift = -c.conv_padding;
+    p.mode = EPI_L2;
+    p.bias = m->b_conv.f();
+    L.run("gemm_conv_l2", [&] { launch_gemm(m->tm_hconv_in, m->w_conv.tm, none, m->tm_emb_out, p, st); });
+  }
+  // attractor init -> aX [B][T][S][D]
+  {
+    GemmParams p = flat_params(Me, D, D, EPI_CONVERT);
+    p.S = S;
+    p.pe_proj = m->pe_proj.f();
+    L.run("gemm_convert", [&] { launch_gemm(m->tm_emb_in, m->w_cvt.tm, none, m->tm_cvt_out, p, st); });
+  }
+  // decoder layers: aX -> time attention -> aY -> speaker attention -> aZ -> FFN -> aX
+  for (int l = 0; l < c.dec_n_layers; ++l) {
+    DecLayer& Dl = *m->dec[l];
+    {
+      GemmParams p = flat_params(Md, 3 * D, D, EPI_BIAS);
+      p.bias = Dl.bqkv1.f();
+      L.run("gemm_qkv", [&] { launch_gemm(m->tm_aX, Dl.wqkv1.tm, none, m->tm_qkv_d_out, p, st); });
+    }
+    {
+      AttnParams a{B, S, T, c.n_heads, c.mask_delay, 1.f / sqrtf(64.f)};
+      L.run("attn_causal", [&] { launch_causal_attn(m->tm_qkv_d_attn, m->tm_ao_d_attn, a, st); });
+    }
+    {
+      GemmParams p = flat_params(Md, D, D, EPI_LN);
+      p.bias = Dl.bo1.f();
+      p.has_residual = 1;
+      p.ln_g = Dl.g11.f();
+      p.ln_b = Dl.be11.f();
+      p.ln_eps = c.ln_eps;
+      L.run("gemm_out_ln", [&] { launch_gemm(m->tm_ao_d, Dl.wo1.tm, m->tm_aX, m->tm_aY, p, st); });
+    }
+    {
+      GemmParams p = flat_params(Md, 3 * D, D, EPI_BIAS);
+      p.bias = Dl.bqkv2.f();
+      L.run("gemm_qkv", [&] { launch_gemm(m->tm_aY, Dl.wqkv2.tm, none, m->tm_qkv_d_out, p, st); });
+    }
+    L.run("spk_attn", [&] {
+      launch_spk_attn(static_cast<const __half*>(m->qkv_d.p), static_cast<__half*>(m->ao_d.p), static_cast<int>(Me),
+                      S, 1.f / sqrtf(64.f), st);
+    });
+    {
+      GemmParams p = flat_params(Md, D, D, EPI_LN);
+      p.bias = Dl.bo2.f();
+      p.has_residual = 1;
+      p.ln_g = Dl.g21.f();
+      p.ln_b = Dl.be21.f();
+      p.ln_eps = c.ln_eps;
+      L.run("gemm_out_ln", [&] { launch_gemm(m->tm_ao_d, Dl.wo2.tm, m->tm_aY, m->tm_aZ, p, st); });
+    }
+    {
+      GemmParams p = flat_params(Md, c.dec_dim_feedforward, D, EPI_BIAS);
+      p.bias = Dl.b1.f();
+      p.relu = 1;
+      L.run("gemm_ffn1", [&] { launch_gemm(m->tm_aZ, Dl.w1.tm, none, m->tm_f_d_out, p, st); });
+    }
+    {
+      GemmParams p = flat_params(Md, D, c.dec_dim_feedforward, EPI_LN);
+      p.bias = Dl.b2.f();
+      p.has_residual = 1;
+      p.ln_g = Dl.g22.f();
+      p.ln_b = Dl.be22.f();
+      p.ln_eps = c.ln_eps;
+      L.run("gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_d_in, Dl.w2.tm, m->tm_aZ, m->tm_aX, p, st); });
+    }
+  }
+  L.run("head", [&] {
+    launch_head(static_cast<const __half*>(m->emb16.p), static_cast<const __half*>(m->aX.p), static_cast<int>(Me), S,
+                logits, emb_out, att_out, st);
+  });
+  m->launches_last = L.count;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void drain_profile(fseend_fs_model* m) {
+  for (auto& e : m->prof_pending) {
+    float ms = 0.f;
+    cudaEventSynchronize(e.b);
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    auto& acc = m->prof_acc[e.name];
+    acc.first += ms;
+    acc.second += 1;
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  m->prof_pending.clear();
+}
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return FSEEND_OK;
+  } catch (const std::invalid_argument& e) {
+    set_last_error(e.what());
+    return FSEEND_ERR_INVALID;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return FSEEND_ERR_CUDA;
+  }
+}
+
+}  // namespace
+}  // namespace fseend
+
+// =============================================================================================== C ABI
+extern "C" {
+
+int fseend_version(void) { return FSEEND_VERSION; }
+const char* fseend_last_error(void) { return g_last_error.c_str(); }
+
+int fseend_device_ok(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+int fseend_fs_create(const fseend_fs_config* cfg, int n_tensors, const char* const* names, const float* const* data,
+                     const long long* numel, fseend_fs_model** out) {
+  if (!cfg || !out || !names || !data || !numel) {
+    set_last_error("null argument");
+    return FSEEND_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (cfg->n_units != 256 || cfg->n_heads * 64 != cfg->n_units) {
+    set_last_error("only n_units=256 with head_dim 64 is supported");
+    return FSEEND_ERR_INVALID;
+  }
+  if (cfg->enc_dim_feedforward % 256 || cfg->dec_dim_feedforward % 256 || cfg->in_size < 1 || cfg->conv_kernel < 1 ||
+      cfg->enc_n_layers < 1 || cfg->dec_n_layers < 0) {
+    set_last_error("unsupported configuration (feed-forward widths must be multiples of 256)");
+    return FSEEND_ERR_INVALID;
+  }
+  if (!fseend_device_ok()) {
+    set_last_error("fseend_b200 requires an sm_100 (B200) device; no CPU fallback exists");
+    return FSEEND_ERR_NO_DEVICE;
+  }
+  auto* m = new fseend_fs_model();
+  m->cfg = *cfg;
+  int rc = guarded([&] {
+    TensorTable tt;
+    for (int i = 0; i < n_tensors; ++i) tt.t[names[i]] = {data[i], numel[i]};
+    build_model(m, tt);
+  });
+  if (rc != FSEEND_OK) {
+    delete m;
+    // a missing tensor is reported distinctly
+    if (rc == FSEEND_ERR_INVALID && g_last_error.find("state_dict") != std::string::npos) rc = FSEEND_ERR_MISSING;
+    return rc;
+  }
+  *out = m;
+  return FSEEND_OK;
+}
+
+void fseend_fs_destroy(fseend_fs_model* m) {
+  if (!m) return;
+  drain_profile(m);
+  delete m;
+}
+
+int fseend_fs_forward(fseend_fs_model* m, const float* x_packed_dev, const int* ilens_host, int B, int max_nspks,
+                      float* logits_dev, float* emb_dev, float* att_dev, void* stream) {
+  if (!m || !x_packed_dev || !ilens_host || !logits_dev) {
+    set_last_error("null argument");
+    return FSEEND_ERR_INVALID;
+  }
+  return guarded([&] {
+    forward_impl(m, x_packed_dev, ilens_host, B, max_nspks, logits_dev, emb_dev, att_dev,
+                 static_cast<cudaStream_t>(stream));
+  });
+}
+
+int fseend_fs_forward_host(fseend_fs_model* m, const float* x_packed_host, const int* ilens_host, int B,
+                           int max_nspks, float* logits_host, float* emb_host, float* att_host) {
+  if (!m || !x_packed_host || !ilens_host || !logits_host) {
+    set_last_error("null argument");
+    return FSEEND_ERR_INVALID;
+  }
+  return guarded([&] {
+    long long total = 0;
+    int T = 0;
+    for (int b = 0; b < B; ++b) {
+      total += ilens_host[b];
+      T = ilens_host[b] > T ? ilens_host[b] : T;
+    }
+    const size_t xin = static_cast<size_t>(total) * m->cfg.in_size * sizeof(float);
+    const size_t n_log = 1ull * B * T * max_nspks;
+    const size_t n_emb = emb_host ? 1ull * B * T * m->cfg.n_units : 0;
+    const size_t n_att = att_host ? 1ull * B * T * max_nspks * m->cfg.n_units : 0;
+    // staging buffers live next to the plan; (re)allocated on growth (make_plan frees them on a shape change)
+    make_plan(m, B, T, max_nspks);
+    if (m->x_stage.bytes < xin) m->x_stage.alloc(xin);
+    const size_t out_bytes = (n_log + n_emb + n_att) * sizeof(float);
+    if (m->logits_stage.bytes < out_bytes) m->logits_stage.alloc(out_bytes);
+    cudaStream_t st = nullptr;
+    CUDA_CHECK(cudaMemcpyAsync(m->x_stage.p, x_packed_host, xin, cudaMemcpyHostToDevice, st));
+    float* dl = static_cast<float*>(m->logits_stage.p);
+    float* de = emb_host ? dl + n_log : nullptr;
+    float* da = att_host ? dl + n_log + n_emb : nullptr;
+    forward_impl(m, static_cast<const float*>(m->x_stage.p), ilens_host, B, max_nspks, dl, de, da, st);
+    CUDA_CHECK(cudaMemcpyAsync(logits_host, dl, n_log * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (emb_host) CUDA_CHECK(cudaMemcpyAsync(emb_host, de, n_emb * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (att_host) CUDA_CHECK(cudaMemcpyAsync(att_host, da, n_att * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int fseend_fs_set_profiling(fseend_fs_model* m, int on) {
+  if (!m) return FSEEND_ERR_INVALID;
+  drain_profile(m);
+  if (on && !m->profiling) m->prof_acc.clear();
+  m->profiling = on != 0;
+  return FSEEND_OK;
+}
+
+int fseend_fs_get_profile(fseend_fs_model* m, int max_entries, char (*names)[32], float* total_ms, int* launches) {
+  if (!m) return FSEEND_ERR_INVALID;
+  drain_profile(m);
+  int i = 0;
+  for (auto& kv : m->prof_acc) {
+    if (i >= max_entries) break;
+    strncpy(names[i], kv.first.c_str(), 31);
+    names[i][31] = 0;
+    total_ms[i] = static_cast<float>(kv.second.first);
+    launches[i] = kv.second.second;
+    ++i;
+  }
+  return i;
+}
+
+int fseend_fs_launches_per_forward(const fseend_fs_model* m) { return m ? m->launches_last : 0; }
+size_t fseend_fs_workspace_bytes(const fseend_fs_model* m) { return m ? m->ws_bytes : 0; }
+
+// ---------------------------------------------------------------------------- single-kernel entry points
+int fseend_op_gemm(const void* a_f16, int rows_per_seq, int n_seq, int K, const void* w_f16, int N, int taps,
+                   int tap_shift, int mode, int relu, const float* bias, const void* residual_f16, const float* ln_g,
+                   const float* ln_b, float ln_eps, const float* pe_proj, int S, const int* seq_len_dev,
+                   void* out_f16, void* stream) {
+  return guarded([&] {
+    if (K % 64 || N % 256 || (mode != EPI_BIAS && N != 256)) throw std::invalid_argument("K%64, N%256 required");
+    if (!fseend_device_ok()) throw std::invalid_argument("sm_100 device required");
+    GemmParams p{};
+    p.rows_per_seq = rows_per_seq;
+    p.n_seq = n_seq;
+    p.tiles_per_seq = (rows_per_seq + 127) / 128;
+    p.n_tiles = N / 256;
+    p.k_blocks = K / 64;
+    p.taps = taps;
+    p.tap_shift = tap_shift;
+    p.mode = mode;
+    p.relu = relu;
+    p.has_residual = residual_f16 != nullptr;
+    p.S = S;
+    p.ln_eps = ln_eps;
+    p.bias = bias;
+    p.ln_g = ln_g;
+    p.ln_b = ln_b;
+    p.pe_proj = pe_proj;
+    p.seq_len = seq_len_dev;
+    CUtensorMap tmA = make_tmap_rows3d(a_f16, K, K, rows_per_seq, n_seq, 128);
+    uint64_t wd[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(taps) * N};
+    uint64_t ws[1] = {static_cast<uint64_t>(K)};
+    uint32_t wb[2] = {64, 256};
+    CUtensorMap tmB = make_tmap_f16(w_f16, 2, wd, ws, wb);
+    CUtensorMap tmO;
+    if (mode == EPI_CONVERT) {
+      uint64_t dims[3] = {256, static_cast<uint64_t>(S), static_cast<uint64_t>(rows_per_seq) * n_seq};
+      uint64_t str[2] = {256, 256ull * S};
+      uint32_t box[3] = {64, 1, 128};
+      tmO = make_tmap_f16(out_f16, 3, dims, str, box);
+    } else {
+      tmO = make_tmap_rows3d(out_f16, N, N, rows_per_seq, n_seq, 128);
+    }
+    CUtensorMap tmR = residual_f16 ? make_tmap_rows3d(residual_f16, N, N, rows_per_seq, n_seq, 128) : tmO;
+    launch_gemm(tmA, tmB, tmR, tmO, p, static_cast<cudaStream_t>(stream));
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int fseend_op_causal_attn(const void* qkv_f16, int B, int T, int S, int H, int mask_delay, float scale, void* out_f16,
+                          void* stream) {
+  return guarded([&] {
+    if (H != 4) throw std::invalid_argument("H must be 4 (4 x 64 = 256)");
+    if (!fseend_device_ok()) throw std::invalid_argument("sm_100 device required");
+    uint64_t dq[4] = {768, static_cast<uint64_t>(S), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+    uint64_t sq[3] = {768, 768ull * S, 768ull * S * T};
+    uint64_t d_o[4] = {256, static_cast<uint64_t>(S), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+    uint64_t so[3] = {256, 256ull * S, 256ull * S * T};
+    uint32_t box[4] = {64, 1, 128, 1};
+    CUtensorMap tq = make_tmap_f16(qkv_f16, 4, dq, sq, box);
+    CUtensorMap to = make_tmap_f16(out_f16, 4, d_o, so, box);
+    AttnParams a{B, S, T, H, mask_delay, scale};
+    launch_causal_attn(tq, to, a, static_cast<cudaStream_t>(stream));
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int fseend_op_spk_attn(const void* qkv_f16, int n_frames, int S, float scale, void* out_f16, void* stream) {
+  return guarded([&] {
+    if (launch_spk_attn(static_cast<const __half*>(qkv_f16), static_cast<__half*>(out_f16), n_frames, S, scale,
+                        static_cast<cudaStream_t>(stream)) != 0)
+      throw std::invalid_argument("S must be in [1,16]");
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int fseend_op_head(const void* emb_f16, const void* att_f16, int n_frames, int S, float* logits, float* emb_f32,
+                   float* att_f32, void* stream) {
+  return guarded([&] {
+    launch_head(static_cast<const __half*>(emb_f16), static_cast<const __half*>(att_f16), n_frames, S, logits, emb_f32,
+                att_f32, static_cast<cudaStream_t>(stream));
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int fseend_op_prep_input(const float* x_packed, const int* cu_seqlens_dev, int B, int Tmax, int Din, int Kpad,
+                         const float* scale, const float* shift, void* out_f16, void* stream) {
+  return guarded([&] {
+    if (Kpad % 2 || Kpad < Din) throw std::invalid_argument("Kpad must be even and >= Din");
+    launch_prep_input(x_packed, cu_seqlens_dev, B, Tmax, Din, Kpad, scale, shift, static_cast<__half*>(out_f16),
+                      static_cast<cudaStream_t>(stream));
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+}  // extern "C"

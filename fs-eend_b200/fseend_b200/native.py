@@ -1,0 +1,247 @@
+"""ctypes binding of include/fseend_b200.h.  torch is used only for device memory and streams.
+
+There is NO CPU fallback: ``lib()`` raises if the shared library has not been built, and model creation
+raises if the current device is not an sm_100 GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .build import LIB_PATH
+
+_lib = None
+
+
+class FseendError(RuntimeError):
+    pass
+
+
+class FsConfig(C.Structure):
+    _fields_ = [
+        ("in_size", C.c_int), ("n_units", C.c_int), ("n_heads", C.c_int), ("enc_n_layers", C.c_int),
+        ("dec_n_layers", C.c_int), ("enc_dim_feedforward", C.c_int), ("dec_dim_feedforward", C.c_int),
+        ("conv_kernel", C.c_int), ("conv_padding", C.c_int), ("mask_delay", C.c_int), ("has_mask", C.c_int),
+        ("bn_eps", C.c_float), ("ln_eps", C.c_float),
+    ]
+
+
+# every symbol include/fseend_b200.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "fseend_version", "fseend_last_error", "fseend_device_ok", "fseend_fs_create", "fseend_fs_destroy",
+    "fseend_fs_forward", "fseend_fs_forward_host", "fseend_fs_set_profiling", "fseend_fs_get_profile",
+    "fseend_fs_launches_per_forward", "fseend_fs_workspace_bytes", "fseend_op_gemm", "fseend_op_causal_attn",
+    "fseend_op_spk_attn", "fseend_op_head", "fseend_op_prep_input",
+]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FseendError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  fseend_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, ip, fp = C.c_void_p, C.c_int, C.c_float
+    L.fseend_version.restype = ip
+    L.fseend_last_error.restype = C.c_char_p
+    L.fseend_device_ok.restype = ip
+    L.fseend_fs_create.restype = ip
+    L.fseend_fs_create.argtypes = [C.POINTER(FsConfig), ip, C.POINTER(C.c_char_p), C.POINTER(vp),
+                                   C.POINTER(C.c_longlong), C.POINTER(vp)]
+    L.fseend_fs_destroy.restype = None
+    L.fseend_fs_destroy.argtypes = [vp]
+    L.fseend_fs_forward.restype = ip
+    L.fseend_fs_forward.argtypes = [vp, vp, C.POINTER(ip), ip, ip, vp, vp, vp, vp]
+    L.fseend_fs_forward_host.restype = ip
+    L.fseend_fs_forward_host.argtypes = [vp, vp, C.POINTER(ip), ip, ip, vp, vp, vp]
+    L.fseend_fs_set_profiling.restype = ip
+    L.fseend_fs_set_profiling.argtypes = [vp, ip]
+    L.fseend_fs_get_profile.restype = ip
+    L.fseend_fs_get_profile.argtypes = [vp, ip, vp, C.POINTER(fp), C.POINTER(ip)]
+    L.fseend_fs_launches_per_forward.restype = ip
+    L.fseend_fs_launches_per_forward.argtypes = [vp]
+    L.fseend_fs_workspace_bytes.restype = C.c_size_t
+    L.fseend_fs_workspace_bytes.argtypes = [vp]
+    L.fseend_op_gemm.restype = ip
+    L.fseend_op_gemm.argtypes = [vp, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, vp, vp, vp, fp, vp, ip, vp, vp, vp]
+    L.fseend_op_causal_attn.restype = ip
+    L.fseend_op_causal_attn.argtypes = [vp, ip, ip, ip, ip, ip, fp, vp, vp]
+    L.fseend_op_spk_attn.restype = ip
+    L.fseend_op_spk_attn.argtypes = [vp, ip, ip, fp, vp, vp]
+    L.fseend_op_head.restype = ip
+    L.fseend_op_head.argtypes = [vp, vp, ip, ip, vp, vp, vp, vp]
+    L.fseend_op_prep_input.restype = ip
+    L.fseend_op_prep_input.argtypes = [vp, vp, ip, ip, ip, ip, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise FseendError(f"fseend error {rc}: {lib().fseend_last_error().decode()}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts: torch.Tensor):
+    for t in ts:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise FseendError("fseend_b200 kernels take contiguous CUDA tensors (no CPU fallback)")
+
+
+class FsModel:
+    """Owns a native fseend_fs_model built from a reference-named state_dict."""
+
+    def __init__(self, cfg: Dict[str, int], state_dict: Dict[str, torch.Tensor]):
+        L = lib()
+        if not torch.cuda.is_available():
+            raise FseendError("fseend_b200 requires a CUDA (sm_100) device; there is no CPU fallback")
+        c = FsConfig(
+            in_size=cfg["in_size"], n_units=cfg["n_units"], n_heads=cfg["n_heads"],
+            enc_n_layers=cfg["enc_n_layers"], dec_n_layers=cfg["dec_n_layers"],
+            enc_dim_feedforward=cfg.get("enc_dim_feedforward", 2048),
+            dec_dim_feedforward=cfg["dec_dim_feedforward"], conv_kernel=cfg.get("conv_kernel", 19),
+            conv_padding=cfg.get("conv_padding", 9), mask_delay=cfg.get("mask_delay", 0), has_mask=int(cfg.get("has_mask", True)),
+            bn_eps=cfg.get("bn_eps", 1e-5), ln_eps=cfg.get("ln_eps", 1e-5))
+        self.cfg = dict(cfg)
+        names, ptrs, numels, keep = [], [], [], []
+        for k, v in state_dict.items():
+            if not torch.is_floating_point(v):
+                continue
+            t = v.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            keep.append(t)
+            names.append(k.encode())
+            ptrs.append(t.data_ptr())
+            numels.append(t.numel())
+        n = len(names)
+        handle = C.c_void_p()
+        _check(L.fseend_fs_create(C.byref(c), n, (C.c_char_p * n)(*names), (C.c_void_p * n)(*ptrs),
+                                  (C.c_longlong * n)(*numels), C.byref(handle)))
+        self._h = handle
+        self._L = L
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.fseend_fs_destroy(h)
+
+    def forward(self, x_packed: torch.Tensor, ilens: Sequence[int], max_nspks: int, want_emb: bool = False,
+                want_att: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """x_packed: CUDA fp32 [sum(ilens), in_size].  Returns padded (logits [B,T,S], emb [B,T,D], att [B,T,S,D])."""
+        _require_cuda(x_packed)
+        if x_packed.dtype != torch.float32:
+            raise FseendError("x must be float32")
+        B, T = len(ilens), int(max(ilens))
+        if x_packed.shape[0] != int(sum(ilens)) or x_packed.shape[1] != self.cfg["in_size"]:
+            raise FseendError("x_packed shape does not match ilens / in_size")
+        D = self.cfg["n_units"]
+        dev = x_packed.device
+        logits = torch.empty(B, T, max_nspks, device=dev, dtype=torch.float32)
+        emb = torch.empty(B, T, D, device=dev, dtype=torch.float32) if want_emb else None
+        att = torch.empty(B, T, max_nspks, D, device=dev, dtype=torch.float32) if want_att else None
+        il = (C.c_int * B)(*[int(i) for i in ilens])
+        _check(self._L.fseend_fs_forward(self._h, _ptr(x_packed), il, B, max_nspks, _ptr(logits), _ptr(emb), _ptr(att),
+                                         _stream()))
+        return logits, emb, att
+
+    def forward_host(self, x_packed: torch.Tensor, ilens: Sequence[int], max_nspks: int, want_emb: bool = False,
+                     want_att: bool = False, out: Optional[torch.Tensor] = None):
+        """Host-buffer entry point (H2D + forward + D2H inside the call).  x_packed: CPU fp32 (pinned or not)."""
+        if x_packed.is_cuda or x_packed.dtype != torch.float32 or not x_packed.is_contiguous():
+            raise FseendError("forward_host takes a contiguous CPU float32 tensor")
+        B, T = len(ilens), int(max(ilens))
+        D = self.cfg["n_units"]
+        logits = out if out is not None else torch.empty(B, T, max_nspks, dtype=torch.float32)
+        emb = torch.empty(B, T, D, dtype=torch.float32) if want_emb else None
+        att = torch.empty(B, T, max_nspks, D, dtype=torch.float32) if want_att else None
+        il = (C.c_int * B)(*[int(i) for i in ilens])
+        _check(self._L.fseend_fs_forward_host(self._h, _ptr(x_packed), il, B, max_nspks, _ptr(logits), _ptr(emb),
+                                              _ptr(att)))
+        return logits, emb, att
+
+    def set_profiling(self, on: bool):
+        _check(self._L.fseend_fs_set_profiling(self._h, 1 if on else 0))
+
+    def get_profile(self) -> Dict[str, Tuple[float, int]]:
+        n = 64
+        names = ((C.c_char * 32) * n)()
+        ms = (C.c_float * n)()
+        cnt = (C.c_int * n)()
+        k = self._L.fseend_fs_get_profile(self._h, n, C.cast(names, C.c_void_p), ms, cnt)
+        return {names[i].value.decode(): (float(ms[i]), int(cnt[i])) for i in range(k)}
+
+    @property
+    def launches_per_forward(self) -> int:
+        return int(self._L.fseend_fs_launches_per_forward(self._h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self._L.fseend_fs_workspace_bytes(self._h))
+
+
+# ------------------------------------------------------------------------------ single-kernel wrappers
+EPI_BIAS, EPI_LN, EPI_L2, EPI_CONVERT = 0, 1, 2, 3
+
+
+def op_gemm(a: torch.Tensor, w: torch.Tensor, mode: int, *, n_seq: int = 1, taps: int = 1, tap_shift: int = 0,
+            relu: bool = False, bias=None, residual=None, ln_g=None, ln_b=None, ln_eps: float = 1e-5, pe_proj=None,
+            S: int = 0, seq_len=None) -> torch.Tensor:
+    """a: fp16 [n_seq*rows_per_seq, K]; w: fp16 [taps*N, K]."""
+    _require_cuda(a, w, bias, residual, ln_g, ln_b, pe_proj, seq_len)
+    rows, K = a.shape
+    N = w.shape[0] // taps
+    rps = rows // n_seq
+    out = torch.empty((rows, S, N) if mode == EPI_CONVERT else (rows, N), device=a.device, dtype=torch.float16)
+    _check(lib().fseend_op_gemm(_ptr(a), rps, n_seq, K, _ptr(w), N, taps, tap_shift, mode, int(relu), _ptr(bias),
+                                _ptr(residual), _ptr(ln_g), _ptr(ln_b), ln_eps, _ptr(pe_proj), S, _ptr(seq_len),
+                                _ptr(out), _stream()))
+    return out
+
+
+def op_causal_attn(qkv: torch.Tensor, mask_delay: int = 0, scale: float = 0.125) -> torch.Tensor:
+    """qkv: fp16 [B, T, S, 768] -> [B, T, S, 256]."""
+    _require_cuda(qkv)
+    B, T, S, _ = qkv.shape
+    out = torch.empty(B, T, S, 256, device=qkv.device, dtype=torch.float16)
+    _check(lib().fseend_op_causal_attn(_ptr(qkv), B, T, S, 4, mask_delay, scale, _ptr(out), _stream()))
+    return out
+
+
+def op_spk_attn(qkv: torch.Tensor, scale: float = 0.125) -> torch.Tensor:
+    """qkv: fp16 [frames, S, 768] -> [frames, S, 256]."""
+    _require_cuda(qkv)
+    F, S, _ = qkv.shape
+    out = torch.empty(F, S, 256, device=qkv.device, dtype=torch.float16)
+    _check(lib().fseend_op_spk_attn(_ptr(qkv), F, S, scale, _ptr(out), _stream()))
+    return out
+
+
+def op_head(emb: torch.Tensor, att: torch.Tensor, want_f32: bool = False):
+    _require_cuda(emb, att)
+    F, S, _ = att.shape
+    logits = torch.empty(F, S, device=emb.device, dtype=torch.float32)
+    e32 = torch.empty(F, 256, device=emb.device, dtype=torch.float32) if want_f32 else None
+    a32 = torch.empty(F, S, 256, device=emb.device, dtype=torch.float32) if want_f32 else None
+    _check(lib().fseend_op_head(_ptr(emb), _ptr(att), F, S, _ptr(logits), _ptr(e32), _ptr(a32), _stream()))
+    return logits, e32, a32
+
+
+def op_prep_input(x_packed: torch.Tensor, cu_seqlens: torch.Tensor, B: int, Tmax: int, Kpad: int, scale: torch.Tensor,
+                  shift: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x_packed, cu_seqlens, scale, shift)
+    out = torch.empty(B, Tmax, Kpad, device=x_packed.device, dtype=torch.float16)
+    _check(lib().fseend_op_prep_input(_ptr(x_packed), _ptr(cu_seqlens), B, Tmax, x_packed.shape[1], Kpad, _ptr(scale),
+                                      _ptr(shift), _ptr(out), _stream()))
+    return out

@@ -1,0 +1,110 @@
+/* fseend_b200 — C ABI of the B200-native FS-EEND hot path (encoder + attractor decoder forward).
+ *
+ * The reference (Audio-WestlakeU/FS-EEND) has no FFI: its hot path is the Python method
+ *   OnlineTransformerDADiarization.test(src, ilens, max_nspks)
+ *   (FS-EEND/nnet/model/onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm.py:67-84)
+ * and .forward() (same file :32-65).  This header is the boundary a maintainer would bind with ctypes
+ * (see INTEGRATION.md); `fs-eend_b200/nnet/` is the Python mirror of the reference's nnet/ API on top of it.
+ *
+ * Conventions: plain pointers and sizes only; all "dev" pointers are CUDA device pointers owned by the
+ * caller; every function returns 0 on success or a negative error code and records a message retrievable
+ * with fseend_last_error(); no hidden host synchronisation in the *_dev entry points; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).  The library requires an sm_100a device and fails
+ * loudly otherwise — there is no CPU fallback.
+ */
+#ifndef FSEEND_B200_H_
+#define FSEEND_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSEEND_VERSION 100
+
+enum {
+  FSEEND_OK = 0,
+  FSEEND_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+  FSEEND_ERR_CUDA = -2,         /* CUDA runtime / driver error      */
+  FSEEND_ERR_MISSING = -3,      /* a required state_dict tensor is missing or has the wrong size */
+  FSEEND_ERR_NO_DEVICE = -4     /* no sm_100 device                 */
+};
+
+/* Constructor kwargs of OnlineTransformerDADiarization (reference model file :11). */
+typedef struct fseend_fs_config {
+  int in_size;              /* 345 = (2*7+1)*23 spliced log-mel                          */
+  int n_units;              /* 256 (only supported width: one LayerNorm row per MMA tile) */
+  int n_heads;              /* n_units / n_heads must be 64                               */
+  int enc_n_layers;
+  int dec_n_layers;
+  int enc_dim_feedforward;  /* 2048: nn.TransformerEncoderLayer default (reference :147)  */
+  int dec_dim_feedforward;
+  int conv_kernel;          /* 2*conv_delay+1 = 19                                        */
+  int conv_padding;         /* 9 (hard-coded in the reference, :30)                       */
+  int mask_delay;
+  int has_mask;             /* 0: encoder attends to all frames (decoder is always causal, reference :116) */
+  float bn_eps;             /* 1e-5 */
+  float ln_eps;             /* 1e-5 */
+} fseend_fs_config;
+
+typedef struct fseend_fs_model fseend_fs_model;
+
+int fseend_version(void);
+const char* fseend_last_error(void);
+/* 1 if the current CUDA device is compute capability 10.x, else 0. */
+int fseend_device_ok(void);
+
+/* Build a model from a reference state_dict: `names[i]` are the reference's own keys
+ * ("enc.bn.weight", "enc.transformer_encoder.layers.0.self_attn.in_proj_weight", ..., "cnn.weight",
+ * "dec.convert.weight", "dec.attractor_decoder.layers.1.norm22.bias"), `data[i]` HOST fp32 pointers,
+ * `numel[i]` element counts.  Weights are converted once (fp16 operands, BatchNorm folded to a
+ * per-channel affine, conv taps split, attractor-init weight split) and uploaded. */
+int fseend_fs_create(const fseend_fs_config* cfg, int n_tensors, const char* const* names,
+                     const float* const* data, const long long* numel, fseend_fs_model** out);
+void fseend_fs_destroy(fseend_fs_model* m);
+
+/* test(): x_packed = concatenation of the B feature matrices (sum(ilens) x in_size, fp32, device),
+ * ilens on the HOST.  Outputs are padded to Tmax = max(ilens):
+ *   logits [B][Tmax][max_nspks] fp32   (rows t >= ilens[b] are unspecified, as in the reference's padded tensors)
+ *   emb    [B][Tmax][n_units]   fp32   or NULL
+ *   att    [B][Tmax][max_nspks][n_units] fp32 (L2-normalised attractors) or NULL */
+int fseend_fs_forward(fseend_fs_model* m, const float* x_packed_dev, const int* ilens_host, int B, int max_nspks,
+                      float* logits_dev, float* emb_dev, float* att_dev, void* stream);
+
+/* Same with HOST buffers (pinned or pageable): H2D copy, forward, D2H copy, stream synchronise. */
+int fseend_fs_forward_host(fseend_fs_model* m, const float* x_packed_host, const int* ilens_host, int B,
+                           int max_nspks, float* logits_host, float* emb_host, float* att_host);
+
+/* Per-kernel timing of the next forward calls (CUDA events around every launch; off by default).
+ * get_profile returns the number of distinct kernels; names[i] (<= 31 chars), total ms and launch count
+ * accumulated since profiling was switched on. */
+int fseend_fs_set_profiling(fseend_fs_model* m, int on);
+int fseend_fs_get_profile(fseend_fs_model* m, int max_entries, char (*names)[32], float* total_ms, int* launches);
+/* Number of kernel launches one forward issues for (B, Tmax, max_nspks). */
+int fseend_fs_launches_per_forward(const fseend_fs_model* m);
+/* Bytes of device workspace currently held by the model's (B, Tmax, S) plan. */
+size_t fseend_fs_workspace_bytes(const fseend_fs_model* m);
+
+/* ---- single-kernel entry points (used by the parity tests; all pointers are device pointers) ---------- */
+
+/* OUT = epilogue(A * W^T): A fp16 [n_seq][rows_per_seq][K], W fp16 [taps*N][K], fp32 accumulate.
+ * mode 0: +bias (+ReLU), N multiple of 256 | 1: LayerNorm(+bias +residual) | 2: L2-normalise(+bias)
+ * | 3: attractor init, out[row][s][:] = acc + pe_proj[s][:].   taps>1: row-shifted accumulation (Conv1d). */
+int fseend_op_gemm(const void* a_f16, int rows_per_seq, int n_seq, int K, const void* w_f16, int N, int taps,
+                   int tap_shift, int mode, int relu, const float* bias, const void* residual_f16,
+                   const float* ln_g, const float* ln_b, float ln_eps, const float* pe_proj, int S,
+                   const int* seq_len_dev, void* out_f16, void* stream);
+/* qkv fp16 [B][T][S][768] -> out fp16 [B][T][S][256]; key j visible to query i iff j <= i + mask_delay. */
+int fseend_op_causal_attn(const void* qkv_f16, int B, int T, int S, int H, int mask_delay, float scale,
+                          void* out_f16, void* stream);
+int fseend_op_spk_attn(const void* qkv_f16, int n_frames, int S, float scale, void* out_f16, void* stream);
+int fseend_op_head(const void* emb_f16, const void* att_f16, int n_frames, int S, float* logits, float* emb_f32,
+                   float* att_f32, void* stream);
+int fseend_op_prep_input(const float* x_packed, const int* cu_seqlens_dev, int B, int Tmax, int Din, int Kpad,
+                         const float* scale, const float* shift, void* out_f16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSEEND_B200_H_ */

@@ -1,0 +1,74 @@
+"""Host-side logic that needs no GPU: the nnet mirror's state_dict ABI, the C-ABI library's exports, and the
+'no CPU fallback' contract."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def make_model(**kw):
+    from nnet.model.onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import OnlineTransformerDADiarization
+    args = dict(n_speakers=4, in_size=345, n_units=256, n_heads=4, enc_n_layers=4, dec_n_layers=2, dropout=0.1,
+                has_mask=True, max_seqlen=500, dec_dim_feedforward=2048)
+    args.update(kw)
+    return OnlineTransformerDADiarization(**args)
+
+
+def test_state_dict_abi_matches_reference():
+    """Keys, shapes and dtypes equal those of the real reference model (dumped by tests/golden/make_golden.py)."""
+    want = {}
+    with open(os.path.join(ROOT, "tests", "golden", "fs_state_dict_abi.txt")) as f:
+        for line in f:
+            k, shape, dt = re.match(r"(\S+) (\(.*\)) (\S+)", line.strip()).groups()
+            want[k] = (eval(shape), dt)
+    sd = make_model().state_dict()
+    got = {k: (tuple(v.shape), str(v.dtype).replace("torch.", "")) for k, v in sd.items()}
+    assert got == want
+    assert sum(p.numel() for p in make_model().parameters()) == 9_974_450
+
+
+def test_same_seed_same_init_as_reference_construction_order():
+    """Two constructions under one seed agree, and the oracle's random_state_dict loads strictly."""
+    from oracle import fs_eend_oracle as O
+    torch.manual_seed(0)
+    a = make_model().state_dict()
+    torch.manual_seed(0)
+    b = make_model().state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    make_model().load_state_dict(O.random_state_dict(0), strict=True)
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from fseend_b200 import native
+    hdr = open(os.path.join(ROOT, "include", "fseend_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(fseend_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(native.EXPORTS)
+    L = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.fseend_version() == 100
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a GPU the product path must fail loudly (never route through the oracle or torch CPU ops)."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fseend_b200.native import FseendError
+    from oracle import fs_eend_oracle as O
+    m = make_model().eval()
+    src, lens = O.synthetic_features(1, 32)
+    with pytest.raises((RuntimeError, FseendError)):
+        m.test(src, lens, 4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "fs-eend_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, fn), encoding="utf-8").read()
+                assert "oracle" not in txt.replace("oracle/", "").lower() or fn == "README.md", (dp, fn)

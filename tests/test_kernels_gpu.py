@@ -1,0 +1,156 @@
+"""Per-kernel parity on a B200: each sm_100a kernel (called through the C ABI) against plain torch fp32
+arithmetic on the SAME fp16-rounded operands.  Tolerances: outputs are stored as fp16 (rel. 2^-11), fp32
+accumulation order differs -> max-abs 5e-3 on O(1) values; logic errors are O(1)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def ln_ref(x, g, b, eps=1e-5):
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), g, b, eps)
+
+
+@pytest.fixture(scope="module")
+def N():
+    from fseend_b200 import native
+    native.lib()
+    assert torch.cuda.is_available() and native.lib().fseend_device_ok() == 1
+    return native
+
+
+def test_gemm_bias_relu_ragged_rows(N):
+    a = rnd(300, 256, seed=1).half()
+    w = rnd(768, 256, scale=1 / 16, seed=2).half()
+    bias = rnd(768, seed=3)
+    out = N.op_gemm(a, w, N.EPI_BIAS, bias=bias)
+    ref = a.float() @ w.float().T + bias
+    assert (out.float() - ref).abs().max().item() < 5e-3
+    out = N.op_gemm(a, w, N.EPI_BIAS, bias=bias, relu=True)
+    assert (out.float() - ref.relu()).abs().max().item() < 5e-3
+
+
+def test_gemm_k384_layernorm(N):
+    a = rnd(1000, 384, seed=4).half()
+    w = rnd(256, 384, scale=1 / 20, seed=5).half()
+    bias, g, b = rnd(256, seed=6), 1 + 0.3 * rnd(256, seed=7), 0.1 * rnd(256, seed=8)
+    out = N.op_gemm(a, w, N.EPI_LN, bias=bias, ln_g=g, ln_b=b)
+    ref = ln_ref(a.float() @ w.float().T + bias, g, b)
+    assert (out.float() - ref).abs().max().item() < 5e-3
+
+
+def test_gemm_k2048_residual_layernorm_large_mean(N):
+    a = rnd(517, 2048, seed=9).half()
+    w = rnd(256, 2048, scale=1 / 45, seed=10).half()
+    res = (rnd(517, 256, seed=11) + 3.0).half()          # large mean: exercises the robust variance merge
+    bias, g, b = rnd(256, seed=12), 1 + 0.3 * rnd(256, seed=13), 0.1 * rnd(256, seed=14)
+    out = N.op_gemm(a, w, N.EPI_LN, bias=bias, residual=res, ln_g=g, ln_b=b)
+    ref = ln_ref(a.float() @ w.float().T + bias + res.float(), g, b)
+    assert (out.float() - ref).abs().max().item() < 5e-3
+
+
+def test_gemm_layernorm_zero_rows_beyond_len(N):
+    n_seq, T = 3, 150
+    a = rnd(n_seq * T, 256, seed=15).half()
+    w = rnd(256, 256, scale=1 / 16, seed=16).half()
+    g, b = 1 + 0.3 * rnd(256, seed=17), 0.1 * rnd(256, seed=18)
+    lens = torch.tensor([150, 77, 1], dtype=torch.int32, device=DEV)
+    out = N.op_gemm(a, w, N.EPI_LN, n_seq=n_seq, ln_g=g, ln_b=b, seq_len=lens).view(n_seq, T, 256)
+    ref = ln_ref(a.float() @ w.float().T, g, b).view(n_seq, T, 256)
+    for i, l in enumerate(lens.tolist()):
+        assert (out[i, :l].float() - ref[i, :l]).abs().max().item() < 5e-3
+        assert out[i, l:].abs().max().item() == 0 if l < T else True
+
+
+def test_gemm_conv_taps_l2(N):
+    """Conv1d(256,256,19,padding=9) + L2 norm as 19 shifted GEMMs with per-sequence zero fill."""
+    n_seq, T, K = 3, 200, 19
+    x = rnd(n_seq, T, 256, seed=19).half()
+    wc = rnd(256, 256, K, scale=1 / 70, seed=20)                    # (out, in, k)
+    bias = rnd(256, seed=21) * 0.1
+    w_taps = wc.permute(2, 0, 1).contiguous().half()                 # [k][out][in]
+    out = N.op_gemm(x.view(-1, 256), w_taps.view(K * 256, 256), N.EPI_L2, n_seq=n_seq, taps=K, tap_shift=-9,
+                    bias=bias).view(n_seq, T, 256)
+    y = torch.nn.functional.conv1d(x.float().transpose(1, 2), w_taps.float().permute(1, 2, 0), bias, padding=9)
+    y = y.transpose(1, 2)
+    ref = y / y.norm(dim=-1, keepdim=True)
+    assert (out.float() - ref).abs().max().item() < 2e-3
+
+
+def test_gemm_convert_broadcast(N):
+    S = 6
+    a = rnd(333, 256, seed=22).half()
+    w = rnd(256, 256, scale=1 / 16, seed=23).half()
+    pe = rnd(16, 256, seed=24)
+    out = N.op_gemm(a, w, N.EPI_CONVERT, pe_proj=pe, S=S)
+    ref = (a.float() @ w.float().T)[:, None, :] + pe[None, :S, :]
+    assert out.shape == (333, S, 256)
+    assert (out.float() - ref).abs().max().item() < 5e-3
+
+
+def attn_ref(qkv, mask_delay, scale=0.125):
+    B, T, S, _ = qkv.shape
+    x = qkv.float().permute(0, 2, 1, 3).reshape(B * S, T, 3, 4, 64)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) * scale
+    i = torch.arange(T, device=qkv.device)
+    s = s.masked_fill(i[None, :] > i[:, None] + mask_delay, float("-inf"))
+    o = torch.softmax(s, dim=-1) @ v                                   # (B*S, H, T, 64)
+    return o.transpose(1, 2).reshape(B, S, T, 256).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("B,T,S,md", [(2, 300, 1, 0), (1, 500, 3, 0), (2, 130, 2, 2), (1, 64, 1, 0), (1, 257, 1, 300)])
+def test_causal_attention(N, B, T, S, md):
+    qkv = rnd(B, T, S, 768, seed=25 + T).half()
+    out = N.op_causal_attn(qkv, mask_delay=md)
+    ref = attn_ref(qkv, md)
+    assert (out.float() - ref).abs().max().item() < 4e-3
+
+
+@pytest.mark.parametrize("S", [4, 6, 10, 16])
+def test_speaker_attention(N, S):
+    F = 777
+    qkv = rnd(F, S, 768, seed=40 + S).half()
+    out = N.op_spk_attn(qkv)
+    x = qkv.float().view(F, S, 3, 4, 64)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    o = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v
+    ref = o.transpose(1, 2).reshape(F, S, 256)
+    assert (out.float() - ref).abs().max().item() < 3e-3
+
+
+def test_head(N):
+    F, S = 1001, 6
+    emb = torch.nn.functional.normalize(rnd(F, 256, seed=50), dim=-1).half()
+    att = rnd(F, S, 256, seed=51).half()
+    logits, e32, a32 = N.op_head(emb, att, want_f32=True)
+    an = att.float() / att.float().norm(dim=-1, keepdim=True)
+    ref = (emb.float()[:, None, :] * an).sum(-1)
+    assert (logits - ref).abs().max().item() < 1e-5
+    assert (a32 - an).abs().max().item() < 1e-6
+    assert torch.equal(e32, emb.float())
+
+
+def test_prep_input(N):
+    lens = [50, 17, 33]
+    B, T, Din, Kpad = 3, 50, 345, 384
+    x = rnd(sum(lens), Din, seed=52)
+    cu = torch.tensor([0, 50, 67, 100], dtype=torch.int32, device=DEV)
+    sc, sh = 1 + 0.2 * rnd(Din, seed=53), rnd(Din, seed=54)
+    out = N.op_prep_input(x, cu, B, T, Kpad, sc, sh)
+    ref = torch.zeros(B, T, Kpad, device=DEV)
+    off = 0
+    for b, l in enumerate(lens):
+        ref[b, :l, :Din] = x[off:off + l] * sc + sh
+        ref[b, l:, :Din] = -1.0 * sc + sh
+        off += l
+    assert torch.equal(out, ref.half())

@@ -1,0 +1,101 @@
+"""End-to-end parity of the sm_100a FS-EEND forward (through the nnet API mirror and the C ABI) against
+(i) golden logits produced by the real reference and (ii) the CPU oracle, plus size-independent properties
+at the BASELINE.json configuration (B=64, T=500, S=6).  Tolerance: 1e-3 max-abs on logits (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fs_eend_oracle as O
+from test_oracle import CASES, load_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def make_model(sd, mask_delay=0):
+    from nnet.model.onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import OnlineTransformerDADiarization
+    m = OnlineTransformerDADiarization(n_speakers=4, in_size=345, n_units=256, n_heads=4, enc_n_layers=4,
+                                       dec_n_layers=2, dropout=0.1, has_mask=True, max_seqlen=500,
+                                       dec_dim_feedforward=2048, mask_delay=mask_delay)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_logits_match_reference_golden(name):
+    sd, src, lens, S, cfg, g = load_case(name)
+    m = make_model(sd, cfg.mask_delay)
+    out, emb, att = m.test([s.cuda() for s in src], lens, max_nspks=S)
+    worst = 0.0
+    for i, o in enumerate(out):
+        ref = g[f"logits_{i}"]
+        assert tuple(o.shape) == ref.shape
+        worst = max(worst, float(np.abs(o.cpu().numpy() - ref).max()))
+        stride = int(g["emb_stride"][i])
+        assert np.abs(emb[i].cpu().numpy()[::stride] - g[f"emb_{i}"]).max() < TOL
+        assert att[i].shape == (lens[i], S, 256)
+    print(f"{name}: max-abs logit error vs reference = {worst:.2e}")
+    assert worst < TOL
+
+
+def test_forward_api_and_emb_consistency_loss():
+    sd, src, lens, S, cfg, g = load_case("ragged_S6")
+    m = make_model(sd)
+    gen = torch.Generator().manual_seed(123)
+    tgt = [(torch.rand(l, S, generator=gen) > 0.6).float() for l in lens]
+    out, loss, emb, att = m(([s.cuda() for s in src]), tgt, lens)
+    assert abs(loss.item() - float(g["emb_consis_loss"])) < 1e-3
+    assert np.abs(out[0].cpu().numpy() - g["fwd_logits_0"]).max() < TOL
+    assert att[0].shape == (lens[0], S - 1, 256)
+
+
+def test_host_buffer_entry_point_matches_device_entry_point():
+    sd, src, lens, S, cfg, g = load_case("ragged_S6")
+    m = make_model(sd)
+    x = torch.cat(src).contiguous()
+    dev_logits, _, _ = m.native().forward(x.cuda(), lens, S)
+    host_logits, _, _ = m.native().forward_host(x.pin_memory(), lens, S)
+    assert torch.equal(dev_logits.cpu(), host_logits)
+
+
+def test_full_size_properties_B64_T500_S6():
+    """BASELINE.json configs[1] shape.  (1) batch invariance: a sequence inside a batch of 64 gives the
+    same logits as alone; (2) the oracle agrees on one sequence; (3) causality: perturbing frames >= 300
+    leaves logits < 300 - 9 untouched; (4) logits are cosines: |y| <= 1."""
+    sd = O.random_state_dict(seed=0, trained_like=True)
+    m = make_model(sd)
+    src, lens = O.synthetic_features(64, 500)
+    srcc = [s.cuda() for s in src]
+    y = torch.stack(m.test_logits(srcc, lens, 6))
+    assert y.shape == (64, 500, 6) and torch.isfinite(y).all() and y.abs().max() <= 1.0 + 1e-3
+    for b in (0, 17, 63):
+        alone = m.test_logits([srcc[b]], [500], 6)[0]
+        assert (alone - y[b]).abs().max().item() < 1e-6
+    with torch.no_grad():
+        ref = O.test(sd, [src[5]], [500], 6, O.Cfg())[0][0]
+    err = (y[5].cpu() - ref).abs().max().item()
+    print(f"B=64 T=500 S=6: max-abs logit error vs oracle = {err:.2e}")
+    assert err < TOL
+    pert = [s.clone() for s in srcc]
+    for s in pert:
+        s[300:] += 1.0
+    y2 = torch.stack(m.test_logits(pert, lens, 6))
+    assert (y2[:, :291] - y[:, :291]).abs().max().item() < 1e-6
+    assert (y2[:, 300:] - y[:, 300:]).abs().max().item() > 1e-3
+
+
+def test_weight_update_rebuilds_native_model():
+    sd = O.random_state_dict(seed=7)
+    m = make_model(sd)
+    src, lens = O.synthetic_features(1, 64)
+    a = m.test_logits([src[0].cuda()], lens, 4)[0]
+    with torch.no_grad():
+        m.cnn.bias.add_(0.5)
+    b = m.test_logits([src[0].cuda()], lens, 4)[0]
+    assert (a - b).abs().max().item() > 1e-4
+    sd2 = {k: v.clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.test({k: v.cpu() for k, v in sd2.items()}, src, lens, 4, O.Cfg())[0][0]
+    assert (b.cpu() - ref).abs().max().item() < TOL
