@@ -407,7 +407,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     p.ln_g = m->g_in.f();
     p.ln_b = m->be_in.f();
     p.ln_eps = c.ln_eps;
-    L.run("gemm_in_ln", [&] { launch_gemm(m->tm_x16, m->w_in.tm, none, m->tm_hA, p, st); });
+    L.run("enc.gemm_in_ln", [&] { launch_gemm(m->tm_x16, m->w_in.tm, none, m->tm_hA, p, st); });
   }
   // encoder layers: hA -> (attn) -> hB -> (ffn) -> hA
   for (int l = 0; l < c.enc_n_layers; ++l) {
@@ -415,11 +415,11 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     {
       GemmParams p = flat_params(Me, 3 * D, D, EPI_BIAS);
       p.bias = E.bqkv.f();
-      L.run("gemm_qkv", [&] { launch_gemm(m->tm_hA, E.wqkv.tm, none, m->tm_qkv_e_out, p, st); });
+      L.run("enc.gemm_qkv", [&] { launch_gemm(m->tm_hA, E.wqkv.tm, none, m->tm_qkv_e_out, p, st); });
     }
     {
       AttnParams a{B, 1, T, c.n_heads, c.has_mask ? c.mask_delay : (1 << 28), 1.f / sqrtf(64.f)};
-      L.run("attn_causal", [&] { launch_causal_attn(m->tm_qkv_e_attn, m->tm_ao_e_attn, a, st); });
+      L.run("enc.attn_causal", [&] { launch_causal_attn(m->tm_qkv_e_attn, m->tm_ao_e_attn, a, st); });
     }
     {
       GemmParams p = flat_params(Me, D, D, EPI_LN);
@@ -428,13 +428,13 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_g = E.g1.f();
       p.ln_b = E.be1.f();
       p.ln_eps = c.ln_eps;
-      L.run("gemm_out_ln", [&] { launch_gemm(m->tm_ao_e, E.wo.tm, m->tm_hA, m->tm_hB, p, st); });
+      L.run("enc.gemm_out_ln", [&] { launch_gemm(m->tm_ao_e, E.wo.tm, m->tm_hA, m->tm_hB, p, st); });
     }
     {
       GemmParams p = flat_params(Me, c.enc_dim_feedforward, D, EPI_BIAS);
       p.bias = E.b1.f();
       p.relu = 1;
-      L.run("gemm_ffn1", [&] { launch_gemm(m->tm_hB, E.w1.tm, none, m->tm_f_e_out, p, st); });
+      L.run("enc.gemm_ffn1", [&] { launch_gemm(m->tm_hB, E.w1.tm, none, m->tm_f_e_out, p, st); });
     }
     {
       GemmParams p = flat_params(Me, D, c.enc_dim_feedforward, EPI_LN);
@@ -451,9 +451,9 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
         p.seq_len = static_cast<const int*>(m->len_dev.p);
         CUtensorMap tmA = make_tmap_rows3d(m->f_e.p, c.enc_dim_feedforward, c.enc_dim_feedforward, T, B, 128);
         CUtensorMap tmR = make_tmap_rows3d(m->hB.p, D, D, T, B, 128);
-        L.run("gemm_ffn2_ln", [&] { launch_gemm(tmA, E.w2.tm, tmR, m->tm_hconv_in, p, st); });
+        L.run("enc.gemm_ffn2_ln", [&] { launch_gemm(tmA, E.w2.tm, tmR, m->tm_hconv_in, p, st); });
       } else {
-        L.run("gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_e_in, E.w2.tm, m->tm_hB, m->tm_hA, p, st); });
+        L.run("enc.gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_e_in, E.w2.tm, m->tm_hB, m->tm_hA, p, st); });
       }
     }
   }
@@ -485,11 +485,11 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     {
       GemmParams p = flat_params(Md, 3 * D, D, EPI_BIAS);
       p.bias = Dl.bqkv1.f();
-      L.run("gemm_qkv", [&] { launch_gemm(m->tm_aX, Dl.wqkv1.tm, none, m->tm_qkv_d_out, p, st); });
+      L.run("dec.gemm_qkv1", [&] { launch_gemm(m->tm_aX, Dl.wqkv1.tm, none, m->tm_qkv_d_out, p, st); });
     }
     {
       AttnParams a{B, S, T, c.n_heads, c.mask_delay, 1.f / sqrtf(64.f)};
-      L.run("attn_causal", [&] { launch_causal_attn(m->tm_qkv_d_attn, m->tm_ao_d_attn, a, st); });
+      L.run("dec.attn_causal", [&] { launch_causal_attn(m->tm_qkv_d_attn, m->tm_ao_d_attn, a, st); });
     }
     {
       GemmParams p = flat_params(Md, D, D, EPI_LN);
@@ -498,14 +498,14 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_g = Dl.g11.f();
       p.ln_b = Dl.be11.f();
       p.ln_eps = c.ln_eps;
-      L.run("gemm_out_ln", [&] { launch_gemm(m->tm_ao_d, Dl.wo1.tm, m->tm_aX, m->tm_aY, p, st); });
+      L.run("dec.gemm_out1_ln", [&] { launch_gemm(m->tm_ao_d, Dl.wo1.tm, m->tm_aX, m->tm_aY, p, st); });
     }
     {
       GemmParams p = flat_params(Md, 3 * D, D, EPI_BIAS);
       p.bias = Dl.bqkv2.f();
-      L.run("gemm_qkv", [&] { launch_gemm(m->tm_aY, Dl.wqkv2.tm, none, m->tm_qkv_d_out, p, st); });
+      L.run("dec.gemm_qkv2", [&] { launch_gemm(m->tm_aY, Dl.wqkv2.tm, none, m->tm_qkv_d_out, p, st); });
     }
-    L.run("spk_attn", [&] {
+    L.run("dec.spk_attn", [&] {
       launch_spk_attn(static_cast<const __half*>(m->qkv_d.p), static_cast<__half*>(m->ao_d.p), static_cast<int>(Me),
                       S, 1.f / sqrtf(64.f), st);
     });
@@ -516,13 +516,13 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_g = Dl.g21.f();
       p.ln_b = Dl.be21.f();
       p.ln_eps = c.ln_eps;
-      L.run("gemm_out_ln", [&] { launch_gemm(m->tm_ao_d, Dl.wo2.tm, m->tm_aY, m->tm_aZ, p, st); });
+      L.run("dec.gemm_out2_ln", [&] { launch_gemm(m->tm_ao_d, Dl.wo2.tm, m->tm_aY, m->tm_aZ, p, st); });
     }
     {
       GemmParams p = flat_params(Md, c.dec_dim_feedforward, D, EPI_BIAS);
       p.bias = Dl.b1.f();
       p.relu = 1;
-      L.run("gemm_ffn1", [&] { launch_gemm(m->tm_aZ, Dl.w1.tm, none, m->tm_f_d_out, p, st); });
+      L.run("dec.gemm_ffn1", [&] { launch_gemm(m->tm_aZ, Dl.w1.tm, none, m->tm_f_d_out, p, st); });
     }
     {
       GemmParams p = flat_params(Md, D, c.dec_dim_feedforward, EPI_LN);
@@ -531,7 +531,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_g = Dl.g22.f();
       p.ln_b = Dl.be22.f();
       p.ln_eps = c.ln_eps;
-      L.run("gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_d_in, Dl.w2.tm, m->tm_aZ, m->tm_aX, p, st); });
+      L.run("dec.gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_d_in, Dl.w2.tm, m->tm_aZ, m->tm_aX, p, st); });
     }
   }
   L.run("head", [&] {
