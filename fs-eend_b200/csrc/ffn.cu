@@ -1,0 +1,373 @@
+// Fused position-wise feed-forward + residual + LayerNorm (post-norm transformer FFN block):
+//     OUT = LN( X + relu(X W1^T + b1) W2^T + b2 )        X: [rows][256] fp16,  W1: [F][256],  W2: [256][F]
+// The F-wide intermediate never leaves the SM: per 128-row tile the hidden dimension is processed in
+// chunks of 128; chunk j's GEMM1 accumulator (TMEM) is bias+ReLU'd into an fp16 smem tile that is the
+// A operand of chunk j's GEMM2, which accumulates the 128x256 output in TMEM across all chunks.
+//
+// Reference: torch.nn.TransformerEncoderLayer._ff_block + norm2 (FS:model:147) and
+// TransformerEncoderFusionLayer._ff_block + norm22 (FS-EEND/nnet/modules/merge_tfm_encoder.py:373,397-399).
+//
+// Roles (192 threads):  warp 0 lane 0 = TMA producer, warp 1 lane 0 = tcgen05 issuer, warps 2-5 = epilogue.
+// Weights stream through a ring of 16 KB slots ([128 rows][64 k] fp16, 128B swizzle).  With kCluster = 2 the
+// two CTAs of a cluster work on adjacent row tiles and share every weight slot: each CTA fetches half of the
+// slots and TMA-multicasts them into both CTAs' rings, halving L2->SM weight traffic (the binding limit of this
+// block: 2 MB of weights per 268 MFLOP tile).
+#include "ffn.cuh"
+#include "ptx.cuh"
+
+namespace fseend {
+
+namespace {
+
+constexpr int kRows = 128;
+constexpr int kD = 256;
+constexpr int kChunk = 128;                 // hidden units per chunk
+constexpr int kSlotBytes = 128 * 64 * 2;    // 16 KB
+constexpr int kXBytes = 4 * kSlotBytes;     // 64 KB: X tile as 4 k-sub-tiles
+constexpr int kPBytes = 2 * kSlotBytes;     // 32 KB per P buffer (2 k-sub-tiles)
+constexpr int kSlots = 6;
+constexpr int kOffX = 0;
+constexpr int kOffP = kOffX + kXBytes;              // 2 buffers
+constexpr int kOffW = kOffP + 2 * kPBytes;
+constexpr int kSmemBytes = kOffW + kSlots * kSlotBytes + 1024;
+constexpr uint32_t kTmemCols = 512;                  // Y [0,256), H0 [256,384), H1 [384,512)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32_sync(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void load_vec32(const float* __restrict__ p, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+    v[4 * i + 0] = t.x;
+    v[4 * i + 1] = t.y;
+    v[4 * i + 2] = t.z;
+    v[4 * i + 3] = t.w;
+  }
+}
+// 32 fp16 columns [c*32, c*32+32) of row r in a tile made of 64-column sub-tiles of kSlotBytes each
+__device__ __forceinline__ void tile_read32(const uint8_t* tile, int r, int c, float (&v)[32]) {
+  const uint8_t* sub = tile + (c >> 1) * kSlotBytes;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u = *reinterpret_cast<const uint4*>(sub + sw128_offset(r, (c & 1) * 4 + q));
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(h[j]);
+      v[q * 8 + 2 * j] = f.x;
+      v[q * 8 + 2 * j + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void tile_write32(uint8_t* tile, int r, int c, const float (&v)[32]) {
+  uint8_t* sub = tile + (c >> 1) * kSlotBytes;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_half2(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_half2(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_half2(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_half2(v[q * 8 + 6], v[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(sub + sw128_offset(r, (c & 1) * 4 + q)) = u;
+  }
+}
+
+template <int kCluster>
+__global__ void __launch_bounds__(192, 1)
+ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+           const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO, const FfnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t x_full, w_full[kSlots], w_empty[kSlots], h_full[2], h_empty[2], p_full[2],
+      p_empty[2], y_full;
+  __shared__ uint32_t tmem_base_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const uint32_t rank = (kCluster > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (kCluster > 1) ? 0x3 : 0x1;
+
+  const int m_tile = blockIdx.x;
+  const int seq = m_tile / p.tiles_per_seq;
+  const int t0 = (m_tile % p.tiles_per_seq) * kRows;
+  const int n_chunks = p.F / kChunk;
+
+  if (tid == 0) {
+    mbar_init(&x_full, 1);
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], kCluster);   // one tcgen05.commit arrival per CTA of the cluster
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&h_full[i], 1);
+      mbar_init(&h_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(&y_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmO);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tmem_Y = tmem_base;
+
+  // Slot sequence shared by producer and MMA issuer:  W1(0) | W1(1) W2(0) | W1(2) W2(1) | ... | W2(n-1)
+  // every "group" is 4 slots; group g: g == 0 -> W1(0); g odd -> W1((g+1)/2) if it exists; g even -> W2(g/2 - 1)
+  // Enumerated explicitly below to keep both roles in lock-step.
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      mbar_arrive_expect_tx(&x_full, kXBytes);
+      for (int ks = 0; ks < 4; ++ks) tma_load_3d(smem + kOffX + ks * kSlotBytes, &tmX, &x_full, ks * 64, t0, seq);
+      uint32_t use = 0;   // global slot-use counter
+      auto load_slot = [&](const CUtensorMap* tm, int c0, int c1) {
+        const int s = use % kSlots;
+        const uint32_t ph = (use / kSlots) & 1;
+        mbar_wait(&w_empty[s], ph ^ 1, 31);
+        mbar_arrive_expect_tx(&w_full[s], kSlotBytes);
+        if (kCluster == 1) {
+          tma_load_2d(smem + kOffW + s * kSlotBytes, tm, &w_full[s], c0, c1);
+        } else if ((use & 1u) == rank) {
+          tma_load_2d_mc(smem + kOffW + s * kSlotBytes, tm, &w_full[s], c0, c1, kMask);
+        }
+        ++use;
+      };
+      auto load_w1 = [&](int j) {   // W1 rows [j*128, +128), k-sub-tile ks -> box (64 k, 128 rows)
+        for (int ks = 0; ks < 4; ++ks) load_slot(&tmW1, ks * 64, j * kChunk);
+      };
+      auto load_w2 = [&](int j) {   // W2[:, j*128 .. +128): k-sub-tile ks2, N halves 0/1 -> box (64 k, 128 rows)
+        for (int ks2 = 0; ks2 < 2; ++ks2)
+          for (int nh = 0; nh < 2; ++nh) load_slot(&tmW2, j * kChunk + ks2 * 64, nh * 128);
+      };
+      load_w1(0);
+      for (int j = 0; j < n_chunks; ++j) {
+        if (j + 1 < n_chunks) load_w1(j + 1);
+        load_w2(j);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc_g1 = make_idesc_f16(128, 128, false);
+      constexpr uint32_t idesc_g2 = make_idesc_f16(128, 256, false);
+      uint32_t use = 0;
+      auto release_slot = [&](int s) {
+        if (kCluster == 1) umma_commit(&w_empty[s]);
+        else umma_commit_mc(&w_empty[s], kMask);
+      };
+      auto gemm1 = [&](int j) {
+        const int hb = j & 1;
+        mbar_wait(&h_empty[hb], ((j >> 1) & 1) ^ 1, 32);     // epilogue has drained H(j-2)
+        tc_fence_after();
+        const uint32_t tmem_H = tmem_base + 256 + hb * 128;
+        for (int ks = 0; ks < 4; ++ks) {
+          const int s = use % kSlots;
+          mbar_wait(&w_full[s], (use / kSlots) & 1, 33);
+          tc_fence_after();
+          const uint64_t adesc = smem_desc_sw128(smem_u32(smem + kOffX + ks * kSlotBytes));
+          const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + kOffW + s * kSlotBytes));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(tmem_H, adesc + 2 * kk, bdesc + 2 * kk, idesc_g1, (ks > 0 || kk > 0) ? 1u : 0u);
+          release_slot(s);
+          ++use;
+        }
+        umma_commit(&h_full[hb]);
+      };
+      auto gemm2 = [&](int j) {
+        const int pb = j & 1;
+        mbar_wait(&p_full[pb], (j >> 1) & 1, 34);            // P(j) written by the epilogue warps
+        tc_fence_after();
+        for (int ks2 = 0; ks2 < 2; ++ks2) {
+          const int s0 = use % kSlots;                        // slots s0 (N rows 0-127) and s0+1 (128-255) are adjacent
+          mbar_wait(&w_full[s0], (use / kSlots) & 1, 35);
+          mbar_wait(&w_full[s0 + 1], ((use + 1) / kSlots) & 1, 36);
+          tc_fence_after();
+          const uint64_t adesc = smem_desc_sw128(smem_u32(smem + kOffP + pb * kPBytes + ks2 * kSlotBytes));
+          const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + kOffW + s0 * kSlotBytes));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(tmem_Y, adesc + 2 * kk, bdesc + 2 * kk, idesc_g2, (j > 0 || ks2 > 0 || kk > 0) ? 1u : 0u);
+          release_slot(s0);
+          release_slot(s0 + 1);
+          use += 2;
+        }
+        umma_commit(&p_empty[pb]);
+      };
+      mbar_wait(&x_full, 0, 30);
+      tc_fence_after();
+      gemm1(0);
+      for (int j = 0; j < n_chunks; ++j) {
+        if (j + 1 < n_chunks) gemm1(j + 1);
+        gemm2(j);
+      }
+      umma_commit(&y_full);
+    }
+    __syncwarp();
+  } else {
+    // -------------------------------------------------------------------- epilogue warps (2..5)
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;            // tile row
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    float acc[32], aux[32];
+    for (int j = 0; j < n_chunks; ++j) {
+      const int hb = j & 1;
+      mbar_wait(&h_full[hb], (j >> 1) & 1, 40);
+      tc_fence_after();
+      if (j >= 2) mbar_wait(&p_empty[hb], ((j >> 1) & 1) ^ 1, 41);   // GEMM2(j-2) has consumed this P buffer
+      uint8_t* ptile = smem + kOffP + hb * kPBytes;
+      const uint32_t tH = tmem_base + 256 + hb * 128 + lane_base;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32_sync(tH + c * 32, acc);
+        load_vec32(p.b1 + j * kChunk + c * 32, aux);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i] + aux[i], 0.f);
+        tile_write32(ptile, r, c, acc);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[hb]);
+      mbar_arrive(&h_empty[hb]);
+    }
+    // ---- final: Y + b2 + X -> LayerNorm -> fp16 -> staging (P buffers, 64 KB) -> TMA store
+    mbar_wait(&y_full, 0, 42);
+    mbar_wait(&x_full, 0, 43);   // residual tile (long since landed; makes the TMA write visible to this thread)
+    tc_fence_after();
+    const uint8_t* xtile = smem + kOffX;
+    uint8_t* staging = smem + kOffP;
+    const uint32_t tY = tmem_Y + lane_base;
+    float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      tmem_ld32_sync(tY + c * 32, acc);
+      load_vec32(p.b2 + c * 32, aux);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] += aux[i];
+      tile_read32(xtile, r, c, aux);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        acc[i] += aux[i];
+        s += acc[i];
+      }
+      const float cm = s * (1.f / 32.f);
+      float cm2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float d = acc[i] - cm;
+        cm2 = fmaf(d, d, cm2);
+      }
+      const float nn = n + 32.f;
+      const float delta = cm - mean;
+      m2 += cm2 + delta * delta * (n * 32.f / nn);
+      mean += delta * (32.f / nn);
+      n = nn;
+    }
+    const float rstd = rsqrtf(m2 * (1.f / 256.f) + p.ln_eps);
+    const bool zero_row = p.seq_len != nullptr && seq < p.n_seq && (t0 + r) >= p.seq_len[seq];
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      tmem_ld32_sync(tY + c * 32, acc);
+      load_vec32(p.b2 + c * 32, aux);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] += aux[i];
+      tile_read32(xtile, r, c, aux);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = (acc[i] + aux[i] - mean) * rstd;
+      load_vec32(p.ln_g + c * 32, aux);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] *= aux[i];
+      load_vec32(p.ln_b + c * 32, aux);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = zero_row ? 0.f : acc[i] + aux[i];
+      tile_write32(staging, r, c, acc);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (tid == 64) {   // first epilogue thread
+      for (int sub = 0; sub < 4; ++sub) tma_store_3d(&tmO, staging + sub * kSlotBytes, sub * 64, t0, seq);
+      tma_store_commit();
+      tma_store_wait_read0();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into / arrive on it
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace
+
+void launch_ffn(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmO,
+                const FfnParams& p, int cluster, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ffn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(ffn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    attr_set = true;
+  }
+  int tiles = p.n_seq * p.tiles_per_seq;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (cluster == 2) {
+    cfg.gridDim = dim3((tiles + 1) / 2 * 2);   // odd tile count: the last CTA runs on zero-filled rows, stores clip
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, ffn_kernel<2>, tmX, tmW1, tmW2, tmO, p);
+  } else {
+    cfg.gridDim = dim3(tiles);
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
+    cudaLaunchKernelEx(&cfg, ffn_kernel<1>, tmX, tmW1, tmW2, tmO, p);
+  }
+}
+
+}  // namespace fseend

@@ -1,0 +1,26 @@
+// Fused FFN + residual + LayerNorm block (see ffn.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace fseend {
+
+struct FfnParams {
+  int rows_per_seq;
+  int n_seq;
+  int tiles_per_seq;   // ceil(rows_per_seq / 128)
+  int F;               // hidden width, multiple of 128
+  float ln_eps;
+  const float* b1;     // [F]
+  const float* b2;     // [256]
+  const float* ln_g;   // [256]
+  const float* ln_b;   // [256]
+  const int* seq_len;  // optional [n_seq]: rows t >= seq_len[b] are written as zeros
+};
+
+// tmX / tmO: 3-D (256, rows_per_seq, n_seq) box (64,128,1);  tmW1: 2-D (256, F) box (64,128);
+// tmW2: 2-D (F, 256) box (64,128).  cluster: 1, or 2 (CTA pairs share weight tiles through TMA multicast).
+void launch_ffn(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmO,
+                const FfnParams& p, int cluster, cudaStream_t stream);
+
+}  // namespace fseend

@@ -19,6 +19,7 @@
 #include "../../include/fseend_b200.h"
 #include "attn.cuh"
 #include "elementwise.cuh"
+#include "ffn.cuh"
 #include "gemm.cuh"
 #include "tmap.h"
 
@@ -59,7 +60,8 @@ struct DevBuf {
 struct WMat {
   DevBuf buf;
   int rows = 0, K = 0;
-  CUtensorMap tm;
+  CUtensorMap tm;     // box (64 k, 256 rows): B operand of the 128x256 GEMM tile
+  CUtensorMap tm128;  // box (64 k, 128 rows): 16 KB weight slots of the fused FFN
   void upload(const std::vector<__half>& h, int rows_, int K_) {
     rows = rows_;
     K = K_;
@@ -69,6 +71,8 @@ struct WMat {
     uint64_t str[1] = {static_cast<uint64_t>(K)};
     uint32_t box[2] = {64, 256};
     tm = make_tmap_f16(buf.p, 2, dims, str, box);
+    uint32_t box128[2] = {64, 128};
+    tm128 = make_tmap_f16(buf.p, 2, dims, str, box128);
   }
 };
 
@@ -120,9 +124,11 @@ struct fseend_fs_model {
   int* cu_host = nullptr;  // pinned [B+1] + [B]
   // descriptors
   CUtensorMap tm_x16, tm_hA, tm_hB, tm_qkv_e_out, tm_qkv_e_attn, tm_ao_e_attn, tm_ao_e, tm_f_e_out, tm_f_e_in;
-  CUtensorMap tm_hconv_in, tm_emb_out, tm_emb_in, tm_cvt_out;
-  CUtensorMap tm_aX, tm_aY, tm_aZ, tm_qkv_d_out, tm_qkv_d_attn, tm_ao_d_attn, tm_ao_d, tm_f_d_out, tm_f_d_in;
+  CUtensorMap tm_hconv_in, tm_hB_seq, tm_emb_out, tm_emb_in, tm_cvt_out;
+  CUtensorMap tm_aX, tm_aY, tm_aZ, tm_qkv_d_out, tm_qkv_d_attn, tm_ao_d_attn, tm_qkv_d_spk, tm_ao_d_spk, tm_ao_d, tm_f_d_out, tm_f_d_in;
 
+  int spk_mode = 1;  // 0: CUDA-core speaker attention, 1: tcgen05 block-diagonal attention
+  int ffn_mode = 2;  // 0: two GEMM launches (hidden layer through HBM), 1: fused kernel, 2: fused + 2-CTA weight multicast
   bool profiling = false;
   std::vector<ProfEntry> prof_pending;
   std::map<std::string, std::pair<double, int>> prof_acc;
@@ -309,6 +315,7 @@ void make_plan(fseend_fs_model* m, int B, int T, int S) {
   m->tm_f_e_in = m->tm_f_e_out;
   // conv: per-sequence tiles so that shifted taps zero-fill across sequence ends
   m->tm_hconv_in = rows_map(m->hA, D, T, B);   // encoder output always ends in hA (see forward)
+  m->tm_hB_seq = rows_map(m->hB, D, T, B);
   m->tm_emb_out = rows_map(m->emb16, D, T, B);
   m->tm_emb_in = rows_map(m->emb16, D, Me, 1);
   {
@@ -323,6 +330,13 @@ void make_plan(fseend_fs_model* m, int B, int T, int S) {
   m->tm_qkv_d_out = rows_map(m->qkv_d, 3 * D, Md, 1);
   m->tm_qkv_d_attn = attn_map(m->qkv_d, 3 * D, S, T, B);
   m->tm_ao_d_attn = attn_map(m->ao_d, D, S, T, B);
+  {
+    uint64_t dq[4] = {static_cast<uint64_t>(3 * D), 1, Md, 1}, sq[3] = {3ull * D, 3ull * D, 3ull * D * Md};
+    uint64_t dout[4] = {static_cast<uint64_t>(D), 1, Md, 1}, so[3] = {1ull * D, 1ull * D, 1ull * D * Md};
+    uint32_t bq[4] = {64, 1, 128, 1}, bo[4] = {64, 1, static_cast<uint32_t>((128 / S) * S), 1};
+    m->tm_qkv_d_spk = make_tmap_f16(m->qkv_d.p, 4, dq, sq, bq);
+    m->tm_ao_d_spk = make_tmap_f16(m->ao_d.p, 4, dout, so, bo);
+  }
   m->tm_ao_d = rows_map(m->ao_d, D, Md, 1);
   m->tm_f_d_out = rows_map(m->f_d, c.dec_dim_feedforward, Md, 1);
   m->tm_f_d_in = m->tm_f_d_out;
@@ -364,6 +378,22 @@ GemmParams flat_params(size_t rows, int N, int K, int mode) {
   p.tap_shift = 0;
   p.mode = mode;
   p.ln_eps = 1e-5f;
+  return p;
+}
+
+FfnParams ffn_params(int rows_per_seq, int n_seq, int F, const FVec& b1, const FVec& b2, const FVec& g, const FVec& b,
+                     float eps, const int* seq_len) {
+  FfnParams p{};
+  p.rows_per_seq = rows_per_seq;
+  p.n_seq = n_seq;
+  p.tiles_per_seq = (rows_per_seq + 127) / 128;
+  p.F = F;
+  p.ln_eps = eps;
+  p.b1 = b1.f();
+  p.b2 = b2.f();
+  p.ln_g = g.f();
+  p.ln_b = b.f();
+  p.seq_len = seq_len;
   return p;
 }
 
@@ -418,8 +448,8 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       L.run("enc.gemm_qkv", [&] { launch_gemm(m->tm_hA, E.wqkv.tm, none, m->tm_qkv_e_out, p, st); });
     }
     {
-      AttnParams a{B, 1, T, c.n_heads, c.has_mask ? c.mask_delay : (1 << 28), 1.f / sqrtf(64.f)};
-      L.run("enc.attn_causal", [&] { launch_causal_attn(m->tm_qkv_e_attn, m->tm_ao_e_attn, a, st); });
+      AttnParams a{B, 1, T, c.n_heads, c.has_mask ? c.mask_delay : (1 << 28), 1.f / sqrtf(64.f), ATTN_CAUSAL, 128};
+      L.run("enc.attn_causal", [&] { launch_attn(m->tm_qkv_e_attn, m->tm_ao_e_attn, a, st); });
     }
     {
       GemmParams p = flat_params(Me, D, D, EPI_LN);
@@ -430,31 +460,42 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_eps = c.ln_eps;
       L.run("enc.gemm_out_ln", [&] { launch_gemm(m->tm_ao_e, E.wo.tm, m->tm_hA, m->tm_hB, p, st); });
     }
-    {
-      GemmParams p = flat_params(Me, c.enc_dim_feedforward, D, EPI_BIAS);
-      p.bias = E.b1.f();
-      p.relu = 1;
-      L.run("enc.gemm_ffn1", [&] { launch_gemm(m->tm_hB, E.w1.tm, none, m->tm_f_e_out, p, st); });
-    }
-    {
-      GemmParams p = flat_params(Me, D, c.enc_dim_feedforward, EPI_LN);
-      p.bias = E.b2.f();
-      p.has_residual = 1;
-      p.ln_g = E.g2.f();
-      p.ln_b = E.be2.f();
-      p.ln_eps = c.ln_eps;
+    const bool last = (l == c.enc_n_layers - 1);
+    if (m->ffn_mode > 0) {
       // last layer: rows t >= ilens[b] become zeros = the reference's truncate + re-pad(0) (FS:model:38-39)
-      if (l == c.enc_n_layers - 1) {
-        p.rows_per_seq = T;
-        p.n_seq = B;
-        p.tiles_per_seq = (T + 127) / 128;
-        p.seq_len = static_cast<const int*>(m->len_dev.p);
-        CUtensorMap tmA = make_tmap_rows3d(m->f_e.p, c.enc_dim_feedforward, c.enc_dim_feedforward, T, B, 128);
-        CUtensorMap tmR = make_tmap_rows3d(m->hB.p, D, D, T, B, 128);
-        L.run("enc.gemm_ffn2_ln", [&] { launch_gemm(tmA, E.w2.tm, tmR, m->tm_hconv_in, p, st); });
-      } else {
-        L.run("enc.gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_e_in, E.w2.tm, m->tm_hB, m->tm_hA, p, st); });
+      FfnParams fp = ffn_params(last ? T : static_cast<int>(Me), last ? B : 1, c.enc_dim_feedforward, E.b1, E.b2, E.g2,
+                                E.be2, c.ln_eps, last ? static_cast<const int*>(m->len_dev.p) : nullptr);
+      const CUtensorMap& tx = last ? m->tm_hB_seq : m->tm_hB;
+      const CUtensorMap& to = last ? m->tm_hconv_in : m->tm_hA;
+      L.run("enc.ffn_fused", [&] { launch_ffn(tx, E.w1.tm128, E.w2.tm128, to, fp, m->ffn_mode, st); });
+    } else {
+      {
+        GemmParams p = flat_params(Me, c.enc_dim_feedforward, D, EPI_BIAS);
+        p.bias = E.b1.f();
+        p.relu = 1;
+        L.run("enc.gemm_ffn1", [&] { launch_gemm(m->tm_hB, E.w1.tm, none, m->tm_f_e_out, p, st); });
       }
+      {
+        GemmParams p = flat_params(Me, D, c.enc_dim_feedforward, EPI_LN);
+        p.bias = E.b2.f();
+        p.has_residual = 1;
+        p.ln_g = E.g2.f();
+        p.ln_b = E.be2.f();
+        p.ln_eps = c.ln_eps;
+        // last layer: rows t >= ilens[b] become zeros = the reference's truncate + re-pad(0) (FS:model:38-39)
+        if (l == c.enc_n_layers - 1) {
+          p.rows_per_seq = T;
+          p.n_seq = B;
+          p.tiles_per_seq = (T + 127) / 128;
+          p.seq_len = static_cast<const int*>(m->len_dev.p);
+          CUtensorMap tmA = make_tmap_rows3d(m->f_e.p, c.enc_dim_feedforward, c.enc_dim_feedforward, T, B, 128);
+          CUtensorMap tmR = make_tmap_rows3d(m->hB.p, D, D, T, B, 128);
+          L.run("enc.gemm_ffn2_ln", [&] { launch_gemm(tmA, E.w2.tm, tmR, m->tm_hconv_in, p, st); });
+        } else {
+          L.run("enc.gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_e_in, E.w2.tm, m->tm_hB, m->tm_hA, p, st); });
+        }
+      }
+  
     }
   }
   if (c.enc_n_layers == 0) throw std::invalid_argument("enc_n_layers must be >= 1");
@@ -488,8 +529,8 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       L.run("dec.gemm_qkv1", [&] { launch_gemm(m->tm_aX, Dl.wqkv1.tm, none, m->tm_qkv_d_out, p, st); });
     }
     {
-      AttnParams a{B, S, T, c.n_heads, c.mask_delay, 1.f / sqrtf(64.f)};
-      L.run("dec.attn_causal", [&] { launch_causal_attn(m->tm_qkv_d_attn, m->tm_ao_d_attn, a, st); });
+      AttnParams a{B, S, T, c.n_heads, c.mask_delay, 1.f / sqrtf(64.f), ATTN_CAUSAL, 128};
+      L.run("dec.attn_causal", [&] { launch_attn(m->tm_qkv_d_attn, m->tm_ao_d_attn, a, st); });
     }
     {
       GemmParams p = flat_params(Md, D, D, EPI_LN);
@@ -505,10 +546,15 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.bias = Dl.bqkv2.f();
       L.run("dec.gemm_qkv2", [&] { launch_gemm(m->tm_aY, Dl.wqkv2.tm, none, m->tm_qkv_d_out, p, st); });
     }
-    L.run("dec.spk_attn", [&] {
-      launch_spk_attn(static_cast<const __half*>(m->qkv_d.p), static_cast<__half*>(m->ao_d.p), static_cast<int>(Me),
-                      S, 1.f / sqrtf(64.f), st);
-    });
+    if (m->spk_mode == 1) {
+      AttnParams a{1, S, static_cast<int>(Md), c.n_heads, 0, 1.f / sqrtf(64.f), ATTN_BLOCKDIAG, (128 / S) * S};
+      L.run("dec.spk_attn", [&] { launch_attn(m->tm_qkv_d_spk, m->tm_ao_d_spk, a, st); });
+    } else {
+      L.run("dec.spk_attn", [&] {
+        launch_spk_attn(static_cast<const __half*>(m->qkv_d.p), static_cast<__half*>(m->ao_d.p),
+                        static_cast<int>(Me), S, 1.f / sqrtf(64.f), st);
+      });
+    }
     {
       GemmParams p = flat_params(Md, D, D, EPI_LN);
       p.bias = Dl.bo2.f();
@@ -518,20 +564,27 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_eps = c.ln_eps;
       L.run("dec.gemm_out2_ln", [&] { launch_gemm(m->tm_ao_d, Dl.wo2.tm, m->tm_aY, m->tm_aZ, p, st); });
     }
-    {
-      GemmParams p = flat_params(Md, c.dec_dim_feedforward, D, EPI_BIAS);
-      p.bias = Dl.b1.f();
-      p.relu = 1;
-      L.run("dec.gemm_ffn1", [&] { launch_gemm(m->tm_aZ, Dl.w1.tm, none, m->tm_f_d_out, p, st); });
-    }
-    {
-      GemmParams p = flat_params(Md, D, c.dec_dim_feedforward, EPI_LN);
-      p.bias = Dl.b2.f();
-      p.has_residual = 1;
-      p.ln_g = Dl.g22.f();
-      p.ln_b = Dl.be22.f();
-      p.ln_eps = c.ln_eps;
-      L.run("dec.gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_d_in, Dl.w2.tm, m->tm_aZ, m->tm_aX, p, st); });
+    if (m->ffn_mode > 0) {
+      FfnParams fp = ffn_params(static_cast<int>(Md), 1, c.dec_dim_feedforward, Dl.b1, Dl.b2, Dl.g22, Dl.be22, c.ln_eps,
+                                nullptr);
+      L.run("dec.ffn_fused", [&] { launch_ffn(m->tm_aZ, Dl.w1.tm128, Dl.w2.tm128, m->tm_aX, fp, m->ffn_mode, st); });
+    } else {
+      {
+        GemmParams p = flat_params(Md, c.dec_dim_feedforward, D, EPI_BIAS);
+        p.bias = Dl.b1.f();
+        p.relu = 1;
+        L.run("dec.gemm_ffn1", [&] { launch_gemm(m->tm_aZ, Dl.w1.tm, none, m->tm_f_d_out, p, st); });
+      }
+      {
+        GemmParams p = flat_params(Md, D, c.dec_dim_feedforward, EPI_LN);
+        p.bias = Dl.b2.f();
+        p.has_residual = 1;
+        p.ln_g = Dl.g22.f();
+        p.ln_b = Dl.be22.f();
+        p.ln_eps = c.ln_eps;
+        L.run("dec.gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_d_in, Dl.w2.tm, m->tm_aZ, m->tm_aX, p, st); });
+      }
+  
     }
   }
   L.run("head", [&] {
@@ -749,6 +802,50 @@ int fseend_op_gemm(const void* a_f16, int rows_per_seq, int n_seq, int K, const 
   });
 }
 
+int fseend_fs_set_option(fseend_fs_model* m, const char* key, int value) {
+  if (!m || !key) return FSEEND_ERR_INVALID;
+  if (strcmp(key, "ffn") == 0 && value >= 0 && value <= 2) {
+    m->ffn_mode = value;
+    return FSEEND_OK;
+  }
+  if (strcmp(key, "spk") == 0 && value >= 0 && value <= 1) {
+    m->spk_mode = value;
+    return FSEEND_OK;
+  }
+  set_last_error(std::string("unknown option or bad value: ") + key);
+  return FSEEND_ERR_INVALID;
+}
+
+int fseend_op_ffn(const void* x_f16, int rows_per_seq, int n_seq, const void* w1_f16, const float* b1,
+                  const void* w2_f16, const float* b2, int F, const float* ln_g, const float* ln_b, float ln_eps,
+                  const int* seq_len_dev, int cluster, void* out_f16, void* stream) {
+  return guarded([&] {
+    if (F % 128 || F < 128) throw std::invalid_argument("F must be a multiple of 128");
+    if (cluster != 1 && cluster != 2) throw std::invalid_argument("cluster must be 1 or 2");
+    if (!fseend_device_ok()) throw std::invalid_argument("sm_100 device required");
+    FfnParams p{};
+    p.rows_per_seq = rows_per_seq;
+    p.n_seq = n_seq;
+    p.tiles_per_seq = (rows_per_seq + 127) / 128;
+    p.F = F;
+    p.ln_eps = ln_eps;
+    p.b1 = b1;
+    p.b2 = b2;
+    p.ln_g = ln_g;
+    p.ln_b = ln_b;
+    p.seq_len = seq_len_dev;
+    CUtensorMap tmX = make_tmap_rows3d(x_f16, 256, 256, rows_per_seq, n_seq, 128);
+    CUtensorMap tmO = make_tmap_rows3d(out_f16, 256, 256, rows_per_seq, n_seq, 128);
+    uint32_t box[2] = {64, 128};
+    uint64_t d1[2] = {256, static_cast<uint64_t>(F)}, s1[1] = {256};
+    uint64_t d2[2] = {static_cast<uint64_t>(F), 256}, s2[1] = {static_cast<uint64_t>(F)};
+    CUtensorMap tmW1 = make_tmap_f16(w1_f16, 2, d1, s1, box);
+    CUtensorMap tmW2 = make_tmap_f16(w2_f16, 2, d2, s2, box);
+    launch_ffn(tmX, tmW1, tmW2, tmO, p, cluster, static_cast<cudaStream_t>(stream));
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
 int fseend_op_causal_attn(const void* qkv_f16, int B, int T, int S, int H, int mask_delay, float scale, void* out_f16,
                           void* stream) {
   return guarded([&] {
@@ -761,8 +858,24 @@ int fseend_op_causal_attn(const void* qkv_f16, int B, int T, int S, int H, int m
     uint32_t box[4] = {64, 1, 128, 1};
     CUtensorMap tq = make_tmap_f16(qkv_f16, 4, dq, sq, box);
     CUtensorMap to = make_tmap_f16(out_f16, 4, d_o, so, box);
-    AttnParams a{B, S, T, H, mask_delay, scale};
-    launch_causal_attn(tq, to, a, static_cast<cudaStream_t>(stream));
+    AttnParams a{B, S, T, H, mask_delay, scale, ATTN_CAUSAL, 128};
+    launch_attn(tq, to, a, static_cast<cudaStream_t>(stream));
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int fseend_op_spk_attn_tc(const void* qkv_f16, int n_frames, int S, float scale, void* out_f16, void* stream) {
+  return guarded([&] {
+    if (S < 1 || S > 16) throw std::invalid_argument("S must be in [1,16]");
+    if (!fseend_device_ok()) throw std::invalid_argument("sm_100 device required");
+    const uint64_t rows = 1ull * n_frames * S;
+    uint64_t dq[4] = {768, 1, rows, 1}, sq[3] = {768, 768, 768 * rows};
+    uint64_t d_o[4] = {256, 1, rows, 1}, so[3] = {256, 256, 256 * rows};
+    uint32_t bq[4] = {64, 1, 128, 1}, bo[4] = {64, 1, static_cast<uint32_t>((128 / S) * S), 1};
+    CUtensorMap tq = make_tmap_f16(qkv_f16, 4, dq, sq, bq);
+    CUtensorMap to = make_tmap_f16(out_f16, 4, d_o, so, bo);
+    AttnParams a{1, S, static_cast<int>(rows), 4, 0, scale, ATTN_BLOCKDIAG, (128 / S) * S};
+    launch_attn(tq, to, a, static_cast<cudaStream_t>(stream));
     CUDA_CHECK(cudaGetLastError());
   });
 }

@@ -33,8 +33,9 @@ class FsConfig(C.Structure):
 EXPORTS = [
     "fseend_version", "fseend_last_error", "fseend_device_ok", "fseend_fs_create", "fseend_fs_destroy",
     "fseend_fs_forward", "fseend_fs_forward_host", "fseend_fs_set_profiling", "fseend_fs_get_profile",
-    "fseend_fs_launches_per_forward", "fseend_fs_workspace_bytes", "fseend_op_gemm", "fseend_op_causal_attn",
-    "fseend_op_spk_attn", "fseend_op_head", "fseend_op_prep_input",
+    "fseend_fs_launches_per_forward", "fseend_fs_workspace_bytes", "fseend_fs_set_option", "fseend_op_gemm",
+    "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
+    "fseend_op_prep_input",
 ]
 
 
@@ -72,6 +73,12 @@ def lib() -> C.CDLL:
     L.fseend_op_gemm.argtypes = [vp, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, vp, vp, vp, fp, vp, ip, vp, vp, vp]
     L.fseend_op_causal_attn.restype = ip
     L.fseend_op_causal_attn.argtypes = [vp, ip, ip, ip, ip, ip, fp, vp, vp]
+    L.fseend_fs_set_option.restype = ip
+    L.fseend_fs_set_option.argtypes = [vp, C.c_char_p, ip]
+    L.fseend_op_ffn.restype = ip
+    L.fseend_op_ffn.argtypes = [vp, ip, ip, vp, vp, vp, vp, ip, vp, vp, fp, vp, ip, vp, vp]
+    L.fseend_op_spk_attn_tc.restype = ip
+    L.fseend_op_spk_attn_tc.argtypes = [vp, ip, ip, fp, vp, vp]
     L.fseend_op_spk_attn.restype = ip
     L.fseend_op_spk_attn.argtypes = [vp, ip, ip, fp, vp, vp]
     L.fseend_op_head.restype = ip
@@ -171,6 +178,9 @@ class FsModel:
                                               _ptr(att)))
         return logits, emb, att
 
+    def set_option(self, key: str, value: int):
+        _check(self._L.fseend_fs_set_option(self._h, key.encode(), int(value)))
+
     def set_profiling(self, on: bool):
         _check(self._L.fseend_fs_set_profiling(self._h, 1 if on else 0))
 
@@ -219,12 +229,24 @@ def op_causal_attn(qkv: torch.Tensor, mask_delay: int = 0, scale: float = 0.125)
     return out
 
 
-def op_spk_attn(qkv: torch.Tensor, scale: float = 0.125) -> torch.Tensor:
+def op_spk_attn(qkv: torch.Tensor, scale: float = 0.125, tensor_core: bool = False) -> torch.Tensor:
     """qkv: fp16 [frames, S, 768] -> [frames, S, 256]."""
     _require_cuda(qkv)
     F, S, _ = qkv.shape
     out = torch.empty(F, S, 256, device=qkv.device, dtype=torch.float16)
-    _check(lib().fseend_op_spk_attn(_ptr(qkv), F, S, scale, _ptr(out), _stream()))
+    fn = lib().fseend_op_spk_attn_tc if tensor_core else lib().fseend_op_spk_attn
+    _check(fn(_ptr(qkv), F, S, scale, _ptr(out), _stream()))
+    return out
+
+
+def op_ffn(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, ln_g: torch.Tensor,
+           ln_b: torch.Tensor, *, n_seq: int = 1, ln_eps: float = 1e-5, seq_len=None, cluster: int = 2) -> torch.Tensor:
+    """x: fp16 [n_seq*rows_per_seq, 256]; w1: fp16 [F, 256]; w2: fp16 [256, F]."""
+    _require_cuda(x, w1, b1, w2, b2, ln_g, ln_b, seq_len)
+    rows = x.shape[0]
+    out = torch.empty_like(x)
+    _check(lib().fseend_op_ffn(_ptr(x), rows // n_seq, n_seq, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), w1.shape[0],
+                               _ptr(ln_g), _ptr(ln_b), ln_eps, _ptr(seq_len), cluster, _ptr(out), _stream()))
     return out
 
 

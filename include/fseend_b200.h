@@ -76,6 +76,11 @@ int fseend_fs_forward(fseend_fs_model* m, const float* x_packed_dev, const int* 
 int fseend_fs_forward_host(fseend_fs_model* m, const float* x_packed_host, const int* ilens_host, int B,
                            int max_nspks, float* logits_host, float* emb_host, float* att_host);
 
+/* Tuning switches.  "ffn": 0 = two GEMM launches (hidden activations through HBM), 1 = fused FFN kernel,
+ * 2 = fused FFN with 2-CTA clusters sharing weight tiles by TMA multicast (default).
+ * "spk": 0 = CUDA-core speaker attention, 1 = tcgen05 block-diagonal attention (default). */
+int fseend_fs_set_option(fseend_fs_model* m, const char* key, int value);
+
 /* Per-kernel timing of the next forward calls (CUDA events around every launch; off by default).
  * get_profile returns the number of distinct kernels; names[i] (<= 31 chars), total ms and launch count
  * accumulated since profiling was switched on. */
@@ -95,10 +100,18 @@ int fseend_op_gemm(const void* a_f16, int rows_per_seq, int n_seq, int K, const 
                    int tap_shift, int mode, int relu, const float* bias, const void* residual_f16,
                    const float* ln_g, const float* ln_b, float ln_eps, const float* pe_proj, int S,
                    const int* seq_len_dev, void* out_f16, void* stream);
+/* OUT = LayerNorm(X + relu(X W1^T + b1) W2^T + b2): X fp16 [n_seq][rows_per_seq][256], W1 fp16 [F][256],
+ * W2 fp16 [256][F]; the F-wide hidden activations stay on chip.  cluster: 1 or 2 (weight multicast). */
+int fseend_op_ffn(const void* x_f16, int rows_per_seq, int n_seq, const void* w1_f16, const float* b1,
+                  const void* w2_f16, const float* b2, int F, const float* ln_g, const float* ln_b, float ln_eps,
+                  const int* seq_len_dev, int cluster, void* out_f16, void* stream);
 /* qkv fp16 [B][T][S][768] -> out fp16 [B][T][S][256]; key j visible to query i iff j <= i + mask_delay. */
 int fseend_op_causal_attn(const void* qkv_f16, int B, int T, int S, int H, int mask_delay, float scale,
                           void* out_f16, void* stream);
+/* Speaker-axis attention, qkv fp16 [n_frames][S][768] -> out fp16 [n_frames][S][256]: CUDA-core kernel and the
+ * tcgen05 block-diagonal variant (the one the model uses). */
 int fseend_op_spk_attn(const void* qkv_f16, int n_frames, int S, float scale, void* out_f16, void* stream);
+int fseend_op_spk_attn_tc(const void* qkv_f16, int n_frames, int S, float scale, void* out_f16, void* stream);
 int fseend_op_head(const void* emb_f16, const void* att_f16, int n_frames, int S, float* logits, float* emb_f32,
                    float* att_f32, void* stream);
 int fseend_op_prep_input(const float* x_packed, const int* cu_seqlens_dev, int B, int Tmax, int Din, int Kpad,

@@ -154,3 +154,50 @@ def test_prep_input(N):
         ref[b, l:, :Din] = -1.0 * sc + sh
         off += l
     assert torch.equal(out, ref.half())
+
+
+@pytest.mark.parametrize("S", [4, 6, 10, 16])
+def test_speaker_attention_tensor_core(N, S):
+    """Block-diagonal tcgen05 variant (the one the model uses) vs fp32 torch."""
+    F = 777
+    qkv = rnd(F, S, 768, seed=40 + S).half()
+    out = N.op_spk_attn(qkv, tensor_core=True)
+    x = qkv.float().view(F, S, 3, 4, 64)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    o = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v
+    ref = o.transpose(1, 2).reshape(F, S, 256)
+    assert (out.float() - ref).abs().max().item() < 4e-3
+
+
+def ffn_ref(x, w1, b1, w2, b2, g, b):
+    h = torch.relu(x.float() @ w1.float().T + b1).half().float()      # hidden activations are fp16 on chip
+    return ln_ref(x.float() + h @ w2.float().T + b2, g, b)
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("rows,F", [(300, 2048), (128 * 5, 256), (1, 1024)])
+def test_fused_ffn(N, cluster, rows, F):
+    x = rnd(rows, 256, seed=60).half()
+    w1 = rnd(F, 256, scale=1 / 16, seed=61).half()
+    w2 = rnd(256, F, scale=1 / math.sqrt(F), seed=62).half()
+    b1, b2 = rnd(F, seed=63) * 0.5, rnd(256, seed=64) * 0.5
+    g, b = 1 + 0.3 * rnd(256, seed=65), 0.1 * rnd(256, seed=66)
+    out = N.op_ffn(x, w1, b1, w2, b2, g, b, cluster=cluster)
+    ref = ffn_ref(x, w1, b1, w2, b2, g, b)
+    assert (out.float() - ref).abs().max().item() < 6e-3
+
+
+def test_fused_ffn_per_sequence_zero_rows(N):
+    n_seq, T, F = 3, 150, 512
+    x = rnd(n_seq * T, 256, seed=70).half()
+    w1 = rnd(F, 256, scale=1 / 16, seed=71).half()
+    w2 = rnd(256, F, scale=1 / 22, seed=72).half()
+    b1, b2 = rnd(F, seed=73) * 0.5, rnd(256, seed=74) * 0.5
+    g, b = 1 + 0.3 * rnd(256, seed=75), 0.1 * rnd(256, seed=76)
+    lens = torch.tensor([150, 77, 1], dtype=torch.int32, device=DEV)
+    out = N.op_ffn(x, w1, b1, w2, b2, g, b, n_seq=n_seq, seq_len=lens, cluster=2).view(n_seq, T, 256)
+    ref = ffn_ref(x, w1, b1, w2, b2, g, b).view(n_seq, T, 256)
+    for i, l in enumerate(lens.tolist()):
+        assert (out[i, :l].float() - ref[i, :l]).abs().max().item() < 6e-3
+        if l < T:
+            assert out[i, l:].abs().max().item() == 0

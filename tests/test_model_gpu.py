@@ -99,3 +99,17 @@ def test_weight_update_rebuilds_native_model():
     with torch.no_grad():
         ref = O.test({k: v.cpu() for k, v in sd2.items()}, src, lens, 4, O.Cfg())[0][0]
     assert (b.cpu() - ref).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("ffn,spk", [(0, 0), (1, 1), (2, 1)])
+def test_kernel_variants_agree_with_reference(ffn, spk):
+    """Every selectable kernel variant (unfused / fused / fused+multicast FFN; CUDA-core / tcgen05 speaker
+    attention) meets the same 1e-3 bound."""
+    sd, src, lens, S, cfg, g = load_case("ragged_S6")
+    m = make_model(sd)
+    m.native().set_option("ffn", ffn)
+    m.native().set_option("spk", spk)
+    out = m.test_logits([s.cuda() for s in src], lens, max_nspks=S)
+    worst = max(float(np.abs(o.cpu().numpy() - g[f"logits_{i}"]).max()) for i, o in enumerate(out))
+    print(f"ffn={ffn} spk={spk}: max-abs logit error vs reference = {worst:.2e}")
+    assert worst < TOL
