@@ -205,6 +205,9 @@ def run_ours(args):
         n_speakers=4, in_size=DIN, n_units=D, n_heads=H, enc_n_layers=ENC_L, dec_n_layers=DEC_L, dropout=0.1,
         has_mask=True, max_seqlen=T, dec_dim_feedforward=FF).cuda().eval()
     native = model.native()
+    for kv in filter(None, os.environ.get("FSEEND_OPTS", "").split(",")):   # e.g. FSEEND_OPTS=ffn=2,spk=0 (kernel variants)
+        k, v = kv.split("=")
+        native.set_option(k, int(v))
     lens = [T] * B
     gen = torch.Generator(device="cpu").manual_seed(777 + rank)
     n_buf = 4   # 4 x 44 MB of inputs > 126 MB L2: inputs are never L2-warm
@@ -312,6 +315,7 @@ def run_ours(args):
         "roofline_attention": roof_attn,
         "cpu_baseline": cpu,
         "kernels": prof_table,
+        "options": os.environ.get("FSEEND_OPTS", "default"),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

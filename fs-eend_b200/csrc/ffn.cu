@@ -20,16 +20,22 @@ namespace fseend {
 namespace {
 
 constexpr int kRows = 128;
-constexpr int kD = 256;
 constexpr int kChunk = 128;                 // hidden units per chunk
 constexpr int kSlotBytes = 128 * 64 * 2;    // 16 KB
 constexpr int kXBytes = 4 * kSlotBytes;     // 64 KB: X tile as 4 k-sub-tiles
 constexpr int kPBytes = 2 * kSlotBytes;     // 32 KB per P buffer (2 k-sub-tiles)
-constexpr int kSlots = 6;
 constexpr int kOffX = 0;
-constexpr int kOffP = kOffX + kXBytes;              // 2 buffers
-constexpr int kOffW = kOffP + 2 * kPBytes;
-constexpr int kSmemBytes = kOffW + kSlots * kSlotBytes + 1024;
+// SS variant: P (fp16 hidden chunk) double-buffered in smem, 6-slot weight ring.
+// TS variant: P lives in TMEM (aliasing the GEMM1 accumulator it was computed from) and is the A operand of
+//             GEMM2 straight from TMEM; the 64 KB this frees go to the weight ring (10 slots).
+template <bool kTS> struct Lay {
+  static constexpr int kSlots = kTS ? 10 : 6;
+  static constexpr int kOffP = kOffX + kXBytes;                         // SS only: 2 buffers
+  static constexpr int kOffW = kTS ? kOffX + kXBytes : kOffP + 2 * kPBytes;
+  static constexpr int kOffStage = kTS ? kOffW : kOffP;                 // 64 KB output staging after the last MMA
+};
+constexpr int kMaxSlots = 10;
+constexpr int kSmemBytes = kXBytes + 2 * kPBytes + 6 * kSlotBytes + 1024;   // = 64 + 160 KB + slack, both variants
 constexpr uint32_t kTmemCols = 512;                  // Y [0,256), H0 [256,384), H1 [384,512)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -54,6 +60,29 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
       ::"r"(smem_u32(bar)), "h"(mask)
       : "memory");
 }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]: A is M x K fp16 packed two per 32-bit TMEM column (lane = row).
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld32_sync(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -100,14 +129,18 @@ __device__ __forceinline__ void tile_write32(uint8_t* tile, int r, int c, const 
   }
 }
 
-template <int kCluster>
+template <int kCluster, bool kTS>
 __global__ void __launch_bounds__(192, 1)
 ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
            const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO, const FfnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t x_full, w_full[kSlots], w_empty[kSlots], h_full[2], h_empty[2], p_full[2],
+  constexpr int kSlots = Lay<kTS>::kSlots;
+  constexpr int kOffP = Lay<kTS>::kOffP;
+  constexpr int kOffW = Lay<kTS>::kOffW;
+  __shared__ __align__(8) uint64_t x_full, w_full[kMaxSlots], w_empty[kMaxSlots], h_full[2], h_empty[2], p_full[2],
       p_empty[2], y_full;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float b1_smem[2][kChunk];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x;
@@ -196,8 +229,10 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       };
       auto gemm1 = [&](int j) {
         const int hb = j & 1;
-        mbar_wait(&h_empty[hb], ((j >> 1) & 1) ^ 1, 32);     // epilogue has drained H(j-2)
-        tc_fence_after();
+        if (!kTS) {
+          mbar_wait(&h_empty[hb], ((j >> 1) & 1) ^ 1, 32);   // epilogue has drained H(j-2)
+          tc_fence_after();
+        }   // TS: H(j) aliases P(j-2), whose GEMM2 precedes this GEMM1 in the in-order tensor pipe
         const uint32_t tmem_H = tmem_base + 256 + hb * 128;
         for (int ks = 0; ks < 4; ++ks) {
           const int s = use % kSlots;
@@ -222,11 +257,18 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           mbar_wait(&w_full[s0], (use / kSlots) & 1, 35);
           mbar_wait(&w_full[s0 + 1], ((use + 1) / kSlots) & 1, 36);
           tc_fence_after();
-          const uint64_t adesc = smem_desc_sw128(smem_u32(smem + kOffP + pb * kPBytes + ks2 * kSlotBytes));
           const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + kOffW + s0 * kSlotBytes));
+          if (kTS) {
+            const uint32_t tmem_P = tmem_base + 256 + pb * 128 + ks2 * 32;   // 64 hidden = 32 packed columns
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_f16(tmem_Y, adesc + 2 * kk, bdesc + 2 * kk, idesc_g2, (j > 0 || ks2 > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16_ts(tmem_Y, tmem_P + 8 * kk, bdesc + 2 * kk, idesc_g2, (j > 0 || ks2 > 0 || kk > 0) ? 1u : 0u);
+          } else {
+            const uint64_t adesc = smem_desc_sw128(smem_u32(smem + kOffP + pb * kPBytes + ks2 * kSlotBytes));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(tmem_Y, adesc + 2 * kk, bdesc + 2 * kk, idesc_g2, (j > 0 || ks2 > 0 || kk > 0) ? 1u : 0u);
+          }
           release_slot(s0);
           release_slot(s0 + 1);
           use += 2;
@@ -249,32 +291,70 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     const int r = quarter * 32 + lane;            // tile row
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     float acc[32], aux[32];
+    const int et = tid - 64;                       // 0..127 among the epilogue threads
+    float b1_next = __ldg(p.b1 + et);              // bias of chunk 0, one element per thread
     for (int j = 0; j < n_chunks; ++j) {
       const int hb = j & 1;
+      // stage this chunk's 128 bias values in smem (double-buffered), prefetch the next chunk's
+      b1_smem[hb][et] = b1_next;
+      if (j + 1 < n_chunks) b1_next = __ldg(p.b1 + (j + 1) * kChunk + et);
+      named_bar_sync(2, 128);
       mbar_wait(&h_full[hb], (j >> 1) & 1, 40);
       tc_fence_after();
-      if (j >= 2) mbar_wait(&p_empty[hb], ((j >> 1) & 1) ^ 1, 41);   // GEMM2(j-2) has consumed this P buffer
+      if (!kTS && j >= 2) mbar_wait(&p_empty[hb], ((j >> 1) & 1) ^ 1, 41);   // GEMM2(j-2) has consumed this P buffer
       uint8_t* ptile = smem + kOffP + hb * kPBytes;
       const uint32_t tH = tmem_base + 256 + hb * 128 + lane_base;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld32_sync(tH + c * 32, acc);
-        load_vec32(p.b1 + j * kChunk + c * 32, aux);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i] + aux[i], 0.f);
-        tile_write32(ptile, r, c, acc);
+      for (int half = 0; half < 2; ++half) {
+        // two 32-column TMEM loads in flight per wait
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tH + half * 64, r0);
+        tmem_ld32(tH + half * 64 + 32, r1);
+        tmem_ld_wait();
+        const float4* bs = reinterpret_cast<const float4*>(&b1_smem[hb][half * 64]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = bs[i];     // same address in every lane: shared-memory broadcast
+          acc[4 * i + 0] = fmaxf(__uint_as_float(r0[4 * i + 0]) + t.x, 0.f);
+          acc[4 * i + 1] = fmaxf(__uint_as_float(r0[4 * i + 1]) + t.y, 0.f);
+          acc[4 * i + 2] = fmaxf(__uint_as_float(r0[4 * i + 2]) + t.z, 0.f);
+          acc[4 * i + 3] = fmaxf(__uint_as_float(r0[4 * i + 3]) + t.w, 0.f);
+        }
+        if (kTS) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r0[i] = pack_half2(acc[2 * i], acc[2 * i + 1]);
+        } else {
+          tile_write32(ptile, r, half * 2, acc);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = bs[8 + i];
+          acc[4 * i + 0] = fmaxf(__uint_as_float(r1[4 * i + 0]) + t.x, 0.f);
+          acc[4 * i + 1] = fmaxf(__uint_as_float(r1[4 * i + 1]) + t.y, 0.f);
+          acc[4 * i + 2] = fmaxf(__uint_as_float(r1[4 * i + 2]) + t.z, 0.f);
+          acc[4 * i + 3] = fmaxf(__uint_as_float(r1[4 * i + 3]) + t.w, 0.f);
+        }
+        if (kTS) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r0[16 + i] = pack_half2(acc[2 * i], acc[2 * i + 1]);
+          // P(j) overwrites the H(j) columns this thread has already consumed: packed columns [half*32, +32)
+          tmem_st32(tH + half * 32, r0);
+        } else {
+          tile_write32(ptile, r, half * 2 + 1, acc);
+        }
       }
-      fence_proxy_async_smem();
+      if (kTS) tmem_st_wait();
+      if (!kTS) fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[hb]);
-      mbar_arrive(&h_empty[hb]);
+      if (!kTS) mbar_arrive(&h_empty[hb]);
     }
     // ---- final: Y + b2 + X -> LayerNorm -> fp16 -> staging (P buffers, 64 KB) -> TMA store
     mbar_wait(&y_full, 0, 42);
     mbar_wait(&x_full, 0, 43);   // residual tile (long since landed; makes the TMA write visible to this thread)
     tc_fence_after();
     const uint8_t* xtile = smem + kOffX;
-    uint8_t* staging = smem + kOffP;
+    uint8_t* staging = smem + Lay<kTS>::kOffStage;
     const uint32_t tY = tmem_Y + lane_base;
     float n = 0.f, mean = 0.f, m2 = 0.f;
 #pragma unroll 1
@@ -337,36 +417,40 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-}  // namespace
-
-void launch_ffn(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmO,
-                const FfnParams& p, int cluster, cudaStream_t stream) {
+template <int kCluster, bool kTS>
+void launch_ffn_t(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmO,
+                  const FfnParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(ffn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(ffn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(ffn_kernel<kCluster, kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     attr_set = true;
   }
-  int tiles = p.n_seq * p.tiles_per_seq;
+  const int tiles = p.n_seq * p.tiles_per_seq;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  if (cluster == 2) {
-    cfg.gridDim = dim3((tiles + 1) / 2 * 2);   // odd tile count: the last CTA runs on zero-filled rows, stores clip
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, ffn_kernel<2>, tmX, tmW1, tmW2, tmO, p);
-  } else {
-    cfg.gridDim = dim3(tiles);
-    cfg.attrs = nullptr;
-    cfg.numAttrs = 0;
-    cudaLaunchKernelEx(&cfg, ffn_kernel<1>, tmX, tmW1, tmW2, tmO, p);
+  cfg.gridDim = dim3((tiles + kCluster - 1) / kCluster * kCluster);   // odd count: the extra CTA sees zero rows, stores clip
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, ffn_kernel<kCluster, kTS>, tmX, tmW1, tmW2, tmO, p);
+}
+
+}  // namespace
+
+// variant: 1 = SS, 2 = SS + 2-CTA multicast, 3 = TS (P in TMEM), 4 = TS + 2-CTA multicast
+void launch_ffn(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmO,
+                const FfnParams& p, int variant, cudaStream_t stream) {
+  switch (variant) {
+    case 1: launch_ffn_t<1, false>(tmX, tmW1, tmW2, tmO, p, stream); break;
+    case 2: launch_ffn_t<2, false>(tmX, tmW1, tmW2, tmO, p, stream); break;
+    case 3: launch_ffn_t<1, true>(tmX, tmW1, tmW2, tmO, p, stream); break;
+    default: launch_ffn_t<2, true>(tmX, tmW1, tmW2, tmO, p, stream); break;
   }
 }
 

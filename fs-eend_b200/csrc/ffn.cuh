@@ -19,8 +19,9 @@ struct FfnParams {
 };
 
 // tmX / tmO: 3-D (256, rows_per_seq, n_seq) box (64,128,1);  tmW1: 2-D (256, F) box (64,128);
-// tmW2: 2-D (F, 256) box (64,128).  cluster: 1, or 2 (CTA pairs share weight tiles through TMA multicast).
+// tmW2: 2-D (F, 256) box (64,128).  variant: 1 = SS, 2 = SS + 2-CTA weight multicast, 3 = TS (hidden chunk in TMEM),
+// 4 = TS + multicast.
 void launch_ffn(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmO,
-                const FfnParams& p, int cluster, cudaStream_t stream);
+                const FfnParams& p, int variant, cudaStream_t stream);
 
 }  // namespace fseend

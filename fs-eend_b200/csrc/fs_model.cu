@@ -128,7 +128,8 @@ struct fseend_fs_model {
   CUtensorMap tm_aX, tm_aY, tm_aZ, tm_qkv_d_out, tm_qkv_d_attn, tm_ao_d_attn, tm_qkv_d_spk, tm_ao_d_spk, tm_ao_d, tm_f_d_out, tm_f_d_in;
 
   int spk_mode = 1;  // 0: CUDA-core speaker attention, 1: tcgen05 block-diagonal attention
-  int ffn_mode = 2;  // 0: two GEMM launches (hidden layer through HBM), 1: fused kernel, 2: fused + 2-CTA weight multicast
+  int ffn_mode = 3;  // 0: two GEMM launches (hidden layer through HBM); fused: 1 = SS, 2 = SS + 2-CTA weight multicast,
+                     // 3 = TS (hidden chunk stays in TMEM), 4 = TS + multicast
   bool profiling = false;
   std::vector<ProfEntry> prof_pending;
   std::map<std::string, std::pair<double, int>> prof_acc;
@@ -804,7 +805,7 @@ int fseend_op_gemm(const void* a_f16, int rows_per_seq, int n_seq, int K, const 
 
 int fseend_fs_set_option(fseend_fs_model* m, const char* key, int value) {
   if (!m || !key) return FSEEND_ERR_INVALID;
-  if (strcmp(key, "ffn") == 0 && value >= 0 && value <= 2) {
+  if (strcmp(key, "ffn") == 0 && value >= 0 && value <= 4) {
     m->ffn_mode = value;
     return FSEEND_OK;
   }
@@ -821,7 +822,7 @@ int fseend_op_ffn(const void* x_f16, int rows_per_seq, int n_seq, const void* w1
                   const int* seq_len_dev, int cluster, void* out_f16, void* stream) {
   return guarded([&] {
     if (F % 128 || F < 128) throw std::invalid_argument("F must be a multiple of 128");
-    if (cluster != 1 && cluster != 2) throw std::invalid_argument("cluster must be 1 or 2");
+    if (cluster < 1 || cluster > 4) throw std::invalid_argument("variant must be 1..4");
     if (!fseend_device_ok()) throw std::invalid_argument("sm_100 device required");
     FfnParams p{};
     p.rows_per_seq = rows_per_seq;

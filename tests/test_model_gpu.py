@@ -72,7 +72,9 @@ def test_full_size_properties_B64_T500_S6():
     assert y.shape == (64, 500, 6) and torch.isfinite(y).all() and y.abs().max() <= 1.0 + 1e-3
     for b in (0, 17, 63):
         alone = m.test_logits([srcc[b]], [500], 6)[0]
-        assert (alone - y[b]).abs().max().item() < 1e-6
+        # not bit-exact: the speaker-attention tile (21 frames) a frame falls into depends on its global row, and
+        # the fp16 partial row sums of P are grouped by tile column -> differences at the fp16-rounding level
+        assert (alone - y[b]).abs().max().item() < 5e-4
     with torch.no_grad():
         ref = O.test(sd, [src[5]], [500], 6, O.Cfg())[0][0]
     err = (y[5].cpu() - ref).abs().max().item()
@@ -101,7 +103,7 @@ def test_weight_update_rebuilds_native_model():
     assert (b.cpu() - ref).abs().max().item() < TOL
 
 
-@pytest.mark.parametrize("ffn,spk", [(0, 0), (1, 1), (2, 1)])
+@pytest.mark.parametrize("ffn,spk", [(0, 0), (1, 1), (2, 1), (3, 1), (4, 1)])
 def test_kernel_variants_agree_with_reference(ffn, spk):
     """Every selectable kernel variant (unfused / fused / fused+multicast FFN; CUDA-core / tcgen05 speaker
     attention) meets the same 1e-3 bound."""
