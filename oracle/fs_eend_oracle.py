@@ -34,6 +34,12 @@ def _ident(x: Tensor) -> Tensor:
     return x
 
 
+# bench.py's CPU arm sets this: attention then goes through torch's fused CPU SDPA kernel — the code path the
+# reference's nn.MultiheadAttention takes under torch >= 2 — instead of the explicit
+# softmax(QK^T)V below.  Same arithmetic (tests/test_oracle.py checks it), faster baseline.
+USE_SDPA = False
+
+
 class Cfg:
     """Hyper-parameters the reference passes as constructor kwargs (FS:model:11)."""
 
@@ -88,11 +94,14 @@ def mha(x: Tensor, sd: SD, prefix: str, n_heads: int, mask: Optional[Tensor], qu
     q = q.reshape(N, L, n_heads, hd).transpose(1, 2)
     k = k.reshape(N, L, n_heads, hd).transpose(1, 2)
     v = v.reshape(N, L, n_heads, hd).transpose(1, 2)
-    s = (quant(q) @ quant(k).transpose(-1, -2)) * (hd ** -0.5)
-    if mask is not None:
-        s = s + mask
-    p = torch.softmax(s, dim=-1)
-    o = quant(p) @ quant(v)                       # (N, H, L, hd)
+    if USE_SDPA and quant is _ident:
+        o = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask)
+    else:
+        s = (quant(q) @ quant(k).transpose(-1, -2)) * (hd ** -0.5)
+        if mask is not None:
+            s = s + mask
+        p = torch.softmax(s, dim=-1)
+        o = quant(p) @ quant(v)                   # (N, H, L, hd)
     o = o.transpose(1, 2).reshape(N, L, E)
     return linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"], quant)
 

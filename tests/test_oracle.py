@@ -87,3 +87,15 @@ def test_fp16_operand_emulation_within_tolerance():
     eb = max(np.abs(o.numpy() - g[f"logits_{i}"]).max() for i, o in enumerate(ob))
     assert e16 < 5e-4
     assert eb > e16
+
+
+def test_sdpa_fast_path_of_the_cpu_arm_is_the_same_arithmetic():
+    sd, src, lens, S, cfg, g = load_case("maskdelay2_S5")
+    with torch.no_grad():
+        a = O.test(sd, src, lens, S, cfg)[0]
+        O.USE_SDPA = True
+        try:
+            b = O.test(sd, src, lens, S, cfg)[0]
+        finally:
+            O.USE_SDPA = False
+    assert max((x - y).abs().max().item() for x, y in zip(a, b)) < 2e-5
