@@ -190,6 +190,92 @@ head_kernel(const __half* __restrict__ emb, const __half* __restrict__ att, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming (frame-by-frame) attention step: one new query row per sequence attends over the projected K/V cache
+// [n_seq][cap][256] (the reference re-projects its cached layer inputs every step, FS:stream_mod:28-35 — same
+// arithmetic).  The block first appends this frame's K/V at `pos`, then attends over keys 0..pos.
+// grid (n_seq, 4 heads), 128 threads: keys are strided over threads, partial softmax states merged through smem.
+__global__ void __launch_bounds__(128)
+step_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache, int cap,
+                 int pos, float scale, __half* __restrict__ out) {
+  const int n = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  __shared__ float q_s[64];
+  __shared__ float red_m[128], red_l[128];
+  __shared__ float red_o[4][64];
+  const __half* row = qkv + static_cast<size_t>(n) * 768;
+  __half* kc = kcache + (static_cast<size_t>(n) * cap) * 256 + h * 64;
+  __half* vc = vcache + (static_cast<size_t>(n) * cap) * 256 + h * 64;
+  if (tid < 64) {
+    q_s[tid] = __half2float(row[h * 64 + tid]) * scale * 1.4426950408889634f;
+    kc[static_cast<size_t>(pos) * 256 + tid] = row[256 + h * 64 + tid];
+    vc[static_cast<size_t>(pos) * 256 + tid] = row[512 + h * 64 + tid];
+  }
+  __syncthreads();
+  float m = -INFINITY, l = 0.f, o[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) o[i] = 0.f;
+  for (int j = tid; j <= pos; j += 128) {
+    const uint4* kp = reinterpret_cast<const uint4*>(kc + static_cast<size_t>(j) * 256);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint4 u = kp[i];
+      const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = __half22float2(hh[t]);
+        s = fmaf(q_s[i * 8 + 2 * t], f.x, s);
+        s = fmaf(q_s[i * 8 + 2 * t + 1], f.y, s);
+      }
+    }
+    const float m_new = fmaxf(m, s);
+    const float a = exp2f(m - m_new), pj = exp2f(s - m_new);
+    l = l * a + pj;
+    const uint4* vp = reinterpret_cast<const uint4*>(vc + static_cast<size_t>(j) * 256);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint4 u = vp[i];
+      const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = __half22float2(hh[t]);
+        o[i * 8 + 2 * t] = fmaf(pj, f.x, o[i * 8 + 2 * t] * a);
+        o[i * 8 + 2 * t + 1] = fmaf(pj, f.y, o[i * 8 + 2 * t + 1] * a);
+      }
+    }
+    m = m_new;
+  }
+  // merge the 128 partial (m, l, o) states
+  red_m[tid] = m;
+  __syncthreads();
+  float gm = -INFINITY;
+  for (int i = 0; i < 128; ++i) gm = fmaxf(gm, red_m[i]);   // smem broadcast reads
+  const float w = (m == -INFINITY) ? 0.f : exp2f(m - gm);
+  red_l[tid] = l * w;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    float v = o[i] * w;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((tid & 31) == 0) red_o[tid >> 5][i] = v;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float lt = 0.f;
+    for (int i = 0; i < 128; ++i) lt += red_l[i];
+    const float v = red_o[0][tid] + red_o[1][tid] + red_o[2][tid] + red_o[3][tid];
+    out[static_cast<size_t>(n) * 256 + h * 64 + tid] = __float2half_rn(v / lt);
+  }
+}
+
+// rows [n_seq] of width 256 copied (or zero-filled when src == nullptr) into hist[n][pos]
+__global__ void hist_append_kernel(const __half* __restrict__ src, __half* __restrict__ hist, int cap, int pos) {
+  const int n = blockIdx.x;
+  const uint32_t* s = src ? reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(n) * 256) : nullptr;
+  uint32_t* d = reinterpret_cast<uint32_t*>(hist + (static_cast<size_t>(n) * cap + pos) * 256);
+  d[threadIdx.x] = s ? s[threadIdx.x] : 0u;
+}
+
 }  // namespace
 
 void launch_prep_input(const float* x, const int* cu_seqlens, int B, int Tmax, int Din, int Kpad, const float* sc,
@@ -211,6 +297,15 @@ void launch_head(const __half* emb, const __half* att, int n_frames, int S, floa
   const int warps_per_block = 8;
   const int grid = (n_frames + warps_per_block - 1) / warps_per_block;
   head_kernel<<<grid, warps_per_block * 32, 0, stream>>>(emb, att, n_frames, S, logits, emb_f32, att_f32);
+}
+
+void launch_step_attn(const __half* qkv, __half* kcache, __half* vcache, int n_seq, int cap, int pos, float scale,
+                      __half* out, cudaStream_t stream) {
+  step_attn_kernel<<<dim3(n_seq, 4), 128, 0, stream>>>(qkv, kcache, vcache, cap, pos, scale, out);
+}
+
+void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int pos, cudaStream_t stream) {
+  hist_append_kernel<<<n_seq, 128, 0, stream>>>(src, hist, cap, pos);
 }
 
 }  // namespace fseend

@@ -18,4 +18,11 @@ int launch_spk_attn(const __half* qkv, __half* out, int n_frames, int S, float s
 void launch_head(const __half* emb, const __half* att, int n_frames, int S, float* logits, float* emb_f32,
                  float* att_f32, cudaStream_t stream);
 
+// Streaming step: append this frame's K/V (from qkv [n_seq][768]) to the caches [n_seq][cap][256] at `pos`, then
+// attend the single query row over keys 0..pos.  out: [n_seq][256] fp16.
+void launch_step_attn(const __half* qkv, __half* kcache, __half* vcache, int n_seq, int cap, int pos, float scale,
+                      __half* out, cudaStream_t stream);
+// hist[n][pos][:] = src[n][:] (or zeros when src == nullptr); hist: [n_seq][cap][256] fp16.
+void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int pos, cudaStream_t stream);
+
 }  // namespace fseend

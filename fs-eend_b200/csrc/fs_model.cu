@@ -140,6 +140,22 @@ struct fseend_fs_model {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Frame-by-frame streaming state (reference: StreamingTransformerEDADiarization.test, FS:stream_model:31-60 and
+// FS:stream_mod:82-269).  Device-resident: projected K/V caches per layer (the reference caches layer inputs and
+// re-projects them every step — identical arithmetic, O(t·d²) less work), the encoder-output history that feeds
+// the look-ahead conv, and one-tile workspaces.
+struct fseend_fs_stream {
+  fseend_fs_model* m = nullptr;
+  int B = 0, S = 0;
+  int cap = 0;        // frames of capacity in every cache
+  int t = 0;          // frames pushed so far (real + flush)
+  std::vector<std::unique_ptr<DevBuf>> enc_k, enc_v, dec_k, dec_v;
+  DevBuf hist, x16, h0, h1, qkv, ao, a0, a1, a2, emb, cu;
+  CUtensorMap tm_x16, tm_h0, tm_h1, tm_qkv_e, tm_ao_e, tm_hist, tm_emb_out, tm_emb_in, tm_cvt_out, tm_a0, tm_a1, tm_a2,
+      tm_qkv_d, tm_ao_d, tm_qkv_spk, tm_ao_spk;
+};
+
 namespace fseend {
 namespace {
 
@@ -596,6 +612,211 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
   CUDA_CHECK(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------ streaming
+void stream_alloc(fseend_fs_stream* s, int cap) {
+  const fseend_fs_config& c = s->m->cfg;
+  const int D = c.n_units, B = s->B, S = s->S;
+  auto grow = [&](DevBuf& buf, size_t n_seq) {
+    DevBuf nb;
+    nb.alloc(n_seq * cap * D * 2);
+    CUDA_CHECK(cudaMemset(nb.p, 0, nb.bytes));
+    if (buf.p && s->cap > 0)
+      CUDA_CHECK(cudaMemcpy2D(nb.p, 1ull * cap * D * 2, buf.p, 1ull * s->cap * D * 2, 1ull * s->cap * D * 2, n_seq,
+                              cudaMemcpyDeviceToDevice));
+    std::swap(buf.p, nb.p);
+    std::swap(buf.bytes, nb.bytes);
+  };
+  CUDA_CHECK(cudaDeviceSynchronize());
+  for (auto& b : s->enc_k) grow(*b, B);
+  for (auto& b : s->enc_v) grow(*b, B);
+  for (auto& b : s->dec_k) grow(*b, 1ull * B * S);
+  for (auto& b : s->dec_v) grow(*b, 1ull * B * S);
+  grow(s->hist, B);
+  s->cap = cap;
+  s->tm_hist = make_tmap_rows3d(s->hist.p, D, D, cap, B, 128);
+}
+
+void stream_init(fseend_fs_stream* s, fseend_fs_model* m, int B, int S) {
+  const fseend_fs_config& c = m->cfg;
+  const int D = c.n_units;
+  s->m = m;
+  s->B = B;
+  s->S = S;
+  for (int l = 0; l < c.enc_n_layers; ++l) {
+    s->enc_k.push_back(std::make_unique<DevBuf>());
+    s->enc_v.push_back(std::make_unique<DevBuf>());
+  }
+  for (int l = 0; l < c.dec_n_layers; ++l) {
+    s->dec_k.push_back(std::make_unique<DevBuf>());
+    s->dec_v.push_back(std::make_unique<DevBuf>());
+  }
+  const size_t Rd = 1ull * B * S;
+  s->x16.alloc(1ull * B * m->Kin * 2);
+  s->h0.alloc(1ull * B * D * 2);
+  s->h1.alloc(1ull * B * D * 2);
+  s->qkv.alloc(Rd * 3 * D * 2);
+  s->ao.alloc(Rd * D * 2);
+  s->a0.alloc(Rd * D * 2);
+  s->a1.alloc(Rd * D * 2);
+  s->a2.alloc(Rd * D * 2);
+  s->emb.alloc(1ull * B * D * 2);
+  {
+    std::vector<int> cu(B + 1);
+    for (int i = 0; i <= B; ++i) cu[i] = i;
+    s->cu.alloc((B + 1) * sizeof(int));
+    CUDA_CHECK(cudaMemcpy(s->cu.p, cu.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  s->tm_x16 = rows_map(s->x16, m->Kin, B, 1);
+  s->tm_h0 = rows_map(s->h0, D, B, 1);
+  s->tm_h1 = rows_map(s->h1, D, B, 1);
+  s->tm_qkv_e = rows_map(s->qkv, 3 * D, B, 1);
+  s->tm_ao_e = rows_map(s->ao, D, B, 1);
+  s->tm_emb_out = rows_map(s->emb, D, 1, B);     // one output row per sequence
+  s->tm_emb_in = rows_map(s->emb, D, B, 1);
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(S), static_cast<uint64_t>(B)};
+    uint64_t str[2] = {static_cast<uint64_t>(D), static_cast<uint64_t>(D) * S};
+    uint32_t box[3] = {64, 1, 128};
+    s->tm_cvt_out = make_tmap_f16(s->a0.p, 3, dims, str, box);
+  }
+  s->tm_a0 = rows_map(s->a0, D, Rd, 1);
+  s->tm_a1 = rows_map(s->a1, D, Rd, 1);
+  s->tm_a2 = rows_map(s->a2, D, Rd, 1);
+  s->tm_qkv_d = rows_map(s->qkv, 3 * D, Rd, 1);
+  s->tm_ao_d = rows_map(s->ao, D, Rd, 1);
+  {
+    uint64_t dq[4] = {static_cast<uint64_t>(3 * D), 1, Rd, 1}, sq[3] = {3ull * D, 3ull * D, 3ull * D * Rd};
+    uint64_t d_o[4] = {static_cast<uint64_t>(D), 1, Rd, 1}, so[3] = {1ull * D, 1ull * D, 1ull * D * Rd};
+    uint32_t bq[4] = {64, 1, 128, 1}, bo[4] = {64, 1, static_cast<uint32_t>((128 / S) * S), 1};
+    s->tm_qkv_spk = make_tmap_f16(s->qkv.p, 4, dq, sq, bq);
+    s->tm_ao_spk = make_tmap_f16(s->ao.p, 4, d_o, so, bo);
+  }
+  stream_alloc(s, 1024);
+}
+
+// One frame.  x_t: device fp32 [B][in_size], or nullptr for a flush step (the reference's dummy_conv_input).
+// Returns 1 and writes logits [B][S] when the look-ahead conv has a full window, else 0.
+int stream_step(fseend_fs_stream* s, const float* x_t, float* logits, cudaStream_t st) {
+  fseend_fs_model* m = s->m;
+  const fseend_fs_config& c = m->cfg;
+  const int D = c.n_units, B = s->B, S = s->S;
+  if (B * S > 128) throw std::invalid_argument("streaming supports B * max_nspks <= 128");
+  if (s->t + 1 > s->cap) stream_alloc(s, s->cap * 2);
+  const float scale = 1.f / sqrtf(64.f);
+  CUtensorMap none = s->tm_h0;
+  const int pos = s->t;          // index of this frame in the encoder history
+  if (x_t) {
+    launch_prep_input(x_t, static_cast<const int*>(s->cu.p), B, 1, c.in_size, m->Kin, m->bn_scale.f(), m->bn_shift.f(),
+                      static_cast<__half*>(s->x16.p), st);
+    {
+      GemmParams p = flat_params(B, D, m->Kin, EPI_LN);
+      p.bias = m->b_in.f();
+      p.ln_g = m->g_in.f();
+      p.ln_b = m->be_in.f();
+      p.ln_eps = c.ln_eps;
+      launch_gemm(s->tm_x16, m->w_in.tm, none, s->tm_h0, p, st);
+    }
+    for (int l = 0; l < c.enc_n_layers; ++l) {
+      EncLayer& E = *m->enc[l];
+      {
+        GemmParams p = flat_params(B, 3 * D, D, EPI_BIAS);
+        p.bias = E.bqkv.f();
+        launch_gemm(s->tm_h0, E.wqkv.tm, none, s->tm_qkv_e, p, st);
+      }
+      // the streaming encoder attends over every past frame (causal by construction, FS:stream_mod:28-35)
+      launch_step_attn(static_cast<const __half*>(s->qkv.p), static_cast<__half*>(s->enc_k[l]->p),
+                       static_cast<__half*>(s->enc_v[l]->p), B, s->cap, pos, scale, static_cast<__half*>(s->ao.p), st);
+      {
+        GemmParams p = flat_params(B, D, D, EPI_LN);
+        p.bias = E.bo.f();
+        p.has_residual = 1;
+        p.ln_g = E.g1.f();
+        p.ln_b = E.be1.f();
+        p.ln_eps = c.ln_eps;
+        launch_gemm(s->tm_ao_e, E.wo.tm, s->tm_h0, s->tm_h1, p, st);
+      }
+      FfnParams fp = ffn_params(B, 1, c.enc_dim_feedforward, E.b1, E.b2, E.g2, E.be2, c.ln_eps, nullptr);
+      launch_ffn(s->tm_h1, E.w1.tm128, E.w2.tm128, s->tm_h0, fp, 3, st);
+    }
+    launch_hist_append(static_cast<const __half*>(s->h0.p), static_cast<__half*>(s->hist.p), B, s->cap, pos, st);
+  } else {
+    launch_hist_append(nullptr, static_cast<__half*>(s->hist.p), B, s->cap, pos, st);
+  }
+  s->t += 1;
+  const int K = c.conv_kernel, center = K / 2;
+  if (s->t < center + 1) {
+    CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
+  const int cidx = s->t - (center + 1);     // output frame index; its window is hist[cidx - center .. cidx + center]
+  {
+    GemmParams p{};
+    p.rows_per_seq = 1;
+    p.n_seq = B;
+    p.tiles_per_seq = 1;
+    p.n_tiles = 1;
+    p.k_blocks = D / 64;
+    p.taps = K;
+    p.tap_shift = -center;
+    p.a_row_offset = cidx;
+    p.mode = EPI_L2;
+    p.bias = m->b_conv.f();
+    launch_gemm(s->tm_hist, m->w_conv.tm, none, s->tm_emb_out, p, st);
+  }
+  {
+    GemmParams p = flat_params(B, D, D, EPI_CONVERT);
+    p.S = S;
+    p.pe_proj = m->pe_proj.f();
+    launch_gemm(s->tm_emb_in, m->w_cvt.tm, none, s->tm_cvt_out, p, st);
+  }
+  const size_t Rd = 1ull * B * S;
+  for (int l = 0; l < c.dec_n_layers; ++l) {
+    DecLayer& Dl = *m->dec[l];
+    {
+      GemmParams p = flat_params(Rd, 3 * D, D, EPI_BIAS);
+      p.bias = Dl.bqkv1.f();
+      launch_gemm(s->tm_a0, Dl.wqkv1.tm, none, s->tm_qkv_d, p, st);
+    }
+    launch_step_attn(static_cast<const __half*>(s->qkv.p), static_cast<__half*>(s->dec_k[l]->p),
+                     static_cast<__half*>(s->dec_v[l]->p), static_cast<int>(Rd), s->cap, cidx, scale,
+                     static_cast<__half*>(s->ao.p), st);
+    {
+      GemmParams p = flat_params(Rd, D, D, EPI_LN);
+      p.bias = Dl.bo1.f();
+      p.has_residual = 1;
+      p.ln_g = Dl.g11.f();
+      p.ln_b = Dl.be11.f();
+      p.ln_eps = c.ln_eps;
+      launch_gemm(s->tm_ao_d, Dl.wo1.tm, s->tm_a0, s->tm_a1, p, st);
+    }
+    {
+      GemmParams p = flat_params(Rd, 3 * D, D, EPI_BIAS);
+      p.bias = Dl.bqkv2.f();
+      launch_gemm(s->tm_a1, Dl.wqkv2.tm, none, s->tm_qkv_d, p, st);
+    }
+    {
+      AttnParams a{1, S, static_cast<int>(Rd), c.n_heads, 0, scale, ATTN_BLOCKDIAG, (128 / S) * S};
+      launch_attn(s->tm_qkv_spk, s->tm_ao_spk, a, st);
+    }
+    {
+      GemmParams p = flat_params(Rd, D, D, EPI_LN);
+      p.bias = Dl.bo2.f();
+      p.has_residual = 1;
+      p.ln_g = Dl.g21.f();
+      p.ln_b = Dl.be21.f();
+      p.ln_eps = c.ln_eps;
+      launch_gemm(s->tm_ao_d, Dl.wo2.tm, s->tm_a1, s->tm_a2, p, st);
+    }
+    FfnParams fp = ffn_params(static_cast<int>(Rd), 1, c.dec_dim_feedforward, Dl.b1, Dl.b2, Dl.g22, Dl.be22, c.ln_eps,
+                              nullptr);
+    launch_ffn(s->tm_a2, Dl.w1.tm128, Dl.w2.tm128, s->tm_a0, fp, 3, st);
+  }
+  launch_head(static_cast<const __half*>(s->emb.p), static_cast<const __half*>(s->a0.p), B, S, logits, nullptr, nullptr,
+              st);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
 void drain_profile(fseend_fs_model* m) {
   for (auto& e : m->prof_pending) {
     float ms = 0.f;
@@ -756,6 +977,35 @@ int fseend_fs_get_profile(fseend_fs_model* m, int max_entries, char (*names)[32]
 
 int fseend_fs_launches_per_forward(const fseend_fs_model* m) { return m ? m->launches_last : 0; }
 size_t fseend_fs_workspace_bytes(const fseend_fs_model* m) { return m ? m->ws_bytes : 0; }
+
+// ---------------------------------------------------------------------------- streaming entry points
+int fseend_fs_stream_create(fseend_fs_model* m, int B, int max_nspks, fseend_fs_stream** out) {
+  if (!m || !out) return FSEEND_ERR_INVALID;
+  *out = nullptr;
+  auto* s = new fseend_fs_stream();
+  int rc = guarded([&] {
+    if (B < 1 || max_nspks < 1 || max_nspks > 16 || B * max_nspks > 128)
+      throw std::invalid_argument("streaming needs 1 <= B * max_nspks <= 128, max_nspks <= 16");
+    if (!m->cfg.has_mask || m->cfg.mask_delay != 0)
+      throw std::invalid_argument("streaming inference is causal: has_mask must be true and mask_delay 0");
+    stream_init(s, m, B, max_nspks);
+  });
+  if (rc != FSEEND_OK) {
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return FSEEND_OK;
+}
+
+void fseend_fs_stream_destroy(fseend_fs_stream* s) { delete s; }
+
+int fseend_fs_stream_step(fseend_fs_stream* s, const float* x_t_dev, float* logits_dev, int* produced, void* stream) {
+  if (!s || !logits_dev || !produced) return FSEEND_ERR_INVALID;
+  return guarded([&] { *produced = stream_step(s, x_t_dev, logits_dev, static_cast<cudaStream_t>(stream)); });
+}
+
+int fseend_fs_stream_frames(const fseend_fs_stream* s) { return s ? s->t : 0; }
 
 // ---------------------------------------------------------------------------- single-kernel entry points
 int fseend_op_gemm(const void* a_f16, int rows_per_seq, int n_seq, int K, const void* w_f16, int N, int taps,

@@ -130,7 +130,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint8_t* sa = smem + s * kStageBytes;
         uint8_t* sb = sa + kABytes;
         mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-        tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, t0 + tap + p.tap_shift, seq);
+        tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, t0 + tap + p.tap_shift + p.a_row_offset, seq);
         tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, tap * (p.n_tiles * BN) + n0);
       }
     }

@@ -23,6 +23,7 @@ struct GemmParams {
   int k_blocks;       // K / 64 (per tap)
   int taps;           // 1 (Linear) or kernel width (Conv1d as shifted GEMMs)
   int tap_shift;      // row offset of tap 0 (Conv1d: -padding)
+  int a_row_offset;   // added to every A row coordinate (streaming conv: output row 0 = window centre)
   int mode;           // GemmEpilogue
   int relu;
   int has_residual;

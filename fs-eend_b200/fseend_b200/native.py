@@ -33,7 +33,8 @@ class FsConfig(C.Structure):
 EXPORTS = [
     "fseend_version", "fseend_last_error", "fseend_device_ok", "fseend_fs_create", "fseend_fs_destroy",
     "fseend_fs_forward", "fseend_fs_forward_host", "fseend_fs_set_profiling", "fseend_fs_get_profile",
-    "fseend_fs_launches_per_forward", "fseend_fs_workspace_bytes", "fseend_fs_set_option", "fseend_op_gemm",
+    "fseend_fs_launches_per_forward", "fseend_fs_workspace_bytes", "fseend_fs_set_option", "fseend_fs_stream_create",
+    "fseend_fs_stream_destroy", "fseend_fs_stream_step", "fseend_fs_stream_frames", "fseend_op_gemm",
     "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
     "fseend_op_prep_input",
 ]
@@ -73,6 +74,14 @@ def lib() -> C.CDLL:
     L.fseend_op_gemm.argtypes = [vp, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, vp, vp, vp, fp, vp, ip, vp, vp, vp]
     L.fseend_op_causal_attn.restype = ip
     L.fseend_op_causal_attn.argtypes = [vp, ip, ip, ip, ip, ip, fp, vp, vp]
+    L.fseend_fs_stream_create.restype = ip
+    L.fseend_fs_stream_create.argtypes = [vp, ip, ip, C.POINTER(vp)]
+    L.fseend_fs_stream_destroy.restype = None
+    L.fseend_fs_stream_destroy.argtypes = [vp]
+    L.fseend_fs_stream_step.restype = ip
+    L.fseend_fs_stream_step.argtypes = [vp, vp, vp, C.POINTER(ip), vp]
+    L.fseend_fs_stream_frames.restype = ip
+    L.fseend_fs_stream_frames.argtypes = [vp]
     L.fseend_fs_set_option.restype = ip
     L.fseend_fs_set_option.argtypes = [vp, C.c_char_p, ip]
     L.fseend_op_ffn.restype = ip
@@ -199,6 +208,38 @@ class FsModel:
     @property
     def workspace_bytes(self) -> int:
         return int(self._L.fseend_fs_workspace_bytes(self._h))
+
+
+class FsStream:
+    """Device-resident streaming state of B parallel recordings on top of an FsModel."""
+
+    def __init__(self, model: FsModel, B: int, max_nspks: int):
+        self._L = lib()
+        self.model = model          # keeps the native model alive
+        self.B, self.S = B, max_nspks
+        h = C.c_void_p()
+        _check(self._L.fseend_fs_stream_create(model._h, B, max_nspks, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.fseend_fs_stream_destroy(h)
+
+    def step(self, x_t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """x_t: CUDA fp32 [B, in_size] or None (flush).  Returns logits [B, S] or None while the conv window fills."""
+        if x_t is not None:
+            _require_cuda(x_t)
+            if x_t.dtype != torch.float32 or tuple(x_t.shape) != (self.B, self.model.cfg["in_size"]):
+                raise FseendError("x_t must be float32 [B, in_size]")
+        out = torch.empty(self.B, self.S, device="cuda", dtype=torch.float32)
+        produced = C.c_int(0)
+        _check(self._L.fseend_fs_stream_step(self._h, _ptr(x_t), _ptr(out), C.byref(produced), _stream()))
+        return out if produced.value else None
+
+    @property
+    def frames(self) -> int:
+        return int(self._L.fseend_fs_stream_frames(self._h))
 
 
 # ------------------------------------------------------------------------------ single-kernel wrappers

@@ -92,6 +92,19 @@ int fseend_fs_launches_per_forward(const fseend_fs_model* m);
 /* Bytes of device workspace currently held by the model's (B, Tmax, S) plan. */
 size_t fseend_fs_workspace_bytes(const fseend_fs_model* m);
 
+/* ---- frame-by-frame streaming (reference: StreamingTransformerEDADiarization.test,
+ * FS-EEND/nnet/model/streaming_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm.py:31-60) --------------------
+ * A stream holds the device-resident state of B parallel recordings: projected K/V caches per layer, the encoder
+ * history feeding the 19-tap look-ahead conv, and the frame counter.  The model must outlive its streams. */
+typedef struct fseend_fs_stream fseend_fs_stream;
+int fseend_fs_stream_create(fseend_fs_model* m, int B, int max_nspks, fseend_fs_stream** out);
+void fseend_fs_stream_destroy(fseend_fs_stream* s);
+/* Push one frame: x_t_dev fp32 [B][in_size], or NULL for a flush step (the reference's dummy_conv_input=True, used
+ * conv_delay times at the end).  *produced = 1 and logits_dev [B][max_nspks] is written once the conv window is
+ * full (from the (conv_delay+1)-th call on), else *produced = 0 (the reference returns None). */
+int fseend_fs_stream_step(fseend_fs_stream* s, const float* x_t_dev, float* logits_dev, int* produced, void* stream);
+int fseend_fs_stream_frames(const fseend_fs_stream* s);
+
 /* ---- single-kernel entry points (used by the parity tests; all pointers are device pointers) ---------- */
 
 /* OUT = epilogue(A * W^T): A fp16 [n_seq][rows_per_seq][K], W fp16 [taps*N][K], fp32 accumulate.

@@ -91,6 +91,10 @@ def main():
     print("stream vs batch max diff", (ys - batch).abs().max().item())
     np.savez_compressed(os.path.join(HERE, "stream_T60_S6.npz"), stream=ys.numpy(), batch=batch.numpy())
 
+    with open(os.path.join(HERE, "fs_stream_state_dict_abi.txt"), "w") as f:
+        for k, v in stream.state_dict().items():
+            f.write(f"{k} {tuple(v.shape)} {str(v.dtype).replace('torch.', '')}\n")
+
     # state_dict ABI: names and shapes of the reference model
     with open(os.path.join(HERE, "fs_state_dict_abi.txt"), "w") as f:
         for k, v in build_ref(O.random_state_dict(0)).state_dict().items():

@@ -72,3 +72,38 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, fn), encoding="utf-8").read()
                 assert "oracle" not in txt.replace("oracle/", "").lower() or fn == "README.md", (dp, fn)
+
+
+def make_stream_model():
+    from nnet.model.streaming_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import StreamingTransformerEDADiarization
+    return StreamingTransformerEDADiarization(in_size=345, n_units=256, n_heads=4, enc_n_layers=4, dec_n_layers=2,
+                                              dropout=0.1, has_mask=True, max_seqlen=500, dec_dim_feedforward=2048)
+
+
+def test_streaming_state_dict_abi_matches_reference():
+    want = {}
+    with open(os.path.join(ROOT, "tests", "golden", "fs_stream_state_dict_abi.txt")) as f:
+        for line in f:
+            k, shape, dt = re.match(r"(\S+) (\(.*\)) (\S+)", line.strip()).groups()
+            want[k] = (eval(shape), dt)
+    got = {k: (tuple(v.shape), str(v.dtype).replace("torch.", "")) for k, v in make_stream_model().state_dict().items()}
+    assert got == want
+
+
+def test_copy_params_from_masked_to_streaming_covers_every_tensor():
+    """Every streaming tensor has a masked-model source of the same shape (reference copy_params.py:7-62), the
+    dead masked parameters (dec.encoder*, norm12) are the only ones left uncopied."""
+    from nnet.model.streaming_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import streaming_to_masked_key
+    from nnet.utils.copy_params import copy_params_from_masked_to_streaming
+    from oracle import fs_eend_oracle as O
+    masked, stream = make_model(), make_stream_model()
+    masked.load_state_dict(O.random_state_dict(3), strict=True)
+    copy_params_from_masked_to_streaming(masked, stream)
+    msd, ssd = masked.state_dict(), stream.state_dict()
+    used = set()
+    for k, v in ssd.items():
+        mk = streaming_to_masked_key(k)
+        used.add(mk)
+        assert torch.equal(v, msd[mk]), k
+    unused = {k for k in msd if k not in used}
+    assert all(k.startswith(("dec.encoder", "dec.encoder_norm")) or ".norm12." in k for k in unused), unused

@@ -115,3 +115,57 @@ def test_kernel_variants_agree_with_reference(ffn, spk):
     worst = max(float(np.abs(o.cpu().numpy() - g[f"logits_{i}"]).max()) for i, o in enumerate(out))
     print(f"ffn={ffn} spk={spk}: max-abs logit error vs reference = {worst:.2e}")
     assert worst < TOL
+
+
+def _make_stream(sd):
+    from nnet.model.streaming_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import StreamingTransformerEDADiarization
+    from nnet.utils.copy_params import copy_params_from_masked_to_streaming
+    masked = make_model(sd)
+    stream = StreamingTransformerEDADiarization(in_size=345, n_units=256, n_heads=4, enc_n_layers=4, dec_n_layers=2,
+                                                dropout=0.1, has_mask=True, max_seqlen=500,
+                                                dec_dim_feedforward=2048).cuda().eval()
+    copy_params_from_masked_to_streaming(masked, stream)
+    return masked, stream
+
+
+def _run_stream(stream, x, S):
+    """The reference's frame loop + flush (FS-EEND/streaming_infer_dia.py:77-86).  x: (B, T, 345) on the GPU."""
+    ys = []
+    for t in range(x.shape[1]):
+        y = stream.test(x[:, t:t + 1], max_nspks=S)
+        assert (y is None) == (t < 9)
+        if y is not None:
+            ys.append(y)
+    for _ in range(9):
+        ys.append(stream.test(torch.zeros(x.shape[0], 1, 345, device="cuda"), max_nspks=S, dummy_conv_input=True))
+    return torch.cat(ys, dim=1)
+
+
+def test_streaming_matches_reference_stream_golden():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stream_T60_S6.npz"))
+    sd = O.random_state_dict(seed=4, trained_like=True)
+    masked, stream = _make_stream(sd)
+    src, _ = O.synthetic_features(1, 60)
+    ys = _run_stream(stream, src[0][None].cuda(), 6)[0].cpu().numpy()
+    assert ys.shape == g["stream"].shape
+    err = np.abs(ys - g["stream"]).max()
+    print(f"streaming T=60: max-abs logit error vs reference frame loop = {err:.2e}")
+    assert err < TOL
+
+
+def test_streaming_equals_batch_path_two_recordings_and_cache_growth():
+    """The reference's own invariant (streaming_infer_dia.py:97): frame-by-frame == batch.  Two recordings in
+    parallel, 1100 frames (> the initial 1024-frame cache capacity, so the caches are re-allocated mid-stream)."""
+    sd = O.random_state_dict(seed=9, trained_like=True)
+    masked, stream = _make_stream(sd)
+    T = 1100
+    src, lens = O.synthetic_features(2, T)
+    x = torch.stack(src).cuda()
+    ys = _run_stream(stream, x, 4)
+    batch = torch.stack(masked.test_logits([s.cuda() for s in src], lens, 4))
+    err = (ys - batch).abs().max().item()
+    print(f"streaming vs batch, B=2 T={T}: max-abs difference = {err:.2e}")
+    assert ys.shape == batch.shape and err < TOL
+    stream.reset()
+    again = _run_stream(stream, x[:, :40], 4)
+    assert (again[:, :31] - ys[:, :31]).abs().max().item() < 1e-6    # deterministic restart after reset()
