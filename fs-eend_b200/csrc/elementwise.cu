@@ -14,7 +14,7 @@ namespace {
 // (the reference pads with -1 BEFORE BatchNorm, FS:model:165-166); columns >= Din are zero.
 __global__ void prep_input_kernel(const float* __restrict__ x, const int* __restrict__ cu, int Tmax, int Din,
                                   int Kpad, const float* __restrict__ sc, const float* __restrict__ sh,
-                                  __half* __restrict__ out) {
+                                  float pad_value, __half* __restrict__ out) {
   const int row = blockIdx.x;  // b * Tmax + t
   const int b = row / Tmax, t = row - b * Tmax;
   const int start = cu[b], len = cu[b + 1] - start;
@@ -23,8 +23,8 @@ __global__ void prep_input_kernel(const float* __restrict__ x, const int* __rest
   for (int i = threadIdx.x; i < Kpad / 2; i += blockDim.x) {
     const int c0 = 2 * i, c1 = 2 * i + 1;
     float v0 = 0.f, v1 = 0.f;
-    if (c0 < Din) v0 = fmaf(src ? __ldg(src + c0) : -1.f, sc[c0], sh[c0]);
-    if (c1 < Din) v1 = fmaf(src ? __ldg(src + c1) : -1.f, sc[c1], sh[c1]);
+    if (c0 < Din) v0 = fmaf(src ? __ldg(src + c0) : pad_value, sc ? sc[c0] : 1.f, sh ? sh[c0] : 0.f);
+    if (c1 < Din) v1 = fmaf(src ? __ldg(src + c1) : pad_value, sc ? sc[c1] : 1.f, sh ? sh[c1] : 0.f);
     dst[i] = __floats2half2_rn(v0, v1);
   }
 }
@@ -276,11 +276,116 @@ __global__ void hist_append_kernel(const __half* __restrict__ src, __half* __res
   d[threadIdx.x] = s ? s[threadIdx.x] : 0u;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Conformer conv module middle (LS:conf/convolution.py:144-146): causal depthwise Conv1d (kernel K <= 32, left
+// zero padding K-1, no bias) -> BatchNorm1d (eval, folded to scale/shift) -> swish.
+// u, out: [n_seq][T][256] fp16.  Block = (64 frames, one sequence); thread = 2 adjacent channels.
+// hist (optional): [n_seq][K-1][256] fp16 one-step cache: prepended instead of zeros, and updated when T == 1.
+__global__ void __launch_bounds__(128)
+dwconv_bn_swish_kernel(const __half* __restrict__ u, const float* __restrict__ w, const float* __restrict__ sc,
+                       const float* __restrict__ sh, int T, int K, __half* __restrict__ hist,
+                       __half* __restrict__ out) {
+  const int n = blockIdx.y, t0 = blockIdx.x * 64, c = threadIdx.x * 2;
+  float w0[32], w1[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    w0[k] = k < K ? w[c * K + k] : 0.f;
+    w1[k] = k < K ? w[(c + 1) * K + k] : 0.f;
+  }
+  const float s0 = sc[c], s1 = sc[c + 1], h0 = sh[c], h1 = sh[c + 1];
+  const __half2* up = reinterpret_cast<const __half2*>(u + static_cast<size_t>(n) * T * 256 + c);
+  __half2* hp = hist ? reinterpret_cast<__half2*>(hist + static_cast<size_t>(n) * (K - 1) * 256 + c) : nullptr;
+  float2 win[32];   // win[k] = input at t - (K-1) + k
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int t = t0 - (K - 1) + k;
+    float2 v = make_float2(0.f, 0.f);
+    if (k < K - 1) {
+      if (t >= 0) v = __half22float2(up[static_cast<size_t>(t) * 128]);
+      else if (hp) v = __half22float2(hp[static_cast<size_t>(t + K - 1) * 128]);
+    }
+    win[k] = v;
+  }
+  const int t_end = min(t0 + 64, T);
+  for (int t = t0; t < t_end; ++t) {
+    const float2 cur = __half22float2(up[static_cast<size_t>(t) * 128]);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k < K - 1) {
+        a0 = fmaf(w0[k], win[k].x, a0);
+        a1 = fmaf(w1[k], win[k].y, a1);
+      }
+    }
+    a0 = fmaf(w0[K - 1], cur.x, a0);
+    a1 = fmaf(w1[K - 1], cur.y, a1);
+#pragma unroll
+    for (int k = 0; k < 31; ++k) win[k] = (k + 1 < K - 1) ? win[k + 1] : win[k];
+    if (K >= 2) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k == K - 2) win[k] = cur;
+    }
+    a0 = fmaf(a0, s0, h0);
+    a1 = fmaf(a1, s1, h1);
+    a0 = a0 / (1.f + __expf(-a0));
+    a1 = a1 / (1.f + __expf(-a1));
+    reinterpret_cast<__half2*>(out + (static_cast<size_t>(n) * T + t) * 256 + c)[0] = __floats2half2_rn(a0, a1);
+  }
+  if (hp && T == 1) {   // one-step: slide the cache
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (k < K - 1) hp[static_cast<size_t>(k) * 128] = __floats2half2_rn(win[k].x, win[k].y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Recurrent retention step (LS:ret:126-144, decay = 1): per (sequence, head) the fp32 state kv (64 x 64) becomes
+// kv * sqrt(t)/sqrt(t+1) + k^T v / sqrt(t+1)  (t = frames already seen), out = q kv -> group norm (eps 1e-6) ->
+// * swish(g).  qkvg: [n_seq][1024] fp16 (q | k*hd^-.5 | v | g); state: [n_seq][4][64][64] fp32; out: [n_seq][256].
+__global__ void __launch_bounds__(64)
+ret_step_kernel(const __half* __restrict__ qkvg, float* __restrict__ state, int t, __half* __restrict__ out) {
+  const int n = blockIdx.x, h = blockIdx.y, d = threadIdx.x;   // thread d owns column d of the state
+  __shared__ float q_s[64], k_s[64], red[2];
+  const __half* row = qkvg + static_cast<size_t>(n) * 1024 + h * 64;
+  q_s[d] = __half2float(row[d]);
+  k_s[d] = __half2float(row[256 + d]);
+  const float v = __half2float(row[512 + d]);
+  const float g = __half2float(row[768 + d]);
+  __syncthreads();
+  float* st = state + (static_cast<size_t>(n) * 4 + h) * 4096;
+  const float a = sqrtf(static_cast<float>(t)) / sqrtf(static_cast<float>(t + 1));
+  const float bsc = 1.f / sqrtf(static_cast<float>(t + 1));
+  float o = 0.f;
+#pragma unroll 8
+  for (int e = 0; e < 64; ++e) {
+    float kv = st[e * 64 + d];
+    kv = (t > 0 ? kv * a : 0.f) + k_s[e] * v * bsc;
+    st[e * 64 + d] = kv;
+    o = fmaf(q_s[e], kv, o);
+  }
+  // group norm over the 64 columns of this head
+  float s = o;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((d & 31) == 0) red[d >> 5] = s;
+  __syncthreads();
+  const float mean = (red[0] + red[1]) * (1.f / 64.f);
+  __syncthreads();
+  float dv = (o - mean) * (o - mean);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) dv += __shfl_xor_sync(0xffffffffu, dv, off);
+  if ((d & 31) == 0) red[d >> 5] = dv;
+  __syncthreads();
+  const float rstd = rsqrtf((red[0] + red[1]) * (1.f / 64.f) + 1e-6f);
+  out[static_cast<size_t>(n) * 256 + h * 64 + d] = __float2half_rn((o - mean) * rstd * (g / (1.f + __expf(-g))));
+}
+
 }  // namespace
 
 void launch_prep_input(const float* x, const int* cu_seqlens, int B, int Tmax, int Din, int Kpad, const float* sc,
-                       const float* sh, __half* out, cudaStream_t stream) {
-  prep_input_kernel<<<B * Tmax, 192, 0, stream>>>(x, cu_seqlens, Tmax, Din, Kpad, sc, sh, out);
+                       const float* sh, __half* out, cudaStream_t stream, float pad_value) {
+  prep_input_kernel<<<B * Tmax, 192, 0, stream>>>(x, cu_seqlens, Tmax, Din, Kpad, sc, sh, pad_value, out);
 }
 
 int launch_spk_attn(const __half* qkv, __half* out, int n_frames, int S, float scale, cudaStream_t stream) {
@@ -306,6 +411,17 @@ void launch_step_attn(const __half* qkv, __half* kcache, __half* vcache, int n_s
 
 void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int pos, cudaStream_t stream) {
   hist_append_kernel<<<n_seq, 128, 0, stream>>>(src, hist, cap, pos);
+}
+
+int launch_dwconv_bn_swish(const __half* u, const float* w, const float* sc, const float* sh, int n_seq, int T, int K,
+                           __half* hist, __half* out, cudaStream_t stream) {
+  if (K < 1 || K > 32) return -1;
+  dwconv_bn_swish_kernel<<<dim3((T + 63) / 64, n_seq), 128, 0, stream>>>(u, w, sc, sh, T, K, hist, out);
+  return 0;
+}
+
+void launch_ret_step(const __half* qkvg, float* state, int n_seq, int t, __half* out, cudaStream_t stream) {
+  ret_step_kernel<<<dim3(n_seq, 4), 64, 0, stream>>>(qkvg, state, t, out);
 }
 
 }  // namespace fseend

@@ -6,9 +6,10 @@
 namespace fseend {
 
 // x: packed fp32 rows [sum(len)][Din]; cu_seqlens: device int[B+1]; out: fp16 [B][Tmax][Kpad].
-// out = x * sc + sh (BatchNorm eval folded into per-channel scale/shift), rows t >= len use x = -1.
+// out = x * sc + sh (BatchNorm eval folded into per-channel scale/shift; nullptr = identity), rows t >= len use
+// x = pad_value (FS-EEND pads with -1 before BatchNorm, LS-EEND with 0).
 void launch_prep_input(const float* x, const int* cu_seqlens, int B, int Tmax, int Din, int Kpad, const float* sc,
-                       const float* sh, __half* out, cudaStream_t stream);
+                       const float* sh, __half* out, cudaStream_t stream, float pad_value = -1.f);
 
 // qkv: [n_frames][S][768] fp16 -> out [n_frames][S][256] fp16; S <= 16.  Returns -1 on unsupported S.
 int launch_spk_attn(const __half* qkv, __half* out, int n_frames, int S, float scale, cudaStream_t stream);
@@ -24,5 +25,12 @@ void launch_step_attn(const __half* qkv, __half* kcache, __half* vcache, int n_s
                       __half* out, cudaStream_t stream);
 // hist[n][pos][:] = src[n][:] (or zeros when src == nullptr); hist: [n_seq][cap][256] fp16.
 void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int pos, cudaStream_t stream);
+
+// Conformer conv-module middle: causal depthwise conv (K <= 32 taps, weight [256][K]) -> BN(eval) affine -> swish.
+// u/out: [n_seq][T][256] fp16; hist: optional [n_seq][K-1][256] one-step cache (updated when T == 1).
+int launch_dwconv_bn_swish(const __half* u, const float* w, const float* sc, const float* sh, int n_seq, int T, int K,
+                           __half* hist, __half* out, cudaStream_t stream);
+// Recurrent retention step for frame index t (0-based): state [n_seq][4][64][64] fp32 updated in place.
+void launch_ret_step(const __half* qkvg, float* state, int n_seq, int t, __half* out, cudaStream_t stream);
 
 }  // namespace fseend

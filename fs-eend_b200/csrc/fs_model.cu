@@ -10,6 +10,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -1160,3 +1161,5 @@ int fseend_op_prep_input(const float* x_packed, const int* cu_seqlens_dev, int B
 }
 
 }  // extern "C"
+
+#include "ls_model.inc"

@@ -76,7 +76,8 @@ __device__ __forceinline__ void tmem_ld32_sync(uint32_t taddr, float (&v)[32]) {
 
 __global__ void __launch_bounds__(128, 2)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+            const __grid_constant__ CUtensorMap tmO2, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
@@ -184,23 +185,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] += aux[i];
       }
-      if (p.relu) {
+      if (p.relu == ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], 0.f);
+      } else if (p.relu == ACT_SWISH) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = acc[i] / (1.f + __expf(-acc[i]));
       }
       staging_write32(staging, r, c, acc);
     }
-  } else if (p.mode == EPI_LN || p.mode == EPI_L2) {
+  } else if (p.mode == EPI_GLU) {
+    // columns [0,128) = value, [128,256) = gate of the same 128 output channels
+    for (int c = 0; c < 4; ++c) {
+      float gate[32];
+      tmem_ld32_sync(trow + c * 32, acc);
+      tmem_ld32_sync(trow + 128 + c * 32, gate);
+      if (p.bias) {
+        load_vec32(p.bias + n0 + c * 32, aux);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += aux[i];
+        load_vec32(p.bias + n0 + 128 + c * 32, aux);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) gate[i] += aux[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = acc[i] / (1.f + __expf(-gate[i]));
+      staging_write32(staging, r, c, acc);
+    }
+  } else if (p.mode == EPI_LN || p.mode == EPI_L2 || p.mode == EPI_RESID) {
+    const float alpha = (p.mode == EPI_RESID) ? p.alpha : 1.f;
+    const bool do_ln = (p.mode == EPI_LN) || (p.mode == EPI_RESID && p.ln_g != nullptr);
+    const bool need_stats = do_ln || p.mode == EPI_L2;
     // pass 1: row statistics (Chan's parallel merge of 32-column chunks: robust to large means)
     RowStats st{0.f, 0.f, 0.f};
     float sumsq = 0.f;
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; need_stats && c < 8; ++c) {
       tmem_ld32_sync(trow + c * 32, acc);
       if (p.bias) {
         load_vec32(p.bias + c * 32, aux);
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] += aux[i];
       }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] *= alpha;
       if (p.has_residual) {
         staging_read32(staging, r, c, aux);
 #pragma unroll
@@ -227,10 +254,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         st.n = nn;
       }
     }
-    float mean = 0.f, scale;
+    float mean = 0.f, scale = 1.f;
     if (p.mode == EPI_L2) {
       scale = sumsq > 0.f ? rsqrtf(sumsq) : 0.f;
-    } else {
+    } else if (do_ln) {
       mean = st.mean;
       scale = rsqrtf(st.m2 * (1.f / 256.f) + p.ln_eps);
     }
@@ -243,6 +270,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] += aux[i];
       }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] *= alpha;
       if (p.has_residual) {
         staging_read32(staging, r, c, aux);
 #pragma unroll
@@ -250,7 +279,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] = (acc[i] - mean) * scale;
-      if (p.mode == EPI_LN) {
+      if (do_ln) {
         load_vec32(p.ln_g + c * 32, aux);
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] *= aux[i];
@@ -266,7 +295,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
 
-  if (p.mode != EPI_CONVERT) {
+  if (p.mode == EPI_GLU) {
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      for (int sub = 0; sub < 2; ++sub)
+        tma_store_3d(&tmO, staging + sub * kSubTileBytes, n_tile * 128 + sub * 64, t0, seq);
+      tma_store_commit();
+      tma_store_wait_read0();
+    }
+  } else if (p.mode != EPI_CONVERT) {
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -274,6 +312,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_store_3d(&tmO, staging + sub * kSubTileBytes, n0 + sub * 64, t0, seq);
       tma_store_commit();
       tma_store_wait_read0();
+    }
+    if (p.ln2_g != nullptr && (p.mode == EPI_LN || p.mode == EPI_RESID)) {
+      // second output: LayerNorm of the (fp16) row just stored, with the next pre-norm sub-layer's affine
+      __syncthreads();   // the TMA store above has finished reading the staging tile
+      RowStats s2{0.f, 0.f, 0.f};
+      for (int c = 0; c < 8; ++c) {
+        staging_read32(staging, r, c, acc);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s += acc[i];
+        const float cm = s * (1.f / 32.f);
+        float m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float d = acc[i] - cm;
+          m2 = fmaf(d, d, m2);
+        }
+        const float nn = s2.n + 32.f;
+        const float delta = cm - s2.mean;
+        s2.m2 += m2 + delta * delta * (s2.n * 32.f / nn);
+        s2.mean += delta * (32.f / nn);
+        s2.n = nn;
+      }
+      const float rstd2 = rsqrtf(s2.m2 * (1.f / 256.f) + p.ln_eps);
+      for (int c = 0; c < 8; ++c) {
+        staging_read32(staging, r, c, acc);
+        load_vec32(p.ln2_g + c * 32, aux);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = (acc[i] - s2.mean) * rstd2 * aux[i];
+        load_vec32(p.ln2_b + c * 32, aux);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += aux[i];
+        staging_write32(staging, r, c, acc);
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        for (int sub = 0; sub < 4; ++sub)
+          tma_store_3d(&tmO2, staging + sub * kSubTileBytes, n0 + sub * 64, t0, seq);
+        tma_store_commit();
+        tma_store_wait_read0();
+      }
     }
   } else {
     // attractor init: S output rows per input row, out[row, s, :] = acc + pe_proj[s, :]
@@ -312,7 +392,18 @@ void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
     attr_set = true;
   }
   const int grid = p.n_seq * p.tiles_per_seq * p.n_tiles;
-  gemm_kernel<<<grid, 128, kSmemBytes, stream>>>(tmA, tmB, tmR, tmO, p);
+  gemm_kernel<<<grid, 128, kSmemBytes, stream>>>(tmA, tmB, tmR, tmO, tmO, p);
+}
+
+void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
+                  const CUtensorMap& tmO2, const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    attr_set = true;
+  }
+  const int grid = p.n_seq * p.tiles_per_seq * p.n_tiles;
+  gemm_kernel<<<grid, 128, kSmemBytes, stream>>>(tmA, tmB, tmR, tmO, tmO2, p);
 }
 
 }  // namespace fseend

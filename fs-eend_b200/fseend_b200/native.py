@@ -29,12 +29,20 @@ class FsConfig(C.Structure):
     ]
 
 
+class LsConfig(C.Structure):
+    _fields_ = [(k, C.c_int) for k in (
+        "in_size", "n_units", "n_heads", "enc_n_layers", "dec_n_layers", "feed_forward_expansion_factor",
+        "dec_dim_feedforward", "conv_kernel_size", "recurrent_chunk_size", "conv_delay")]
+
+
 # every symbol include/fseend_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "fseend_version", "fseend_last_error", "fseend_device_ok", "fseend_fs_create", "fseend_fs_destroy",
     "fseend_fs_forward", "fseend_fs_forward_host", "fseend_fs_set_profiling", "fseend_fs_get_profile",
     "fseend_fs_launches_per_forward", "fseend_fs_workspace_bytes", "fseend_fs_set_option", "fseend_fs_stream_create",
-    "fseend_fs_stream_destroy", "fseend_fs_stream_step", "fseend_fs_stream_frames", "fseend_op_gemm",
+    "fseend_fs_stream_destroy", "fseend_fs_stream_step", "fseend_fs_stream_frames", "fseend_ls_create",
+    "fseend_ls_destroy", "fseend_ls_padded_len", "fseend_ls_forward", "fseend_ls_launches_per_forward", "fseend_op_gemm",
+    "fseend_op_gemm_ex", "fseend_op_retention", "fseend_op_dwconv_bn_swish", "fseend_op_ret_step",
     "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
     "fseend_op_prep_input",
 ]
@@ -82,6 +90,25 @@ def lib() -> C.CDLL:
     L.fseend_fs_stream_step.argtypes = [vp, vp, vp, C.POINTER(ip), vp]
     L.fseend_fs_stream_frames.restype = ip
     L.fseend_fs_stream_frames.argtypes = [vp]
+    L.fseend_ls_create.restype = ip
+    L.fseend_ls_create.argtypes = [C.POINTER(LsConfig), ip, C.POINTER(C.c_char_p), C.POINTER(vp),
+                                   C.POINTER(C.c_longlong), C.POINTER(vp)]
+    L.fseend_ls_destroy.restype = None
+    L.fseend_ls_destroy.argtypes = [vp]
+    L.fseend_ls_padded_len.restype = ip
+    L.fseend_ls_padded_len.argtypes = [vp, ip]
+    L.fseend_ls_forward.restype = ip
+    L.fseend_ls_forward.argtypes = [vp, vp, C.POINTER(ip), ip, ip, vp, vp, vp, vp]
+    L.fseend_ls_launches_per_forward.restype = ip
+    L.fseend_ls_launches_per_forward.argtypes = [vp]
+    L.fseend_op_gemm_ex.restype = ip
+    L.fseend_op_gemm_ex.argtypes = [vp, ip, ip, ip, vp, ip, ip, ip, vp, vp, fp, vp, vp, vp, vp, fp, vp, vp, vp, vp]
+    L.fseend_op_retention.restype = ip
+    L.fseend_op_retention.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, vp]
+    L.fseend_op_dwconv_bn_swish.restype = ip
+    L.fseend_op_dwconv_bn_swish.argtypes = [vp, vp, vp, vp, ip, ip, ip, vp, vp, vp]
+    L.fseend_op_ret_step.restype = ip
+    L.fseend_op_ret_step.argtypes = [vp, vp, ip, ip, vp, vp]
     L.fseend_fs_set_option.restype = ip
     L.fseend_fs_set_option.argtypes = [vp, C.c_char_p, ip]
     L.fseend_op_ffn.restype = ip
@@ -210,6 +237,64 @@ class FsModel:
         return int(self._L.fseend_fs_workspace_bytes(self._h))
 
 
+def _pack_state_dict(state_dict):
+    names, ptrs, numels, keep = [], [], [], []
+    for k, v in state_dict.items():
+        if not torch.is_floating_point(v):
+            continue
+        t = v.detach().to(device="cpu", dtype=torch.float32).contiguous()
+        keep.append(t)
+        names.append(k.encode())
+        ptrs.append(t.data_ptr())
+        numels.append(t.numel())
+    n = len(names)
+    return n, (C.c_char_p * n)(*names), (C.c_void_p * n)(*ptrs), (C.c_longlong * n)(*numels), keep
+
+
+class LsModel:
+    """Owns a native fseend_ls_model built from a reference-named LS-EEND state_dict."""
+
+    def __init__(self, cfg: Dict[str, int], state_dict: Dict[str, torch.Tensor]):
+        L = lib()
+        if not torch.cuda.is_available():
+            raise FseendError("fseend_b200 requires a CUDA (sm_100) device; there is no CPU fallback")
+        c = LsConfig(**{k: int(cfg[k]) for k, _ in LsConfig._fields_})
+        self.cfg = dict(cfg)
+        n, names, ptrs, numels, keep = _pack_state_dict(state_dict)
+        handle = C.c_void_p()
+        _check(L.fseend_ls_create(C.byref(c), n, names, ptrs, numels, C.byref(handle)))
+        self._h, self._L = handle, L
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.fseend_ls_destroy(h)
+
+    def forward(self, x_packed: torch.Tensor, ilens: Sequence[int], max_nspks: int, want_emb: bool = False,
+                want_att: bool = False):
+        """Returns (logits [B,Tp,S], emb [B,Tp,D] | None, att [B,Tp,S,D] | None); Tp = max(ilens) rounded up to the
+        retention chunk (the reference pads the same way)."""
+        _require_cuda(x_packed)
+        if x_packed.dtype != torch.float32:
+            raise FseendError("x must be float32")
+        B = len(ilens)
+        if x_packed.shape[0] != int(sum(ilens)) or x_packed.shape[1] != self.cfg["in_size"]:
+            raise FseendError("x_packed shape does not match ilens / in_size")
+        Tp = int(self._L.fseend_ls_padded_len(self._h, int(max(ilens))))
+        D, dev = self.cfg["n_units"], x_packed.device
+        logits = torch.empty(B, Tp, max_nspks, device=dev, dtype=torch.float32)
+        emb = torch.empty(B, Tp, D, device=dev, dtype=torch.float32) if want_emb else None
+        att = torch.empty(B, Tp, max_nspks, D, device=dev, dtype=torch.float32) if want_att else None
+        il = (C.c_int * B)(*[int(i) for i in ilens])
+        _check(self._L.fseend_ls_forward(self._h, _ptr(x_packed), il, B, max_nspks, _ptr(logits), _ptr(emb), _ptr(att),
+                                         _stream()))
+        return logits, emb, att
+
+    @property
+    def launches_per_forward(self) -> int:
+        return int(self._L.fseend_ls_launches_per_forward(self._h))
+
+
 class FsStream:
     """Device-resident streaming state of B parallel recordings on top of an FsModel."""
 
@@ -307,4 +392,53 @@ def op_prep_input(x_packed: torch.Tensor, cu_seqlens: torch.Tensor, B: int, Tmax
     out = torch.empty(B, Tmax, Kpad, device=x_packed.device, dtype=torch.float16)
     _check(lib().fseend_op_prep_input(_ptr(x_packed), _ptr(cu_seqlens), B, Tmax, x_packed.shape[1], Kpad, _ptr(scale),
                                       _ptr(shift), _ptr(out), _stream()))
+    return out
+
+
+EPI_GLU, EPI_RESID = 4, 5
+ACT_NONE, ACT_RELU, ACT_SWISH = 0, 1, 2
+
+
+def op_gemm_ex(a: torch.Tensor, w: torch.Tensor, mode: int, *, n_seq: int = 1, act: int = 0, bias=None, residual=None,
+               alpha: float = 1.0, ln_g=None, ln_b=None, ln2_g=None, ln2_b=None, ln_eps: float = 1e-5, seq_len=None):
+    """Returns (out, out2 | None)."""
+    _require_cuda(a, w, bias, residual, ln_g, ln_b, ln2_g, ln2_b, seq_len)
+    rows, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if mode == EPI_GLU else N
+    out = torch.empty(rows, n_out, device=a.device, dtype=torch.float16)
+    out2 = torch.empty_like(out) if ln2_g is not None else None
+    _check(lib().fseend_op_gemm_ex(_ptr(a), rows // n_seq, n_seq, K, _ptr(w), N, mode, act, _ptr(bias), _ptr(residual),
+                                   alpha, _ptr(ln_g), _ptr(ln_b), _ptr(ln2_g), _ptr(ln2_b), ln_eps, _ptr(seq_len),
+                                   _ptr(out), _ptr(out2), _stream()))
+    return out, out2
+
+
+def op_retention(qkvg: torch.Tensor, chunk: int) -> torch.Tensor:
+    """qkvg: fp16 [B, T, S, 1024] -> [B, T, S, 256] (swish(g) * GroupNorm(retention))."""
+    _require_cuda(qkvg)
+    B, T, S, _ = qkvg.shape
+    nc = T // chunk
+    state = torch.zeros(B * S * 4 * nc, 64, 64, device=qkvg.device, dtype=torch.float16)
+    cs = torch.ones(B * S * 4 * nc, device=qkvg.device, dtype=torch.float32)
+    out = torch.empty(B, T, S, 256, device=qkvg.device, dtype=torch.float16)
+    _check(lib().fseend_op_retention(_ptr(qkvg), B, S, T, chunk, _ptr(state), _ptr(cs), _ptr(out), _stream()))
+    return out
+
+
+def op_dwconv_bn_swish(u: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, hist=None):
+    """u: fp16 [n_seq, T, 256]; w: fp32 [256, K]."""
+    _require_cuda(u, w, scale, shift, hist)
+    n_seq, T, _ = u.shape
+    out = torch.empty_like(u)
+    _check(lib().fseend_op_dwconv_bn_swish(_ptr(u), _ptr(w), _ptr(scale), _ptr(shift), n_seq, T, w.shape[1],
+                                           _ptr(hist), _ptr(out), _stream()))
+    return out
+
+
+def op_ret_step(qkvg: torch.Tensor, state: torch.Tensor, t: int) -> torch.Tensor:
+    """qkvg: fp16 [n_seq, 1024]; state: fp32 [n_seq, 4, 64, 64] (updated in place)."""
+    _require_cuda(qkvg, state)
+    out = torch.empty(qkvg.shape[0], 256, device=qkvg.device, dtype=torch.float16)
+    _check(lib().fseend_op_ret_step(_ptr(qkvg), _ptr(state), qkvg.shape[0], t, _ptr(out), _stream()))
     return out

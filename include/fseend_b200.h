@@ -105,6 +105,35 @@ void fseend_fs_stream_destroy(fseend_fs_stream* s);
 int fseend_fs_stream_step(fseend_fs_stream* s, const float* x_t_dev, float* logits_dev, int* produced, void* stream);
 int fseend_fs_stream_frames(const fseend_fs_stream* s);
 
+/* ---- LS-EEND (Conformer-retention encoder + retention attractor decoder) -----------------------------------------
+ * Reference: OnlineConformerRetentionDADiarization (LS-EEND/nnet/model/onl_conformer_retention_enc_1dcnn_tfm_
+ * retention_enc_linear_non_autoreg_pos_enc_l2norm_emb_loss_mask.py:14-147), constructor kwargs :15-32. */
+typedef struct fseend_ls_config {
+  int in_size;                        /* 345 */
+  int n_units;                        /* 256 */
+  int n_heads;                        /* 4 (head_dim 64) */
+  int enc_n_layers;
+  int dec_n_layers;
+  int feed_forward_expansion_factor;  /* 4 (conf yaml :35); only 4 is supported */
+  int dec_dim_feedforward;            /* 2048 */
+  int conv_kernel_size;               /* 16: causal depthwise conv of the Conformer conv module */
+  int recurrent_chunk_size;           /* 500: retention chunk; inputs are zero-padded to a multiple of it */
+  int conv_delay;                     /* 9: look-ahead Conv1d kernel = 2*conv_delay+1 */
+} fseend_ls_config;
+typedef struct fseend_ls_model fseend_ls_model;
+
+/* names[i]: the reference's state_dict keys ("enc.encoder.layers.0.sequential.1.module.self_attn.q_proj.weight", ...). */
+int fseend_ls_create(const fseend_ls_config* cfg, int n_tensors, const char* const* names, const float* const* data,
+                     const long long* numel, fseend_ls_model** out);
+void fseend_ls_destroy(fseend_ls_model* m);
+/* Tp = max(ilens) rounded up to a multiple of recurrent_chunk_size: the padded length of every output below. */
+int fseend_ls_padded_len(const fseend_ls_model* m, int max_ilen);
+/* test(): x_packed [sum(ilens)][in_size] fp32 device; logits [B][Tp][max_nspks], emb [B][Tp][256] or NULL,
+ * att [B][Tp][max_nspks][256] or NULL (fp32, device). */
+int fseend_ls_forward(fseend_ls_model* m, const float* x_packed_dev, const int* ilens_host, int B, int max_nspks,
+                      float* logits_dev, float* emb_dev, float* att_dev, void* stream);
+int fseend_ls_launches_per_forward(const fseend_ls_model* m);
+
 /* ---- single-kernel entry points (used by the parity tests; all pointers are device pointers) ---------- */
 
 /* OUT = epilogue(A * W^T): A fp16 [n_seq][rows_per_seq][K], W fp16 [taps*N][K], fp32 accumulate.
@@ -130,6 +159,23 @@ int fseend_op_head(const void* emb_f16, const void* att_f16, int n_frames, int S
                    float* att_f32, void* stream);
 int fseend_op_prep_input(const float* x_packed, const int* cu_seqlens_dev, int B, int Tmax, int Din, int Kpad,
                          const float* scale, const float* shift, void* out_f16, void* stream);
+
+/* GEMM with the LS-EEND epilogues: mode 0 (+bias, act 0 none / 1 ReLU / 2 swish), 4 (GLU: N/2 outputs), 1 (LayerNorm),
+ * 5 (y = residual + alpha*(acc+bias); out = ln_g ? LN(y) : y); out2 (optional) = LayerNorm(out; ln2_g, ln2_b). */
+int fseend_op_gemm_ex(const void* a_f16, int rows_per_seq, int n_seq, int K, const void* w_f16, int N, int mode, int act,
+                      const float* bias, const void* residual_f16, float alpha, const float* ln_g, const float* ln_b,
+                      const float* ln2_g, const float* ln2_b, float ln_eps, const int* seq_len_dev, void* out_f16,
+                      void* out2_f16, void* stream);
+/* Chunkwise retention + group norm + swish gate: qkvg fp16 [B][T][S][1024] (q | k*hd^-.5 | v | g) -> out fp16
+ * [B][T][S][256].  state fp16 [B*S*4*(T/chunk)][64][64] and cross_scale fp32 [B*S*4*(T/chunk)] are workspaces. */
+int fseend_op_retention(const void* qkvg_f16, int B, int S, int T, int chunk, void* state_f16, float* cross_scale,
+                        void* out_f16, void* stream);
+/* Causal depthwise conv (weight fp32 [256][K]) -> per-channel affine -> swish; u/out fp16 [n_seq][T][256];
+ * hist: optional one-step cache fp16 [n_seq][K-1][256] (updated when T == 1). */
+int fseend_op_dwconv_bn_swish(const void* u_f16, const float* w, const float* scale, const float* shift, int n_seq,
+                              int T, int K, void* hist_f16, void* out_f16, void* stream);
+/* Recurrent retention step for 0-based frame index t: state fp32 [n_seq][4][64][64] updated in place. */
+int fseend_op_ret_step(const void* qkvg_f16, float* state, int n_seq, int t, void* out_f16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,169 @@
+"""LS-EEND on B200: per-kernel parity of the LS-specific kernels against torch fp32 on the same fp16 operands, and
+the end-to-end forward against golden logits of the real reference.
+
+End-to-end tolerance.  The LS-EEND network amplifies operand rounding at isolated frames (per-head LayerNorm, eps 1e-6,
+over near-constant retention outputs): emulating fp16 operands in the CPU oracle gives median 1.6e-4 / p99 2.6e-3 /
+max 2.3e-2 on these synthetic weights, and only a split-precision (hi+lo fp16, 3 MMAs) path reaches 1e-4 everywhere
+(DESIGN.md §1).  The tests therefore assert median < 5e-4, p95 < 2e-3 and max < 8e-2, and print the distribution;
+the north-star max-abs 1e-3 bound is NOT met on the tail for LS-EEND in this round."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fs_eend_oracle as FO
+from oracle import ls_eend_oracle as O
+from test_oracle_ls import LS_CASES, load_ls_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def N():
+    from fseend_b200 import native
+    native.lib()
+    return native
+
+
+def ln_ref(x, g, b, eps=1e-5):
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), g, b, eps)
+
+
+def test_gemm_swish_and_glu(N):
+    a = rnd(300, 256, seed=1).half()
+    w = rnd(1024, 256, scale=1 / 16, seed=2).half()
+    bias = rnd(1024, seed=3) * 0.3
+    out, _ = N.op_gemm_ex(a, w, N.EPI_BIAS, act=N.ACT_SWISH, bias=bias)
+    ref = torch.nn.functional.silu(a.float() @ w.float().T + bias)
+    assert (out.float() - ref).abs().max().item() < 5e-3
+    # GLU: weight rows arranged per 256-row tile as [128 value | 128 gate]
+    w2 = rnd(512, 256, scale=1 / 16, seed=4).half()          # logical (2D, D): value rows 0..255, gate rows 256..511
+    b2 = rnd(512, seed=5) * 0.3
+    idx = torch.cat([torch.cat([torch.arange(128 * t, 128 * t + 128), 256 + torch.arange(128 * t, 128 * t + 128)])
+                     for t in range(2)]).to(DEV)
+    out, _ = N.op_gemm_ex(a, w2[idx].contiguous(), N.EPI_GLU, bias=b2[idx].contiguous())
+    h = a.float() @ w2.float().T + b2
+    ref = h[:, :256] * torch.sigmoid(h[:, 256:])
+    assert out.shape == (300, 256)
+    assert (out.float() - ref).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("with_ln1", [False, True])
+def test_gemm_residual_dual_layernorm(N, with_ln1):
+    a = rnd(517, 1024, seed=6).half()
+    w = rnd(256, 1024, scale=1 / 32, seed=7).half()
+    res = (rnd(517, 256, seed=8) * 2).half()
+    bias = rnd(256, seed=9) * 0.3
+    g1, b1 = 1 + 0.3 * rnd(256, seed=10), 0.1 * rnd(256, seed=11)
+    g2, b2 = 1 + 0.3 * rnd(256, seed=12), 0.1 * rnd(256, seed=13)
+    out, out2 = N.op_gemm_ex(a, w, N.EPI_RESID, bias=bias, residual=res, alpha=0.5,
+                             ln_g=g1 if with_ln1 else None, ln_b=b1 if with_ln1 else None, ln2_g=g2, ln2_b=b2)
+    y = res.float() + 0.5 * (a.float() @ w.float().T + bias)
+    if with_ln1:
+        y = ln_ref(y, g1, b1)
+    assert (out.float() - y).abs().max().item() < 8e-3
+    ref2 = ln_ref(out.float(), g2, b2)                 # the kernel normalises the fp16 row it just stored
+    assert (out2.float() - ref2).abs().max().item() < 5e-3
+
+
+def test_dwconv_bn_swish_batch_and_one_step(N):
+    n, T, K = 3, 150, 16
+    u = rnd(n, T, 256, seed=14).half()
+    w = rnd(256, K, scale=0.3, seed=15)
+    sc, sh = 1 + 0.2 * rnd(256, seed=16), 0.2 * rnd(256, seed=17)
+    out = N.op_dwconv_bn_swish(u, w, sc, sh)
+    up = torch.nn.functional.pad(u.float(), (0, 0, K - 1, 0))
+    y = sum(up[:, k:k + T] * w[:, k] for k in range(K))
+    ref = torch.nn.functional.silu(y * sc + sh)
+    assert (out.float() - ref).abs().max().item() < 3e-3
+    # one-step form with the (K-1)-frame cache reproduces the batch result frame by frame
+    hist = torch.zeros(n, K - 1, 256, device=DEV, dtype=torch.float16)
+    for t in range(40):
+        o = N.op_dwconv_bn_swish(u[:, t:t + 1].contiguous(), w, sc, sh, hist=hist)
+        assert (o[:, 0].float() - ref[:, t]).abs().max().item() < 3e-3
+
+
+def retention_ref(qkvg, chunk):
+    """fp32 torch restatement of chunk_recurrent_forward + group norm + gate on the (fp16-rounded) q,k,v,g."""
+    B, T, S, _ = qkvg.shape
+    x = qkvg.float().permute(0, 2, 1, 3).reshape(B * S, T, 4, 4, 64)      # (N, T, {q,k,v,g}, H, hd)
+    q, k, v, g = (x[:, :, i].transpose(1, 2) for i in range(4))            # (N, H, T, hd)
+    N_, H, nc, C = B * S, 4, T // chunk, chunk
+    q, k, v = (t.reshape(N_, H, nc, C, 64) for t in (q, k, v))
+    j = torch.arange(C, device=qkvg.device, dtype=torch.float32)
+    mask = torch.tril(torch.ones(C, C, device=qkvg.device)) / (j + 1).sqrt()[:, None]
+    qk = (q @ k.transpose(-1, -2)) * mask
+    inner = qk.abs().sum(-1, keepdim=True).clamp(min=1)
+    inner_out = (qk / inner) @ v
+    kv = k.transpose(-1, -2) @ (v / math.sqrt(C))
+    state = torch.zeros(N_, H, 64, 64, device=qkvg.device)
+    scale = torch.ones(N_, H, 1, 1, device=qkvg.device)
+    outs = []
+    for c in range(nc):
+        cross = (q[:, :, c] * (math.sqrt(C) / (j + 1).sqrt())[:, None]) @ (state / scale)
+        alls = torch.maximum(inner[:, :, c], scale)
+        outs.append(inner_out[:, :, c] / (alls / inner[:, :, c]) + cross / (alls / scale))
+        state = state + kv[:, :, c]
+        scale = state.abs().sum(-2, keepdim=True).max(-1, keepdim=True).values.clamp(min=1)
+    o = torch.stack(outs, dim=2).reshape(N_, H, T, 64)
+    o = (o - o.mean(-1, keepdim=True)) / torch.sqrt(o.var(-1, unbiased=False, keepdim=True) + 1e-6)
+    o = o * torch.nn.functional.silu(g)
+    return o.transpose(1, 2).reshape(B, S, T, 256).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("B,T,S,chunk", [(2, 500, 1, 500), (1, 1000, 3, 500), (1, 384, 2, 128)])
+def test_retention_chunkwise(N, B, T, S, chunk):
+    qkvg = rnd(B, T, S, 1024, scale=0.7, seed=20 + T).half()
+    out = N.op_retention(qkvg, chunk)
+    ref = retention_ref(qkvg, chunk)
+    err = (out.float() - ref).abs()
+    print(f"retention B={B} T={T} S={S}: max {err.max().item():.2e} mean {err.mean().item():.2e}")
+    # group-norm amplifies fp16 rounding of P at rows whose head output is nearly constant: bound the bulk tightly
+    assert err.mean().item() < 2e-3 and err.flatten().kthvalue(int(0.99 * err.numel())).values.item() < 2e-2
+
+
+def test_retention_step_matches_chunkwise_first_chunk(N):
+    n, T = 5, 60
+    qkvg = rnd(n, T, 1024, scale=0.7, seed=31).half()
+    state = torch.zeros(n, 4, 64, 64, device=DEV)
+    outs = torch.stack([N.op_ret_step(qkvg[:, t].contiguous(), state, t) for t in range(T)], dim=1)   # (n, T, 256)
+    x = qkvg.float().reshape(n, T, 4, 4, 64)
+    q, k, v, g = (x[:, :, i].transpose(1, 2) for i in range(4))
+    j = torch.arange(T, device=DEV, dtype=torch.float32)
+    s = torch.tril(q @ k.transpose(-1, -2)) / (j + 1).sqrt()[:, None]
+    o = s @ v
+    o = (o - o.mean(-1, keepdim=True)) / torch.sqrt(o.var(-1, unbiased=False, keepdim=True) + 1e-6)
+    ref = (o * torch.nn.functional.silu(g)).transpose(1, 2).reshape(n, T, 256)
+    assert (outs.float() - ref).abs().max().item() < 5e-3
+
+
+def make_ls_model(sd):
+    from nnet.model.onl_conformer_retention_enc_1dcnn_tfm_retention_enc_linear_non_autoreg_pos_enc_l2norm_emb_loss_mask import (
+        OnlineConformerRetentionDADiarization)
+    m = OnlineConformerRetentionDADiarization(
+        n_speakers=8, in_size=345, n_units=256, n_heads=4, enc_n_layers=4, dec_n_layers=2, dropout=0.1,
+        max_seqlen=1000, recurrent_chunk_size=500, feed_forward_expansion_factor=4, dec_dim_feedforward=2048,
+        conv_kernel_size=16)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("name", list(LS_CASES))
+def test_ls_logits_vs_reference_golden(name):
+    sd, src, lens, S, g = load_ls_case(name)
+    m = make_ls_model(sd)
+    out, emb, att = m.test([s.cuda() for s in src], lens, max_nspks=S)
+    errs = np.concatenate([np.abs(o.cpu().numpy() - g[f"logits_{i}"]).ravel() for i, o in enumerate(out)])
+    med, p95, p99, mx = np.median(errs), np.percentile(errs, 95), np.percentile(errs, 99), errs.max()
+    print(f"{name}: logit error vs reference  median {med:.2e}  p95 {p95:.2e}  p99 {p99:.2e}  max {mx:.2e}")
+    assert all(tuple(o.shape) == g[f"logits_{i}"].shape for i, o in enumerate(out))
+    assert att[0].shape == (lens[0], S, 256) and emb[0].shape == (lens[0], 256)
+    assert med < 5e-4 and p95 < 2e-3 and mx < 8e-2
