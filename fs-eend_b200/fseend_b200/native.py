@@ -41,7 +41,9 @@ EXPORTS = [
     "fseend_fs_forward", "fseend_fs_forward_host", "fseend_fs_set_profiling", "fseend_fs_get_profile",
     "fseend_fs_launches_per_forward", "fseend_fs_workspace_bytes", "fseend_fs_set_option", "fseend_fs_stream_create",
     "fseend_fs_stream_destroy", "fseend_fs_stream_step", "fseend_fs_stream_frames", "fseend_ls_create",
-    "fseend_ls_destroy", "fseend_ls_padded_len", "fseend_ls_forward", "fseend_ls_launches_per_forward", "fseend_op_gemm",
+    "fseend_ls_destroy", "fseend_ls_padded_len", "fseend_ls_forward", "fseend_ls_launches_per_forward",
+    "fseend_ls_stream_create", "fseend_ls_stream_destroy", "fseend_ls_stream_reset", "fseend_ls_stream_step",
+    "fseend_ls_stream_enc_step", "fseend_ls_stream_dec_step", "fseend_op_gemm",
     "fseend_op_gemm_ex", "fseend_op_retention", "fseend_op_dwconv_bn_swish", "fseend_op_ret_step",
     "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
     "fseend_op_prep_input",
@@ -101,6 +103,18 @@ def lib() -> C.CDLL:
     L.fseend_ls_forward.argtypes = [vp, vp, C.POINTER(ip), ip, ip, vp, vp, vp, vp]
     L.fseend_ls_launches_per_forward.restype = ip
     L.fseend_ls_launches_per_forward.argtypes = [vp]
+    L.fseend_ls_stream_create.restype = ip
+    L.fseend_ls_stream_create.argtypes = [vp, ip, ip, C.POINTER(vp)]
+    L.fseend_ls_stream_destroy.restype = None
+    L.fseend_ls_stream_destroy.argtypes = [vp]
+    L.fseend_ls_stream_reset.restype = ip
+    L.fseend_ls_stream_reset.argtypes = [vp]
+    L.fseend_ls_stream_step.restype = ip
+    L.fseend_ls_stream_step.argtypes = [vp, vp, vp, C.POINTER(ip), vp]
+    L.fseend_ls_stream_enc_step.restype = ip
+    L.fseend_ls_stream_enc_step.argtypes = [vp, vp, ip, vp, vp]
+    L.fseend_ls_stream_dec_step.restype = ip
+    L.fseend_ls_stream_dec_step.argtypes = [vp, vp, ip, vp, vp]
     L.fseend_op_gemm_ex.restype = ip
     L.fseend_op_gemm_ex.argtypes = [vp, ip, ip, ip, vp, ip, ip, ip, vp, vp, fp, vp, vp, vp, vp, fp, vp, vp, vp, vp]
     L.fseend_op_retention.restype = ip
@@ -293,6 +307,46 @@ class LsModel:
     @property
     def launches_per_forward(self) -> int:
         return int(self._L.fseend_ls_launches_per_forward(self._h))
+
+
+class LsStream:
+    """One-step (recurrent) LS-EEND state of B parallel recordings on top of an LsModel."""
+
+    def __init__(self, model: "LsModel", B: int, max_nspks: int):
+        self._L = lib()
+        self.model, self.B, self.S = model, B, max_nspks
+        h = C.c_void_p()
+        _check(self._L.fseend_ls_stream_create(model._h, B, max_nspks, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.fseend_ls_stream_destroy(h)
+
+    def reset(self):
+        _check(self._L.fseend_ls_stream_reset(self._h))
+
+    def step(self, x_t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """Fused frame step.  x_t: CUDA fp32 [B, in_size] or None (flush).  Returns logits [B, S] or None."""
+        if x_t is not None:
+            _require_cuda(x_t)
+        out = torch.empty(self.B, self.S, device="cuda", dtype=torch.float32)
+        produced = C.c_int(0)
+        _check(self._L.fseend_ls_stream_step(self._h, _ptr(x_t), _ptr(out), C.byref(produced), _stream()))
+        return out if produced.value else None
+
+    def enc_step(self, x_t: torch.Tensor, t: int) -> torch.Tensor:
+        _require_cuda(x_t)
+        emb = torch.empty(self.B, self.model.cfg["n_units"], device="cuda", dtype=torch.float32)
+        _check(self._L.fseend_ls_stream_enc_step(self._h, _ptr(x_t), int(t), _ptr(emb), _stream()))
+        return emb
+
+    def dec_step(self, emb: torch.Tensor, t: int) -> torch.Tensor:
+        _require_cuda(emb)
+        att = torch.empty(self.B, self.S, self.model.cfg["n_units"], device="cuda", dtype=torch.float32)
+        _check(self._L.fseend_ls_stream_dec_step(self._h, _ptr(emb), int(t), _ptr(att), _stream()))
+        return att
 
 
 class FsStream:

@@ -24,6 +24,60 @@ class PositionalEncoding(nn.Module):
         self.register_buffer("pe", pe.unsqueeze(0))
 
 
+def _stream_for(owner, states, B, max_nspks):
+    """The native one-step state bound to the caller-owned state list (the reference keeps its recurrent state in
+    these dicts/tensors, LS-EEND/streaming_infer_dia.py:37-49; here they carry a handle to the device state)."""
+    from fseend_b200.native import LsStream
+    holder = states[0] if isinstance(states, (list, tuple)) and states and isinstance(states[0], dict) else None
+    key = "_fseend_stream"
+    st = holder.get(key) if holder is not None else getattr(owner, "_default_stream", None)
+    native = owner.native()
+    if st is None or st.model is not native or st.B != B or st.S != max_nspks:
+        st = LsStream(native, B, max_nspks)
+        if holder is not None:
+            holder[key] = st
+        else:
+            owner._default_stream = st
+    return st
+
+
+class StreamingConv1d(nn.Module):
+    """Frame-by-frame look-ahead Conv1d (reference model file :151-186): ``.conv`` holds the weights (loaded from
+    model.cnn by the caller), ``.buffer``/``.t`` the window state.  The 19-tap window product runs as one tcgen05
+    GEMM (K = 19*256) through the C ABI."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=19):
+        super().__init__()
+        from collections import deque
+        self.kernel_size = kernel_size
+        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size, padding=0)
+        self.buffer = deque(maxlen=kernel_size)
+        self.center = kernel_size // 2
+        self.t = 0
+        self._w16 = None
+        self._w_key = None
+
+    @torch.no_grad()
+    def forward(self, x_t):
+        """x_t: (B, C, 1) -> (B, C_out, 1), or None for the first ``center`` frames."""
+        from fseend_b200 import native as N
+        self.t += 1
+        self.buffer.append(x_t)
+        if self.t < self.center + 1:
+            return None
+        pad = [torch.zeros_like(x_t)] * (self.kernel_size - len(self.buffer))
+        win = torch.cat(pad + list(self.buffer), dim=2)                       # (B, C, K)
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version)
+        if self._w16 is None or self._w_key != key:
+            # out[b, co] = sum_{k, ci} W[co, ci, k] * win[b, ci, k]  ->  A [B, K*C] (k-major), W' [C_out, K*C]
+            self._w16 = w.detach().permute(0, 2, 1).reshape(w.shape[0], -1).to(torch.float16).contiguous()
+            self._w_key = key
+        a = win.permute(0, 2, 1).reshape(win.shape[0], -1).to(torch.float16).contiguous()
+        y = N.op_gemm(a, self._w16, N.EPI_BIAS, bias=self.conv.bias.detach().float().contiguous())
+        return y.float().unsqueeze(-1)
+
+
 class EmbeddingEncoderModule(nn.Module):
     def __init__(self, in_size, n_units, n_heads, n_layers, recurrent_chunk_size, feed_forward_expansion_factor=8,
                  conv_expansion_factor=2, dropout=0.1, conv_kernel_size=16, half_step_residual=True, max_seqlen=500):
@@ -37,6 +91,17 @@ class EmbeddingEncoderModule(nn.Module):
             feed_forward_dropout_p=dropout, attention_dropout_p=dropout, conv_dropout_p=dropout,
             conv_kernel_size=conv_kernel_size, half_step_residual=half_step_residual,
             recurrent_chunk_size=recurrent_chunk_size)
+        self._owner = None
+
+    @torch.no_grad()
+    def forward_one_step(self, x_t: Tensor, t: int, ret_states: list, conv_caches: list) -> Tensor:
+        """Reference :291-293 -> conformer/encoder.py:223-228.  x_t: (B, 1, in_size) -> (B, 1, n_units).  The
+        recurrent state lives on the device, bound to ``ret_states``; ``conv_caches`` is accepted for signature
+        compatibility (its contents are not used)."""
+        owner = self._owner()
+        st = _stream_for(owner, ret_states, x_t.shape[0], getattr(owner, "_one_step_nspks", 4))
+        dev = owner.cnn.weight.device
+        return st.enc_step(x_t[:, 0].to(device=dev, dtype=torch.float32).contiguous(), t).unsqueeze(1)
 
 
 class MaskedTransformerDecoderModel(nn.Module):
@@ -53,6 +118,17 @@ class MaskedTransformerDecoderModel(nn.Module):
         self.layers = nn.ModuleList([
             TransformerEncoderFusionLayer(n_units, n_heads, recurrent_chunk_size, dim_feedforward, dropout,
                                           batch_first=True) for _ in range(n_layers)])
+        self._owner = None
+
+    @torch.no_grad()
+    def forward_one_step(self, emb_t: Tensor, t: int, max_nspks: int, ret_states: list) -> Tensor:
+        """Reference :235-243.  emb_t: (B, 1, D) conv'ed + L2-normalised embedding -> (B, 1, max_nspks, D)
+        un-normalised attractors of decoder frame t."""
+        owner = self._owner()
+        st = _stream_for(owner, ret_states, emb_t.shape[0], max_nspks)
+        dev = owner.cnn.weight.device
+        att = st.dec_step(emb_t[:, 0].to(device=dev, dtype=torch.float32).contiguous(), t)
+        return att.unsqueeze(1)
 
 
 class OnlineConformerRetentionDADiarization(nn.Module):
@@ -77,6 +153,15 @@ class OnlineConformerRetentionDADiarization(nn.Module):
         self.cnn = nn.Conv1d(n_units, n_units, kernel_size=2 * conv_delay + 1, padding=conv_delay)
         self._native = None
         self._native_key = None
+        import weakref
+        self.enc._owner = weakref.ref(self)
+        self.dec._owner = weakref.ref(self)
+
+    def new_stream(self, batch_size: int = 1, max_nspks: int = 6):
+        """Fused one-step driver (encoder + look-ahead conv + decoder + head per call): ``stream.step(x_t)`` with
+        x_t (B, in_size) returns (B, max_nspks) logits of frame t - conv_delay or None; ``stream.step(None)`` flushes."""
+        from fseend_b200.native import LsStream
+        return LsStream(self.native(), batch_size, max_nspks)
 
     def _native_cfg(self):
         return dict(in_size=self.enc.in_size, n_units=self.n_units, n_heads=self.enc.n_heads,

@@ -134,6 +134,19 @@ int fseend_ls_forward(fseend_ls_model* m, const float* x_packed_dev, const int* 
                       float* logits_dev, float* emb_dev, float* att_dev, void* stream);
 int fseend_ls_launches_per_forward(const fseend_ls_model* m);
 
+/* One-step (recurrent) LS-EEND.  State per stream: retention states + conv caches (O(1) per frame) and the encoder
+ * history of the look-ahead conv.  fseend_ls_stream_step is the fused loop body of streaming_predict
+ * (LS-EEND/streaming_infer_dia.py:52-97; x_t NULL = flush step); enc_step / dec_step are the split entry points behind
+ * model.enc.forward_one_step (conformer/encoder.py:223-228) and model.dec.forward_one_step (model file :235-243),
+ * t = 0 resets the corresponding states. */
+typedef struct fseend_ls_stream fseend_ls_stream;
+int fseend_ls_stream_create(fseend_ls_model* m, int B, int max_nspks, fseend_ls_stream** out);
+void fseend_ls_stream_destroy(fseend_ls_stream* s);
+int fseend_ls_stream_reset(fseend_ls_stream* s);
+int fseend_ls_stream_step(fseend_ls_stream* s, const float* x_t_dev, float* logits_dev, int* produced, void* stream);
+int fseend_ls_stream_enc_step(fseend_ls_stream* s, const float* x_t_dev, int t, float* emb_dev, void* stream);
+int fseend_ls_stream_dec_step(fseend_ls_stream* s, const float* emb_dev, int t, float* att_dev, void* stream);
+
 /* ---- single-kernel entry points (used by the parity tests; all pointers are device pointers) ---------- */
 
 /* OUT = epilogue(A * W^T): A fp16 [n_seq][rows_per_seq][K], W fp16 [taps*N][K], fp32 accumulate.
