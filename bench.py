@@ -287,12 +287,18 @@ def run_ours(args):
         prof_table = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] // n_prof,
                           "tflops": (algorithmic_flops(k, B, T, S) / (v[0] / v[1] * 1e-3) / 1e12)
                           if algorithmic_flops(k, B, T, S) else None} for k, v in prof.items()}
+        traffic = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f)
+        except Exception:
+            pass
         dom = max(prof, key=lambda k: prof[k][0])
         d_ms = prof[dom][0] / prof[dom][1]
         fl = algorithmic_flops(dom, B, T, S)
         ach = fl / (d_ms * 1e-3) / 1e12
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+                "frac": ach / pk["tflops"], "traffic": traffic.get(dom), "peak_source": pk["source"],
                 "avg_launch_ms": d_ms, "algorithmic_flops_per_launch": fl}
         for k in ("dec.attn_causal",):
             if k in prof:
