@@ -20,8 +20,11 @@ struct AttnParams {
   int tile_rows;     // block-diagonal: rows per CTA
 };
 
-// causal:     tmQKV 4-D (768, S, T, B) box (64,1,128,1);   tmO 4-D (256, S, T, B) box (64,1,128,1)
-// block-diag: tmQKV 4-D (768, 1, rows, 1) box (64,1,128,1); tmO 4-D (256, 1, rows, 1) box (64,1,tile_rows,1)
-void launch_attn(const CUtensorMap& tmQKV, const CUtensorMap& tmO, const AttnParams& p, cudaStream_t stream);
+// causal:     tmQ 4-D (768, S, T, B) box (64,1,128,1), tmKV same tensor with box (64,1,64,1);
+//             tmO 4-D (256, S, T, B) box (64,1,128,1)
+// block-diag: tmQ 4-D (768, 1, rows, 1) box (64,1,128,1), tmKV box (64,1,64,1); tmO 4-D (256, 1, rows, 1) box
+//             (64,1,tile_rows,1)
+void launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const CUtensorMap& tmO, const AttnParams& p,
+                 cudaStream_t stream);
 
 }  // namespace fseend

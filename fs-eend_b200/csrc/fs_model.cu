@@ -126,7 +126,7 @@ struct fseend_fs_model {
   // descriptors
   CUtensorMap tm_x16, tm_hA, tm_hB, tm_qkv_e_out, tm_qkv_e_attn, tm_ao_e_attn, tm_ao_e, tm_f_e_out, tm_f_e_in;
   CUtensorMap tm_hconv_in, tm_hB_seq, tm_emb_out, tm_emb_in, tm_cvt_out;
-  CUtensorMap tm_aX, tm_aY, tm_aZ, tm_qkv_d_out, tm_qkv_d_attn, tm_ao_d_attn, tm_qkv_d_spk, tm_ao_d_spk, tm_ao_d, tm_f_d_out, tm_f_d_in;
+  CUtensorMap tm_aX, tm_aY, tm_aZ, tm_qkv_d_out, tm_qkv_d_attn, tm_ao_d_attn, tm_qkv_d_spk, tm_ao_d_spk, tm_ao_d, tm_qkv_e_kv, tm_qkv_d_kv, tm_qkv_d_spk_kv, tm_f_d_out, tm_f_d_in;
 
   int spk_mode = 1;  // 0: CUDA-core speaker attention, 1: tcgen05 block-diagonal attention
   int ffn_mode = 3;  // 0: two GEMM launches (hidden layer through HBM); fused: 1 = SS, 2 = SS + 2-CTA weight multicast,
@@ -154,7 +154,7 @@ struct fseend_fs_stream {
   std::vector<std::unique_ptr<DevBuf>> enc_k, enc_v, dec_k, dec_v;
   DevBuf hist, x16, h0, h1, qkv, ao, a0, a1, a2, emb, cu;
   CUtensorMap tm_x16, tm_h0, tm_h1, tm_qkv_e, tm_ao_e, tm_hist, tm_emb_out, tm_emb_in, tm_cvt_out, tm_a0, tm_a1, tm_a2,
-      tm_qkv_d, tm_ao_d, tm_qkv_spk, tm_ao_spk;
+      tm_qkv_d, tm_ao_d, tm_qkv_spk, tm_qkv_spk_kv, tm_ao_spk;
 };
 
 namespace fseend {
@@ -284,10 +284,10 @@ void build_model(fseend_fs_model* m, const TensorTable& tt) {
 CUtensorMap rows_map(const DevBuf& buf, uint64_t cols, uint64_t rows_per_seq, uint64_t n_seq) {
   return make_tmap_rows3d(buf.p, cols, cols, rows_per_seq, n_seq, 128);
 }
-CUtensorMap attn_map(const DevBuf& buf, uint64_t cols, int S, int T, int B) {
+CUtensorMap attn_map(const DevBuf& buf, uint64_t cols, int S, int T, int B, uint32_t box_rows = 128) {
   uint64_t dims[4] = {cols, static_cast<uint64_t>(S), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
   uint64_t str[3] = {cols, cols * S, cols * S * T};
-  uint32_t box[4] = {64, 1, 128, 1};
+  uint32_t box[4] = {64, 1, box_rows, 1};
   return make_tmap_f16(buf.p, 4, dims, str, box);
 }
 
@@ -327,6 +327,7 @@ void make_plan(fseend_fs_model* m, int B, int T, int S) {
   m->tm_hB = rows_map(m->hB, D, Me, 1);
   m->tm_qkv_e_out = rows_map(m->qkv_e, 3 * D, Me, 1);
   m->tm_qkv_e_attn = attn_map(m->qkv_e, 3 * D, 1, T, B);
+  m->tm_qkv_e_kv = attn_map(m->qkv_e, 3 * D, 1, T, B, 64);
   m->tm_ao_e_attn = attn_map(m->ao_e, D, 1, T, B);
   m->tm_ao_e = rows_map(m->ao_e, D, Me, 1);
   m->tm_f_e_out = rows_map(m->f_e, c.enc_dim_feedforward, Me, 1);
@@ -347,12 +348,15 @@ void make_plan(fseend_fs_model* m, int B, int T, int S) {
   m->tm_aZ = rows_map(m->aZ, D, Md, 1);
   m->tm_qkv_d_out = rows_map(m->qkv_d, 3 * D, Md, 1);
   m->tm_qkv_d_attn = attn_map(m->qkv_d, 3 * D, S, T, B);
+  m->tm_qkv_d_kv = attn_map(m->qkv_d, 3 * D, S, T, B, 64);
   m->tm_ao_d_attn = attn_map(m->ao_d, D, S, T, B);
   {
     uint64_t dq[4] = {static_cast<uint64_t>(3 * D), 1, Md, 1}, sq[3] = {3ull * D, 3ull * D, 3ull * D * Md};
     uint64_t dout[4] = {static_cast<uint64_t>(D), 1, Md, 1}, so[3] = {1ull * D, 1ull * D, 1ull * D * Md};
     uint32_t bq[4] = {64, 1, 128, 1}, bo[4] = {64, 1, static_cast<uint32_t>((128 / S) * S), 1};
     m->tm_qkv_d_spk = make_tmap_f16(m->qkv_d.p, 4, dq, sq, bq);
+    uint32_t bkv[4] = {64, 1, 64, 1};
+    m->tm_qkv_d_spk_kv = make_tmap_f16(m->qkv_d.p, 4, dq, sq, bkv);
     m->tm_ao_d_spk = make_tmap_f16(m->ao_d.p, 4, dout, so, bo);
   }
   m->tm_ao_d = rows_map(m->ao_d, D, Md, 1);
@@ -467,7 +471,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     }
     {
       AttnParams a{B, 1, T, c.n_heads, c.has_mask ? c.mask_delay : (1 << 28), 1.f / sqrtf(64.f), ATTN_CAUSAL, 128};
-      L.run("enc.attn_causal", [&] { launch_attn(m->tm_qkv_e_attn, m->tm_ao_e_attn, a, st); });
+      L.run("enc.attn_causal", [&] { launch_attn(m->tm_qkv_e_attn, m->tm_qkv_e_kv, m->tm_ao_e_attn, a, st); });
     }
     {
       GemmParams p = flat_params(Me, D, D, EPI_LN);
@@ -548,7 +552,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     }
     {
       AttnParams a{B, S, T, c.n_heads, c.mask_delay, 1.f / sqrtf(64.f), ATTN_CAUSAL, 128};
-      L.run("dec.attn_causal", [&] { launch_attn(m->tm_qkv_d_attn, m->tm_ao_d_attn, a, st); });
+      L.run("dec.attn_causal", [&] { launch_attn(m->tm_qkv_d_attn, m->tm_qkv_d_kv, m->tm_ao_d_attn, a, st); });
     }
     {
       GemmParams p = flat_params(Md, D, D, EPI_LN);
@@ -566,7 +570,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     }
     if (m->spk_mode == 1) {
       AttnParams a{1, S, static_cast<int>(Md), c.n_heads, 0, 1.f / sqrtf(64.f), ATTN_BLOCKDIAG, (128 / S) * S};
-      L.run("dec.spk_attn", [&] { launch_attn(m->tm_qkv_d_spk, m->tm_ao_d_spk, a, st); });
+      L.run("dec.spk_attn", [&] { launch_attn(m->tm_qkv_d_spk, m->tm_qkv_d_spk_kv, m->tm_ao_d_spk, a, st); });
     } else {
       L.run("dec.spk_attn", [&] {
         launch_spk_attn(static_cast<const __half*>(m->qkv_d.p), static_cast<__half*>(m->ao_d.p),
@@ -690,6 +694,8 @@ void stream_init(fseend_fs_stream* s, fseend_fs_model* m, int B, int S) {
     uint64_t d_o[4] = {static_cast<uint64_t>(D), 1, Rd, 1}, so[3] = {1ull * D, 1ull * D, 1ull * D * Rd};
     uint32_t bq[4] = {64, 1, 128, 1}, bo[4] = {64, 1, static_cast<uint32_t>((128 / S) * S), 1};
     s->tm_qkv_spk = make_tmap_f16(s->qkv.p, 4, dq, sq, bq);
+    uint32_t bkv[4] = {64, 1, 64, 1};
+    s->tm_qkv_spk_kv = make_tmap_f16(s->qkv.p, 4, dq, sq, bkv);
     s->tm_ao_spk = make_tmap_f16(s->ao.p, 4, d_o, so, bo);
   }
   stream_alloc(s, 1024);
@@ -797,7 +803,7 @@ int stream_step(fseend_fs_stream* s, const float* x_t, float* logits, cudaStream
     }
     {
       AttnParams a{1, S, static_cast<int>(Rd), c.n_heads, 0, scale, ATTN_BLOCKDIAG, (128 / S) * S};
-      launch_attn(s->tm_qkv_spk, s->tm_ao_spk, a, st);
+      launch_attn(s->tm_qkv_spk, s->tm_qkv_spk_kv, s->tm_ao_spk, a, st);
     }
     {
       GemmParams p = flat_params(Rd, D, D, EPI_LN);
@@ -1109,9 +1115,11 @@ int fseend_op_causal_attn(const void* qkv_f16, int B, int T, int S, int H, int m
     uint64_t so[3] = {256, 256ull * S, 256ull * S * T};
     uint32_t box[4] = {64, 1, 128, 1};
     CUtensorMap tq = make_tmap_f16(qkv_f16, 4, dq, sq, box);
+    uint32_t bkv[4] = {64, 1, 64, 1};
+    CUtensorMap tkv = make_tmap_f16(qkv_f16, 4, dq, sq, bkv);
     CUtensorMap to = make_tmap_f16(out_f16, 4, d_o, so, box);
     AttnParams a{B, S, T, H, mask_delay, scale, ATTN_CAUSAL, 128};
-    launch_attn(tq, to, a, static_cast<cudaStream_t>(stream));
+    launch_attn(tq, tkv, to, a, static_cast<cudaStream_t>(stream));
     CUDA_CHECK(cudaGetLastError());
   });
 }
@@ -1125,9 +1133,11 @@ int fseend_op_spk_attn_tc(const void* qkv_f16, int n_frames, int S, float scale,
     uint64_t d_o[4] = {256, 1, rows, 1}, so[3] = {256, 256, 256 * rows};
     uint32_t bq[4] = {64, 1, 128, 1}, bo[4] = {64, 1, static_cast<uint32_t>((128 / S) * S), 1};
     CUtensorMap tq = make_tmap_f16(qkv_f16, 4, dq, sq, bq);
+    uint32_t bkv[4] = {64, 1, 64, 1};
+    CUtensorMap tkv = make_tmap_f16(qkv_f16, 4, dq, sq, bkv);
     CUtensorMap to = make_tmap_f16(out_f16, 4, d_o, so, bo);
     AttnParams a{1, S, static_cast<int>(rows), 4, 0, scale, ATTN_BLOCKDIAG, (128 / S) * S};
-    launch_attn(tq, to, a, static_cast<cudaStream_t>(stream));
+    launch_attn(tq, tkv, to, a, static_cast<cudaStream_t>(stream));
     CUDA_CHECK(cudaGetLastError());
   });
 }

@@ -48,14 +48,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a mis-programmed pipeline traps (launch failure on the host) instead of hanging the GPU.
-#ifndef FSEEND_WAIT_LIMIT_CYCLES
-#define FSEEND_WAIT_LIMIT_CYCLES 4000000000ll  // ~2 s at 1.9 GHz
+// mbarrier.try_wait suspends the thread in hardware for a bounded time, so the loop below is a few instructions
+// per wake-up; the iteration limit corresponds to seconds.
+#ifndef FSEEND_WAIT_LIMIT_SPINS
+#define FSEEND_WAIT_LIMIT_SPINS (1u << 26)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > FSEEND_WAIT_LIMIT_CYCLES) {
+    if (++spins > FSEEND_WAIT_LIMIT_SPINS) {
       printf("[fseend] mbarrier wait timeout: tag=%d block=(%d,%d) thread=%d parity=%u\n", tag, blockIdx.x,
              blockIdx.y, threadIdx.x, parity);
       __trap();
