@@ -3,19 +3,21 @@
 //   * ATTN_BLOCKDIAG : speaker-axis attention — the [frames*S] attractor rows are processed as 128-row tiles in
 //                      which a row only sees the S rows of its own frame (block-diagonal mask).
 //
-// One CTA = one (sequence, head, 128-query tile); KV is consumed in 64-row tiles.  160 threads:
-//   warps 0-3 : softmax; thread r owns query row r (TMEM lane r).  One TMEM pass per KV tile (64 scores in
-//               registers), ex2.approx in fp32 (the packed f16x2 form lowers to two MUFU ops plus permutes — measured),
-//               P written as fp16 into a 128B-swizzled smem tile (A operand of the PV MMA).
-//               O accumulates in TMEM across KV tiles; when a row's running max grows, the warp rescales its
-//               O rows in place (tcgen05.ld -> scale -> tcgen05.st), FlashAttention-4 style.
-//   warp 4    : lane 0 issues TMA loads (Q once; K/V tiles through a 4-stage ring) and the tcgen05 MMAs
-//               S = Q K^T (M128 N64 K64) and O += P V (M128 N64 K64, V consumed MN-major straight from its
-//               row-major [kv][64] TMA tile).
-// S (TMEM) and P (smem) are double-buffered: QK^T of tile j+2 is issued as soon as the softmax of tile j has read
-// its scores, so the softmax warps never wait for the tensor pipe in steady state and the PV of tile j runs under the
-// softmax of tile j+1.  Causality skips KV tiles above the diagonal; warps whose rows see nothing of a diagonal tile
-// skip its exponentials.  Two CTAs per SM (112 KB smem, 256 TMEM columns each).
+// PERSISTENT kernel: 2 CTAs per SM, each looping over work items (sequence, head, 128-query tile), heaviest first.
+// Profiling the one-item-per-CTA versions showed the same L2->SM sector rate (85 sectors/ns) for both masks and
+// ~30 KB in flight per SM: load -> compute -> store ran serially per CTA, so the kernel was bound by memory-level
+// parallelism, not by MUFU, issue slots or the tensor pipe.  Here a dedicated TMA warp runs ahead across item
+// boundaries (Q double-buffered, 3-stage K/V ring), keeping loads of the next item in flight under the current one.
+//
+// Roles (192 threads):
+//   warps 0-3 : softmax; thread r owns query row r (TMEM lane r).  One TMEM pass per 64-column KV tile, ex2.approx in
+//               fp32, P packed to fp16 into a 128B-swizzled smem tile (A operand of the PV MMA).  O accumulates in
+//               TMEM; when a row's running max grows the warp rescales its O rows in place (tcgen05.ld/st).
+//   warp 4    : lane 0 = TMA producer (Q, K/V tiles).
+//   warp 5    : lane 0 = tcgen05 issuer: S = Q K^T (M128 N64 K64) and O += P V (M128 N64 K64, V consumed MN-major
+//               straight from its row-major [kv][64] tile).  S (TMEM) and P (smem) are double-buffered.
+// Causality skips KV tiles above the diagonal; warps whose rows see nothing of a diagonal half-tile skip its
+// exponentials.
 #include "attn.cuh"
 #include "ptx.cuh"
 
@@ -23,32 +25,23 @@ namespace fseend {
 
 namespace {
 
-constexpr int kTile = 128;                 // query rows per CTA
+constexpr int kTile = 128;                 // query rows per item
 constexpr int kKV = 64;                    // KV rows per tile
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kQBytes = kTile * 64 * 2;    // 16 KB
 constexpr int kKBytes = kKV * 64 * 2;      // 8 KB
 constexpr int kStageBytes = 2 * kKBytes;   // K then V
 constexpr int kPBytes = kTile * kKV * 2;   // 16 KB
-constexpr int kOffQ = 0;
-constexpr int kOffKV = kOffQ + kQBytes;
-constexpr int kOffP = kOffKV + kStages * kStageBytes;   // 2 buffers
-constexpr int kOffBar = kOffP + 2 * kPBytes;            // mbarriers + tmem slot at the tail of dynamic smem
-constexpr int kSmemBytes = kOffBar + 256;
+constexpr int kOffQ = 0;                                   // 2 buffers
+constexpr int kOffKV = kOffQ + 2 * kQBytes;
+constexpr int kOffP = kOffKV + kStages * kStageBytes;      // 2 buffers
+constexpr int kOffBar = kOffP + 2 * kPBytes;               // mbarriers + tmem slot at the tail of dynamic smem
+constexpr int kSmemBytes = kOffBar + 256;                  // 112 KB + 256 B
 constexpr uint32_t kTmemCols = 256;        // S0 [0,64), S1 [64,128), O [128,192)
-
-#ifndef FSEEND_ATTN_EXP_F32
-#define FSEEND_ATTN_EXP_F32 0
-#endif
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
-  uint32_t y;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
 
@@ -65,18 +58,51 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__global__ void __launch_bounds__(160, 2)
+// One work item: coordinates and KV extent.
+struct Item {
+  int q0, h, b, s, n_kv, kv_first, last_key;
+};
+__device__ __forceinline__ Item decode_item(const AttnParams& p, int id) {
+  Item it;
+  if (p.mode == ATTN_CAUSAL) {
+    const int n_qt = (p.T + kTile - 1) / kTile;
+    const int per_qt = p.H * p.B * p.S;
+    const int qt = n_qt - 1 - id / per_qt;          // heaviest (latest) query tiles first
+    const int rest = id % per_qt;
+    it.h = rest % p.H;
+    const int z = rest / p.H;
+    it.b = z / p.S;
+    it.s = z % p.S;
+    it.q0 = qt * kTile;
+    it.last_key = min(it.q0 + kTile - 1 + p.mask_delay, p.T - 1);
+    it.n_kv = it.last_key / kKV + 1;
+    it.kv_first = 0;
+  } else {
+    it.h = id % p.H;
+    it.b = 0;
+    it.s = 0;
+    it.q0 = (id / p.H) * p.tile_rows;               // T = total rows; tile_rows = (128 / S) * S
+    it.last_key = min(it.q0 + p.tile_rows, p.T) - 1 - it.q0;   // tile-relative
+    it.n_kv = it.last_key / kKV + 1;
+    it.kv_first = it.q0;
+  }
+  return it;
+}
+
+__global__ void __launch_bounds__(192, 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-            const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+            const __grid_constant__ CUtensorMap tmO, const AttnParams p, const int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;     // [4]
-  uint64_t* kv_empty = bars + 5;    // [4]
-  uint64_t* s_full = bars + 9;      // [2]
-  uint64_t* p_ready = bars + 11;    // [2]
-  uint64_t* pv_done = bars + 13;    // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* q_full = bars + 0;      // [2]
+  uint64_t* q_empty = bars + 2;     // [2]
+  uint64_t* kv_full = bars + 4;     // [3]
+  uint64_t* kv_empty = bars + 7;    // [3]
+  uint64_t* s_full = bars + 10;     // [2]
+  uint64_t* p_ready = bars + 12;    // [2]
+  uint64_t* pv_done = bars + 14;    // [2]
+  uint64_t* o_free = bars + 16;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -86,44 +112,25 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     __trap();
   }
 
-  // ---- tile coordinates
-  int q0, h, b, s, n_kv, kv_first, last_key = 0;
-  h = blockIdx.y;
-  if (p.mode == ATTN_CAUSAL) {
-    const int n_qt = (p.T + kTile - 1) / kTile;
-    const int qt = n_qt - 1 - static_cast<int>(blockIdx.x);  // heaviest (latest) query tiles first
-    b = blockIdx.z / p.S;
-    s = blockIdx.z % p.S;
-    q0 = qt * kTile;
-    last_key = min(q0 + kTile - 1 + p.mask_delay, p.T - 1);
-    n_kv = last_key / kKV + 1;
-    kv_first = 0;
-  } else {
-    b = 0;
-    s = 0;
-    q0 = blockIdx.x * p.tile_rows;   // T = total rows; tile_rows = (128 / S) * S
-    last_key = min(q0 + p.tile_rows, p.T) - 1 - q0;   // tile-relative
-    n_kv = last_key / kKV + 1;
-    kv_first = q0;
-  }
-
   if (tid == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 128);
       mbar_init(&pv_done[i], 1);
     }
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(o_free, 128);
     fence_barrier_init();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmO);
   }
-  if (warp == 4) tmem_alloc(tmem_base_slot, kTmemCols);
+  if (warp == 5) tmem_alloc(tmem_base_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -132,55 +139,73 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   if (warp == 4) {
     if (lane == 0) {
-      // ------------------------------------------------------------ control thread: TMA + MMA issue
-      auto load_kv = [&](int j) {
-        const int st = j % kStages;
-        const int row = kv_first + j * kKV;
-        uint8_t* dst = smem + kOffKV + st * kStageBytes;
-        mbar_arrive_expect_tx(&kv_full[st], kStageBytes);
-        tma_load_4d(dst, &tmKV, &kv_full[st], 256 + h * 64, s, row, b);
-        tma_load_4d(dst + kKBytes, &tmKV, &kv_full[st], 512 + h * 64, s, row, b);
-      };
+      // ------------------------------------------------------------ TMA producer (runs ahead across items)
+      uint32_t g = 0;   // KV tiles issued so far (ring position)
+      uint32_t n = 0;   // items issued so far
+      for (int id = blockIdx.x; id < n_items; id += gridDim.x, ++n) {
+        const Item it = decode_item(p, id);
+        const int qb = n & 1;
+        mbar_wait(&q_empty[qb], ((n >> 1) & 1) ^ 1, 10);
+        mbar_arrive_expect_tx(&q_full[qb], kQBytes);
+        tma_load_4d(smem + kOffQ + qb * kQBytes, &tmQ, &q_full[qb], it.h * 64, it.s, it.q0, it.b);
+        for (int j = 0; j < it.n_kv; ++j, ++g) {
+          const int st = g % kStages;
+          mbar_wait(&kv_empty[st], ((g / kStages) & 1) ^ 1, 11);
+          uint8_t* dst = smem + kOffKV + st * kStageBytes;
+          const int row = it.kv_first + j * kKV;
+          mbar_arrive_expect_tx(&kv_full[st], kStageBytes);
+          tma_load_4d(dst, &tmKV, &kv_full[st], 256 + it.h * 64, it.s, row, it.b);
+          tma_load_4d(dst + kKBytes, &tmKV, &kv_full[st], 512 + it.h * 64, it.s, row, it.b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
       constexpr uint32_t idesc_qk = make_idesc_f16(128, kKV, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, true);
-      const uint64_t qdesc = smem_desc_sw128(smem_u32(smem + kOffQ));
-      auto issue_qk = [&](int j) {
-        const int st = j % kStages;
-        mbar_wait(&kv_full[st], (j / kStages) & 1, 11);
-        tc_fence_after();
-        const uint64_t kdesc = smem_desc_sw128(smem_u32(smem + kOffKV + st * kStageBytes));
-        const uint32_t tmem_S = tmem_base + (j & 1) * kKV;
+      uint32_t g = 0, n = 0;
+      for (int id = blockIdx.x; id < n_items; id += gridDim.x, ++n) {
+        const Item it = decode_item(p, id);
+        const int qb = n & 1;
+        const uint64_t qdesc = smem_desc_sw128(smem_u32(smem + kOffQ + qb * kQBytes));
+        auto issue_qk = [&](uint32_t gj) {
+          const int st = gj % kStages;
+          mbar_wait(&kv_full[st], (gj / kStages) & 1, 12);
+          tc_fence_after();
+          const uint64_t kdesc = smem_desc_sw128(smem_u32(smem + kOffKV + st * kStageBytes));
+          const uint32_t tmem_S = tmem_base + (gj & 1) * kKV;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_S, qdesc + 2 * kk, kdesc + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
-      };
-
-      mbar_arrive_expect_tx(q_full, kQBytes);
-      tma_load_4d(smem + kOffQ, &tmQ, q_full, h * 64, s, q0, b);
-      for (int j = 0; j < min(n_kv, kStages); ++j) load_kv(j);
-      mbar_wait(q_full, 0, 10);
-      issue_qk(0);
-      if (n_kv > 1) issue_qk(1);
-
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % kStages, pb = j & 1;
-        mbar_wait(&p_ready[pb], (j >> 1) & 1, 12);   // P(j) in smem, S(j) fully read, O rescaled if needed
-        tc_fence_after();
-        const int valid_cols = min(kKV, last_key - j * kKV + 1);
-        const int n_k16 = (valid_cols + 15) >> 4;
-        const uint64_t pdesc = smem_desc_sw128(smem_u32(smem + kOffP + pb * kPBytes));
-        const uint64_t vdesc = smem_desc_sw128(smem_u32(smem + kOffKV + st * kStageBytes + kKBytes));
-        for (int kk = 0; kk < n_k16; ++kk) {
-          // V is MN-major: 16 kv rows = 16 * 128 B = 2048 B per K step -> +128 in 16-byte units
-          umma_f16(tmem_O, pdesc + 2 * kk, vdesc + 128 * kk, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_S, qdesc + 2 * kk, kdesc + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
+          umma_commit(&s_full[gj & 1]);
+        };
+        mbar_wait(&q_full[qb], (n >> 1) & 1, 13);
+        issue_qk(g);
+        if (it.n_kv > 1) issue_qk(g + 1);
+        if (it.n_kv <= 2) umma_commit(&q_empty[qb]);   // every QK^T of this item has been issued
+        for (int j = 0; j < it.n_kv; ++j) {
+          const uint32_t gj = g + j;
+          const int st = gj % kStages, pb = gj & 1;
+          mbar_wait(&p_ready[pb], (gj >> 1) & 1, 14);   // P(j) in smem, S(j) fully read, O rescaled if needed
+          if (j == 0) mbar_wait(o_free, (n & 1) ^ 1, 15);   // the previous item's O has been read out
+          tc_fence_after();
+          const int valid_cols = min(kKV, it.last_key - j * kKV + 1);
+          const int n_k16 = (valid_cols + 15) >> 4;
+          const uint64_t pdesc = smem_desc_sw128(smem_u32(smem + kOffP + pb * kPBytes));
+          const uint64_t vdesc = smem_desc_sw128(smem_u32(smem + kOffKV + st * kStageBytes + kKBytes));
+          for (int kk = 0; kk < n_k16; ++kk) {
+            // V is MN-major: 16 kv rows = 16 * 128 B = 2048 B per K step -> +128 in 16-byte units
+            umma_f16(tmem_O, pdesc + 2 * kk, vdesc + 128 * kk, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&pv_done[pb]);
+          umma_commit(&kv_empty[st]);
+          if (j + 2 < it.n_kv) {
+            issue_qk(gj + 2);                          // S(j) has been consumed: its TMEM buffer is free
+            if (j + 3 == it.n_kv) umma_commit(&q_empty[qb]);
+          }
         }
-        umma_commit(&pv_done[pb]);
-        umma_commit(&kv_empty[st]);
-        if (j + 2 < n_kv) issue_qk(j + 2);           // S(j) has been consumed: its TMEM buffer is free
-        if (j + kStages < n_kv) {
-          mbar_wait(&kv_empty[st], (j / kStages) & 1, 14);
-          load_kv(j + kStages);
-        }
+        g += it.n_kv;
       }
     }
     __syncwarp();
@@ -189,172 +214,181 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const int r = tid;                 // query row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     const float sl = p.scale * 1.4426950408889634f;
-    float m_run = -INFINITY, l_run = 0.f;
+    uint32_t g = 0, n = 0;
+    for (int id = blockIdx.x; id < n_items; id += gridDim.x, ++n) {
+      const Item it = decode_item(p, id);
+      const int q0 = it.q0;
+      float m_run = -INFINITY, l_run = 0.f;
 
-    for (int j = 0; j < n_kv; ++j) {
-      const int pb = j & 1;
-      // visible columns of this KV tile for this row: [lo, hi] (tile-relative)
-      int lo, hi, whi;      // whi: largest hi within the warp (warp-uniform)
-      bool full_tile;       // CTA-uniform: every row sees all 64 columns
-      if (p.mode == ATTN_CAUSAL) {
-        lo = 0;
-        hi = min(q0 + r + p.mask_delay, p.T - 1) - j * kKV;
-        whi = min(q0 + warp * 32 + 31 + p.mask_delay, p.T - 1) - j * kKV;
-        full_tile = (j * kKV + kKV - 1) <= min(q0 + p.mask_delay, p.T - 1);
-      } else {
-        const int flo = (r / p.S) * p.S;                       // first row of this row's frame (128-tile relative)
-        int fhi = (r < p.tile_rows) ? flo + p.S - 1 : -1;
-        if (q0 + fhi >= p.T) fhi = p.T - 1 - q0;
-        lo = flo - j * kKV;
-        hi = fhi - j * kKV;
-        whi = kKV;                                             // frames straddle tiles: no warp-level skipping
-        full_tile = false;
-      }
-      uint8_t* ptile = smem + kOffP + pb * kPBytes;
-      const uint32_t tmem_S = tmem_base + pb * kKV + lane_base;
+      for (int j = 0; j < it.n_kv; ++j) {
+        const uint32_t gj = g + j;
+        const int pb = gj & 1;
+        // visible columns of this KV tile for this row: [lo, hi] (tile-relative)
+        int lo, hi, whi, wlo;   // whi / wlo: largest / smallest hi within the warp (warp-uniform)
+        bool full_tile;         // CTA-uniform: every row sees all 64 columns
+        if (p.mode == ATTN_CAUSAL) {
+          lo = 0;
+          hi = min(q0 + r + p.mask_delay, p.T - 1) - j * kKV;
+          whi = min(q0 + warp * 32 + 31 + p.mask_delay, p.T - 1) - j * kKV;
+          wlo = min(q0 + warp * 32 + p.mask_delay, p.T - 1) - j * kKV;
+          full_tile = (j * kKV + kKV - 1) <= min(q0 + p.mask_delay, p.T - 1);
+        } else {
+          const int flo = (r / p.S) * p.S;                       // first row of this row's frame (128-tile relative)
+          int fhi = (r < p.tile_rows) ? flo + p.S - 1 : -1;
+          if (q0 + fhi >= p.T) fhi = p.T - 1 - q0;
+          lo = flo - j * kKV;
+          hi = fhi - j * kKV;
+          whi = kKV;                                             // frames straddle tiles: no warp-level skipping
+          wlo = -1;
+          full_tile = false;
+        }
+        uint8_t* ptile = smem + kOffP + pb * kPBytes;
+        const uint32_t tmem_S = tmem_base + pb * kKV + lane_base;
 
-      mbar_wait(&s_full[pb], (j >> 1) & 1, 20);
-      tc_fence_after();
-      float m_new = m_run, alpha = 1.f, psum = 0.f;
-      if (j >= 2) {
-        mbar_wait(&pv_done[pb], ((j - 2) >> 1) & 1, 21);   // PV(j-2) has consumed this P buffer
-      }
-      // Per 32-column half of the tile, warp-uniformly: 0 = every row of the warp sees all 32 columns,
-      // 1 = mixed (per-element compare), 2 = no row sees any of them (skip the exponentials, P = 0).
-      int hmode[2];
-      if (full_tile) {
-        hmode[0] = hmode[1] = 0;
-      } else if (p.mode == ATTN_CAUSAL) {
-        const int wlo = min(q0 + warp * 32 + p.mask_delay, p.T - 1) - j * kKV;   // smallest hi within the warp
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) hmode[hh] = (hh * 32 + 31 <= wlo) ? 0 : ((hh * 32 > whi) ? 2 : 1);
-      } else {
-        hmode[0] = hmode[1] = 1;
-      }
-      if (hmode[0] != 2 || hmode[1] != 2) {
-        uint32_t sv[64];
-        {
-          uint32_t(&a0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
-          uint32_t(&a1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
-          tmem_ld32(tmem_S, a0);
-          tmem_ld32(tmem_S + 32, a1);
-          tmem_ld_wait();
-        }
-        float mx = -INFINITY;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          if (hmode[hh] == 1) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = hh * 32 + i;
-              sv[c] = (c >= lo && c <= hi) ? sv[c] : 0xff800000u;   // -inf
-            }
-          }
-          if (hmode[hh] != 2) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[hh * 32 + i]));
-          }
-        }
-        m_new = fmaxf(m_run, mx);
-        const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * sl;
-        alpha = (m_new == m_run) ? 1.f : ex2(m_run * sl - m_scaled);   // m_run = -inf -> 0
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          if (hmode[hh] == 2) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<uint4*>(ptile + sw128_offset(r, hh * 4 + q)) = make_uint4(0, 0, 0, 0);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t e[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int c = hh * 32 + q * 8 + 2 * t;
-                const float p0 = ex2(fmaf(__uint_as_float(sv[c]), sl, -m_scaled));
-                const float p1 = ex2(fmaf(__uint_as_float(sv[c + 1]), sl, -m_scaled));
-                psum += p0 + p1;
-                e[t] = pack_half2(p0, p1);
-              }
-              *reinterpret_cast<uint4*>(ptile + sw128_offset(r, hh * 4 + q)) = make_uint4(e[0], e[1], e[2], e[3]);
-            }
-          }
-        }
-      } else {
-        // no row of this warp sees any column of this tile (upper part of a diagonal tile): P = 0
-#pragma unroll
-        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(ptile + sw128_offset(r, q)) = make_uint4(0, 0, 0, 0);
-      }
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        // some row of this warp raised its running max: rescale the warp's 32 O rows in TMEM.  O must be quiescent:
-        // PV(j-1) (the last MMA issued so far that writes O) has to be complete.
-        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1, 22);
+        mbar_wait(&s_full[pb], (gj >> 1) & 1, 20);
         tc_fence_after();
+        float m_new = m_run, alpha = 1.f, psum = 0.f;
+        if (gj >= 2) mbar_wait(&pv_done[pb], ((gj - 2) >> 1) & 1, 21);   // PV(g-2) has consumed this P buffer
+        // Per 32-column half of the tile, warp-uniformly: 0 = every row of the warp sees all 32 columns,
+        // 1 = mixed (per-element compare), 2 = no row sees any of them (skip the exponentials, P = 0).
+        int hmode[2];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tmem_O + lane_base + c * 32, o);
-          tmem_ld_wait();
+        for (int hh = 0; hh < 2; ++hh)
+          hmode[hh] = full_tile ? 0 : ((hh * 32 + 31 <= wlo) ? 0 : ((hh * 32 > whi) ? 2 : 1));
+        if (hmode[0] != 2 || hmode[1] != 2) {
+          uint32_t sv[64];
+          {
+            uint32_t(&a0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
+            uint32_t(&a1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
+            tmem_ld32(tmem_S, a0);
+            tmem_ld32(tmem_S + 32, a1);
+            tmem_ld_wait();
+          }
+          float mx = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(tmem_O + lane_base + c * 32, o);
+          for (int hh = 0; hh < 2; ++hh) {
+            if (hmode[hh] == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int c = hh * 32 + i;
+                sv[c] = (c >= lo && c <= hi) ? sv[c] : 0xff800000u;   // -inf
+              }
+            }
+            if (hmode[hh] != 2) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[hh * 32 + i]));
+            }
+          }
+          m_new = fmaxf(m_run, mx);
+          const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * sl;
+          alpha = (m_new == m_run) ? 1.f : ex2(m_run * sl - m_scaled);   // m_run = -inf -> 0
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (hmode[hh] == 2) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(ptile + sw128_offset(r, hh * 4 + q)) = make_uint4(0, 0, 0, 0);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t e[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const int c = hh * 32 + q * 8 + 2 * t;
+                  const float p0 = ex2(fmaf(__uint_as_float(sv[c]), sl, -m_scaled));
+                  const float p1 = ex2(fmaf(__uint_as_float(sv[c + 1]), sl, -m_scaled));
+                  psum += p0 + p1;
+                  e[t] = pack_half2(p0, p1);
+                }
+                *reinterpret_cast<uint4*>(ptile + sw128_offset(r, hh * 4 + q)) = make_uint4(e[0], e[1], e[2], e[3]);
+              }
+            }
+          }
+        } else {
+          // no row of this warp sees any column of this tile (upper part of a diagonal tile): P = 0
+#pragma unroll
+          for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(ptile + sw128_offset(r, q)) = make_uint4(0, 0, 0, 0);
         }
-        tmem_st_wait();
-      }
-      l_run = l_run * alpha + psum;
-      m_run = m_new;
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+          // some row of this warp raised its running max: rescale the warp's 32 O rows in TMEM.  O must be quiescent:
+          // PV(j-1) (the last MMA issued so far that writes O) has to be complete.
+          mbar_wait(&pv_done[(gj - 1) & 1], ((gj - 1) >> 1) & 1, 22);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_base + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_base + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+        l_run = l_run * alpha + psum;
+        m_run = m_new;
 
-      fence_proxy_async_smem();   // P visible to the tensor-core (async) proxy
-      tc_fence_before();          // order our tcgen05.ld/st before the MMAs issued after the barrier
-      mbar_arrive(&p_ready[pb]);
-    }
-    // ---- epilogue: O / l -> fp16 -> staging (P buffer 0; every MMA has completed) -> TMA store
-    mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1, 23);
-    tc_fence_after();
-    uint8_t* stage = smem + kOffP;
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld32(tmem_O + lane_base + c * 32, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 u;
-        u.x = pack_half2(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
-        u.y = pack_half2(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
-        u.z = pack_half2(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
-        u.w = pack_half2(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
-        *reinterpret_cast<uint4*>(stage + sw128_offset(r, c * 4 + q)) = u;
+        fence_proxy_async_smem();   // P visible to the tensor-core (async) proxy
+        tc_fence_before();          // order our tcgen05.ld/st before the MMAs issued after the barrier
+        mbar_arrive(&p_ready[pb]);
       }
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(1, 128);
-    if (tid == 0) {
-      tma_store_4d(&tmO, stage, h * 64, s, q0, b);   // box rows = 128 (causal) or tile_rows (block-diagonal)
-      tma_store_commit();
-      tma_store_wait_read0();
+      g += it.n_kv;
+      // ---- item epilogue: O / l -> fp16 -> staging -> TMA store.  Every MMA of this item has completed once the
+      // last PV has, so both P buffers are free; the next item's first P goes to buffer g & 1, so stage in the other.
+      const uint32_t gl = g - 1;
+      mbar_wait(&pv_done[gl & 1], (gl >> 1) & 1, 23);
+      tc_fence_after();
+      uint8_t* stage = smem + kOffP + ((g & 1) ^ 1) * kPBytes;
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tmem_O + lane_base + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_half2(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+          u.y = pack_half2(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+          u.z = pack_half2(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+          u.w = pack_half2(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(stage + sw128_offset(r, c * 4 + q)) = u;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(o_free);          // O has been read out: the next item's first PV may overwrite it
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (tid == 0) {
+        tma_store_4d(&tmO, stage, it.h * 64, it.s, q0, it.b);   // box rows = 128 (causal) or tile_rows (block-diagonal)
+        tma_store_commit();
+        tma_store_wait_read0();     // the staging buffer may be rewritten (as P) two tiles from now
+      }
+      named_bar_sync(1, 128);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace
 
 void launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const CUtensorMap& tmO, const AttnParams& p,
                  cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int num_sms = 0;
+  if (!num_sms) {
     cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    attr_set = true;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  dim3 grid;
-  if (p.mode == ATTN_CAUSAL) grid = dim3((p.T + kTile - 1) / kTile, p.H, p.B * p.S);
-  else grid = dim3((p.T + p.tile_rows - 1) / p.tile_rows, p.H, 1);
-  attn_kernel<<<grid, 160, kSmemBytes, stream>>>(tmQ, tmKV, tmO, p);
+  int n_items;
+  if (p.mode == ATTN_CAUSAL) n_items = ((p.T + kTile - 1) / kTile) * p.H * p.B * p.S;
+  else n_items = ((p.T + p.tile_rows - 1) / p.tile_rows) * p.H;
+  const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
+  attn_kernel<<<grid, 192, kSmemBytes, stream>>>(tmQ, tmKV, tmO, p, n_items);
 }
 
 }  // namespace fseend
