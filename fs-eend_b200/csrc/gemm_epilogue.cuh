@@ -89,14 +89,36 @@ __device__ __forceinline__ void tmem_ld32_sync(uint32_t taddr, float (&v)[32]) {
 
 // `staging` holds the residual tile on entry when p.has_residual.  `sync()` synchronises the 128 epilogue threads;
 // `store_thread` issues the TMA stores.  trow = TMEM address of this thread's lane quarter, column 0 of the tile.
-template <class Sync>
+// kHalves = 2: two threads share a row (same TMEM lane quarter, different warps); thread `half` owns columns
+// [half*128, half*128+128) and the row statistics are merged through `xchg` ([2][128] float4 in shared memory).
+template <int kHalves, class Sync>
 __device__ __forceinline__ void row_tile_epilogue(const GemmParams& p, const EpiParams& sp, const CUtensorMap& tmO,
                                                   const CUtensorMap& tmO2, uint32_t trow, uint8_t* staging, int r,
-                                                  bool store_thread, int n0, int n_tile, int t0, int seq, Sync sync) {
+                                                  bool store_thread, int n0, int n_tile, int t0, int seq, Sync sync,
+                                                  int half = 0, float4* xchg = nullptr) {
   float acc[32], aux[32];
+  const int c0 = half * (8 / kHalves), c1 = c0 + 8 / kHalves;        // 32-column chunks owned by this thread
+  const int g0 = half * (4 / kHalves), g1 = g0 + 4 / kHalves;        // GLU output chunks
+  // merge this thread's (n, mean, m2 | sumsq) with its partner's
+  auto merge_stats = [&](RowStats& st, float& sumsq) {
+    if (kHalves == 2) {
+      xchg[half * 128 + r] = make_float4(st.n, st.mean, st.m2, sumsq);
+      sync();
+      const float4 o = xchg[(half ^ 1) * 128 + r];
+      sync();
+      const float nn = st.n + o.x;
+      if (nn > 0.f) {
+        const float delta = o.y - st.mean;
+        st.m2 += o.z + delta * delta * (st.n * o.x / nn);
+        st.mean += delta * (o.x / nn);
+        st.n = nn;
+      }
+      sumsq += o.w;
+    }
+  };
 
   if (p.mode == EPI_BIAS) {
-    for (int c = 0; c < 8; ++c) {
+    for (int c = c0; c < c1; ++c) {
       tmem_ld32_sync(trow + c * 32, acc);
       if (p.bias) {
         smem_vec32(sp.bias + c * 32, aux);
@@ -114,7 +136,7 @@ __device__ __forceinline__ void row_tile_epilogue(const GemmParams& p, const Epi
     }
   } else if (p.mode == EPI_GLU) {
     // columns [0,128) = value, [128,256) = gate of the same 128 output channels
-    for (int c = 0; c < 4; ++c) {
+    for (int c = g0; c < g1; ++c) {
       float gate[32];
       tmem_ld32_sync(trow + c * 32, acc);
       tmem_ld32_sync(trow + 128 + c * 32, gate);
@@ -137,7 +159,7 @@ __device__ __forceinline__ void row_tile_epilogue(const GemmParams& p, const Epi
     // pass 1: row statistics (Chan's parallel merge of 32-column chunks: robust to large means)
     RowStats st{0.f, 0.f, 0.f};
     float sumsq = 0.f;
-    for (int c = 0; need_stats && c < 8; ++c) {
+    for (int c = c0; need_stats && c < c1; ++c) {
       tmem_ld32_sync(trow + c * 32, acc);
       if (p.bias) {
         smem_vec32(sp.bias + c * 32, aux);
@@ -172,6 +194,7 @@ __device__ __forceinline__ void row_tile_epilogue(const GemmParams& p, const Epi
         st.n = nn;
       }
     }
+    if (need_stats) merge_stats(st, sumsq);
     float mean = 0.f, scale = 1.f;
     if (p.mode == EPI_L2) {
       scale = sumsq > 0.f ? rsqrtf(sumsq) : 0.f;
@@ -181,7 +204,7 @@ __device__ __forceinline__ void row_tile_epilogue(const GemmParams& p, const Epi
     }
     const bool zero_row = p.seq_len != nullptr && (t0 + r) >= p.seq_len[seq];
     // pass 2: normalise, affine, pack
-    for (int c = 0; c < 8; ++c) {
+    for (int c = c0; c < c1; ++c) {
       tmem_ld32_sync(trow + c * 32, acc);
       if (p.bias) {
         smem_vec32(sp.bias + c * 32, aux);
@@ -235,7 +258,7 @@ __device__ __forceinline__ void row_tile_epilogue(const GemmParams& p, const Epi
       // second output: LayerNorm of the (fp16) row just stored, with the next pre-norm sub-layer's affine
       sync();   // the TMA store above has finished reading the staging tile
       RowStats s2{0.f, 0.f, 0.f};
-      for (int c = 0; c < 8; ++c) {
+      for (int c = c0; c < c1; ++c) {
         staging_read32(staging, r, c, acc);
         float s = 0.f;
 #pragma unroll
@@ -253,8 +276,12 @@ __device__ __forceinline__ void row_tile_epilogue(const GemmParams& p, const Epi
         s2.mean += delta * (32.f / nn);
         s2.n = nn;
       }
+      {
+        float dummy = 0.f;
+        merge_stats(s2, dummy);
+      }
       const float rstd2 = rsqrtf(s2.m2 * (1.f / 256.f) + p.ln_eps);
-      for (int c = 0; c < 8; ++c) {
+      for (int c = c0; c < c1; ++c) {
         staging_read32(staging, r, c, acc);
         smem_vec32(sp.g2 + c * 32, aux);
 #pragma unroll
@@ -277,7 +304,7 @@ __device__ __forceinline__ void row_tile_epilogue(const GemmParams& p, const Epi
     // attractor init: S output rows per input row, out[row, s, :] = acc + pe_proj[s, :]
     const int row0 = seq * p.rows_per_seq + t0;
     for (int s = 0; s < p.S; ++s) {
-      for (int c = 0; c < 8; ++c) {
+      for (int c = c0; c < c1; ++c) {
         tmem_ld32_sync(trow + c * 32, acc);
         load_vec32(p.pe_proj + s * 256 + c * 32, aux);
 #pragma unroll
