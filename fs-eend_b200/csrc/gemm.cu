@@ -1,10 +1,12 @@
 // tcgen05 row-tile GEMM with fused epilogues (see gemm.cuh).
 //
-// One CTA (128 threads) computes one 128 x 256 output tile:
+// One CTA (256 threads) computes one 128 x 256 output tile:
 //   thread 0   : TMA producer  (A tile 128x64 + W tile 256x64 per k-block, 2-stage mbarrier ring)
 //   thread 32  : MMA issuer    (tcgen05.mma kind::f16, M=128 N=256 K=16, accumulator = 256 TMEM columns)
-//   all 4 warps: epilogue      (tcgen05.ld: thread r owns output row r -> row-local LN / L2 / bias / ReLU,
-//                               fp16 pack into a 128B-swizzled staging tile, TMA store)
+//   all 8 warps: epilogue      (tcgen05.ld: two threads per output row, 128 columns each; row-local LN / L2 /
+//                               bias / activation with the row statistics merged through smem; fp16 pack into a
+//                               128B-swizzled staging tile, TMA store).  The row epilogues are instruction/latency
+//                               bound, so they get all the warps the register file allows at 2 CTAs/SM.
 // Two CTAs are resident per SM (2 x ~97 KB smem, 2 x 256 TMEM columns): one CTA's epilogue overlaps the
 // other's main loop.
 #include <stdlib.h>
@@ -26,7 +28,7 @@ using gemm_detail::kSubTileBytes;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
 constexpr uint32_t kTmemCols = 256;
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
             const __grid_constant__ CUtensorMap tmO2, const GemmParams p) {
@@ -37,6 +39,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __shared__ __align__(8) uint64_t res_bar;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) gemm_detail::EpiParams epi_params;
+  __shared__ __align__(16) float4 xchg[2 * 128];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem;  // aliases the pipeline stages; only touched after every MMA has completed
@@ -65,7 +68,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmO);
   }
   if (warp == 2) tmem_alloc(&tmem_base_slot, kTmemCols);
-  gemm_detail::load_epi_params(epi_params, p, n0, tid, 128);
+  gemm_detail::load_epi_params(epi_params, p, n0, tid, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -127,8 +130,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     mbar_wait(&res_bar, 0, 4);
   }
 
-  gemm_detail::row_tile_epilogue<1>(p, epi_params, tmO, tmO2, tmem_base + (static_cast<uint32_t>(warp * 32) << 16), staging, tid,
-                                 tid == 0, n0, n_tile, t0, seq, [] { __syncthreads(); });
+  {
+    const int quarter = warp & 3, half = warp >> 2;       // TMEM lane quarter; column half owned by this thread
+    gemm_detail::row_tile_epilogue<2>(p, epi_params, tmO, tmO2, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16),
+                                      staging, quarter * 32 + lane, tid == 0, n0, n_tile, t0, seq,
+                                      [] { __syncthreads(); }, half, xchg);
+  }
 
   tc_fence_before();
   __syncthreads();
@@ -171,7 +178,7 @@ void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
     attr_set = true;
   }
   const int grid = p.n_seq * p.tiles_per_seq * p.n_tiles;
-  gemm_kernel<<<grid, 128, kSmemBytes, stream>>>(tmA, tmB, tmR, tmO, tmO, p);
+  gemm_kernel<<<grid, 256, kSmemBytes, stream>>>(tmA, tmB, tmR, tmO, tmO, p);
 }
 
 void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
@@ -186,7 +193,7 @@ void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     attr_set = true;
   }
   const int grid = p.n_seq * p.tiles_per_seq * p.n_tiles;
-  gemm_kernel<<<grid, 128, kSmemBytes, stream>>>(tmA, tmB, tmR, tmO, tmO2, p);
+  gemm_kernel<<<grid, 256, kSmemBytes, stream>>>(tmA, tmB, tmR, tmO, tmO2, p);
 }
 
 }  // namespace fseend
