@@ -106,7 +106,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int lane = tid & 31;
   if (tid == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("[fseend] attn: dynamic smem base not 1024-aligned\n");
     __trap();
@@ -137,8 +136,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_base_slot;
   const uint32_t tmem_O = tmem_base + 128;
 
+  // Role warps stay converged and elect one lane only around the TMA / tcgen05 instructions (operands then live in
+  // uniform registers; a single diverged lane makes ptxas wrap each UTCHMMA in an ELECT loop with R2UR moves).
   if (warp == 4) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------------------ TMA producer (runs ahead across items)
       uint32_t g = 0;   // KV tiles issued so far (ring position)
       uint32_t n = 0;   // items issued so far
@@ -146,23 +147,29 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const Item it = decode_item(p, id);
         const int qb = n & 1;
         mbar_wait(&q_empty[qb], ((n >> 1) & 1) ^ 1, 10);
-        mbar_arrive_expect_tx(&q_full[qb], kQBytes);
-        tma_load_4d(smem + kOffQ + qb * kQBytes, &tmQ, &q_full[qb], it.h * 64, it.s, it.q0, it.b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[qb], kQBytes);
+          tma_load_4d(smem + kOffQ + qb * kQBytes, &tmQ, &q_full[qb], it.h * 64, it.s, it.q0, it.b);
+        }
+        __syncwarp();
         for (int j = 0; j < it.n_kv; ++j, ++g) {
           const int st = g % kStages;
           mbar_wait(&kv_empty[st], ((g / kStages) & 1) ^ 1, 11);
           uint8_t* dst = smem + kOffKV + st * kStageBytes;
           const int row = it.kv_first + j * kKV;
-          mbar_arrive_expect_tx(&kv_full[st], kStageBytes);
-          tma_load_4d(dst, &tmKV, &kv_full[st], 256 + it.h * 64, it.s, row, it.b);
-          tma_load_4d(dst + kKBytes, &tmKV, &kv_full[st], 512 + it.h * 64, it.s, row, it.b);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&kv_full[st], kStageBytes);
+            tma_load_4d(dst, &tmKV, &kv_full[st], 256 + it.h * 64, it.s, row, it.b);
+            tma_load_4d(dst + kKBytes, &tmKV, &kv_full[st], 512 + it.h * 64, it.s, row, it.b);
+          }
+          __syncwarp();
         }
       }
     }
     __syncwarp();
   } else if (warp == 5) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
+    {
+      // ------------------------------------------------------------ MMA issuer (warp-converged)
       constexpr uint32_t idesc_qk = make_idesc_f16(128, kKV, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, true);
       uint32_t g = 0, n = 0;
@@ -170,20 +177,23 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const Item it = decode_item(p, id);
         const int qb = n & 1;
         const uint64_t qdesc = smem_desc_sw128(smem_u32(smem + kOffQ + qb * kQBytes));
-        auto issue_qk = [&](uint32_t gj) {
+        auto issue_qk = [&](uint32_t gj, bool last_qk) {
           const int st = gj % kStages;
           mbar_wait(&kv_full[st], (gj / kStages) & 1, 12);
           tc_fence_after();
           const uint64_t kdesc = smem_desc_sw128(smem_u32(smem + kOffKV + st * kStageBytes));
           const uint32_t tmem_S = tmem_base + (gj & 1) * kKV;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_S, qdesc + 2 * kk, kdesc + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
-          umma_commit(&s_full[gj & 1]);
+            for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_S, qdesc + 2 * kk, kdesc + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
+            umma_commit(&s_full[gj & 1]);
+            if (last_qk) umma_commit(&q_empty[qb]);   // every QK^T of this item has been issued
+          }
+          __syncwarp();
         };
         mbar_wait(&q_full[qb], (n >> 1) & 1, 13);
-        issue_qk(g);
-        if (it.n_kv > 1) issue_qk(g + 1);
-        if (it.n_kv <= 2) umma_commit(&q_empty[qb]);   // every QK^T of this item has been issued
+        issue_qk(g, it.n_kv == 1);
+        if (it.n_kv > 1) issue_qk(g + 1, it.n_kv == 2);
         for (int j = 0; j < it.n_kv; ++j) {
           const uint32_t gj = g + j;
           const int st = gj % kStages, pb = gj & 1;
@@ -194,16 +204,16 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           const int n_k16 = (valid_cols + 15) >> 4;
           const uint64_t pdesc = smem_desc_sw128(smem_u32(smem + kOffP + pb * kPBytes));
           const uint64_t vdesc = smem_desc_sw128(smem_u32(smem + kOffKV + st * kStageBytes + kKBytes));
-          for (int kk = 0; kk < n_k16; ++kk) {
-            // V is MN-major: 16 kv rows = 16 * 128 B = 2048 B per K step -> +128 in 16-byte units
-            umma_f16(tmem_O, pdesc + 2 * kk, vdesc + 128 * kk, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          if (elect_one()) {
+            for (int kk = 0; kk < n_k16; ++kk) {
+              // V is MN-major: 16 kv rows = 16 * 128 B = 2048 B per K step -> +128 in 16-byte units
+              umma_f16(tmem_O, pdesc + 2 * kk, vdesc + 128 * kk, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&pv_done[pb]);
+            umma_commit(&kv_empty[st]);
           }
-          umma_commit(&pv_done[pb]);
-          umma_commit(&kv_empty[st]);
-          if (j + 2 < it.n_kv) {
-            issue_qk(gj + 2);                          // S(j) has been consumed: its TMEM buffer is free
-            if (j + 3 == it.n_kv) umma_commit(&q_empty[qb]);
-          }
+          __syncwarp();
+          if (j + 2 < it.n_kv) issue_qk(gj + 2, j + 3 == it.n_kv);   // S(j) has been consumed: its TMEM buffer is free
         }
         g += it.n_kv;
       }

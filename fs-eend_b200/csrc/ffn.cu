@@ -185,22 +185,32 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   // every "group" is 4 slots; group g: g == 0 -> W1(0); g odd -> W1((g+1)/2) if it exists; g even -> W2(g/2 - 1)
   // Enumerated explicitly below to keep both roles in lock-step.
 
+  // Role warps run their loops with all 32 lanes converged and elect one lane only around the TMA / tcgen05
+  // instructions: descriptors, addresses and loop state then live in uniform registers.  (Issuing from a single
+  // diverged lane made ptxas wrap every UTCHMMA in an ELECT loop with R2UR moves — ~13 dependent instructions per MMA,
+  // which left the tensor pipe ~45 % busy.)
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------------------------ TMA producer
-      mbar_arrive_expect_tx(&x_full, kXBytes);
-      for (int ks = 0; ks < 4; ++ks) tma_load_3d(smem + kOffX + ks * kSlotBytes, &tmX, &x_full, ks * 64, t0, seq);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&x_full, kXBytes);
+        for (int ks = 0; ks < 4; ++ks) tma_load_3d(smem + kOffX + ks * kSlotBytes, &tmX, &x_full, ks * 64, t0, seq);
+      }
+      __syncwarp();
       uint32_t use = 0;   // global slot-use counter
       auto load_slot = [&](const CUtensorMap* tm, int c0, int c1) {
         const int s = use % kSlots;
         const uint32_t ph = (use / kSlots) & 1;
         mbar_wait(&w_empty[s], ph ^ 1, 31);
-        mbar_arrive_expect_tx(&w_full[s], kSlotBytes);
-        if (kCluster == 1) {
-          tma_load_2d(smem + kOffW + s * kSlotBytes, tm, &w_full[s], c0, c1);
-        } else if ((use & 1u) == rank) {
-          tma_load_2d_mc(smem + kOffW + s * kSlotBytes, tm, &w_full[s], c0, c1, kMask);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&w_full[s], kSlotBytes);
+          if (kCluster == 1) {
+            tma_load_2d(smem + kOffW + s * kSlotBytes, tm, &w_full[s], c0, c1);
+          } else if ((use & 1u) == rank) {
+            tma_load_2d_mc(smem + kOffW + s * kSlotBytes, tm, &w_full[s], c0, c1, kMask);
+          }
         }
+        __syncwarp();
         ++use;
       };
       auto load_w1 = [&](int j) {   // W1 rows [j*128, +128), k-sub-tile ks -> box (64 k, 128 rows)
@@ -218,12 +228,12 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
+    {
+      // ------------------------------------------------------------------ MMA issuer (warp-converged, see above)
       constexpr uint32_t idesc_g1 = make_idesc_f16(128, 128, false);
       constexpr uint32_t idesc_g2 = make_idesc_f16(128, 256, false);
       uint32_t use = 0;
-      auto release_slot = [&](int s) {
+      auto release_slot = [&](int s) {   // called by the elected lane
         if (kCluster == 1) umma_commit(&w_empty[s]);
         else umma_commit_mc(&w_empty[s], kMask);
       };
@@ -240,13 +250,16 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           tc_fence_after();
           const uint64_t adesc = smem_desc_sw128(smem_u32(smem + kOffX + ks * kSlotBytes));
           const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + kOffW + s * kSlotBytes));
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_f16(tmem_H, adesc + 2 * kk, bdesc + 2 * kk, idesc_g1, (ks > 0 || kk > 0) ? 1u : 0u);
-          release_slot(s);
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(tmem_H, adesc + 2 * kk, bdesc + 2 * kk, idesc_g1, (ks > 0 || kk > 0) ? 1u : 0u);
+            release_slot(s);
+            if (ks == 3) umma_commit(&h_full[hb]);
+          }
+          __syncwarp();
           ++use;
         }
-        umma_commit(&h_full[hb]);
       };
       auto gemm2 = [&](int j) {
         const int pb = j & 1;
@@ -258,22 +271,25 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           mbar_wait(&w_full[s0 + 1], ((use + 1) / kSlots) & 1, 36);
           tc_fence_after();
           const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + kOffW + s0 * kSlotBytes));
-          if (kTS) {
-            const uint32_t tmem_P = tmem_base + 256 + pb * 128 + ks2 * 32;   // 64 hidden = 32 packed columns
+          if (elect_one()) {
+            if (kTS) {
+              const uint32_t tmem_P = tmem_base + 256 + pb * 128 + ks2 * 32;   // 64 hidden = 32 packed columns
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16_ts(tmem_Y, tmem_P + 8 * kk, bdesc + 2 * kk, idesc_g2, (j > 0 || ks2 > 0 || kk > 0) ? 1u : 0u);
-          } else {
-            const uint64_t adesc = smem_desc_sw128(smem_u32(smem + kOffP + pb * kPBytes + ks2 * kSlotBytes));
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16_ts(tmem_Y, tmem_P + 8 * kk, bdesc + 2 * kk, idesc_g2, (j > 0 || ks2 > 0 || kk > 0) ? 1u : 0u);
+            } else {
+              const uint64_t adesc = smem_desc_sw128(smem_u32(smem + kOffP + pb * kPBytes + ks2 * kSlotBytes));
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16(tmem_Y, adesc + 2 * kk, bdesc + 2 * kk, idesc_g2, (j > 0 || ks2 > 0 || kk > 0) ? 1u : 0u);
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16(tmem_Y, adesc + 2 * kk, bdesc + 2 * kk, idesc_g2, (j > 0 || ks2 > 0 || kk > 0) ? 1u : 0u);
+            }
+            release_slot(s0);
+            release_slot(s0 + 1);
+            if (ks2 == 1) umma_commit(&p_empty[pb]);
           }
-          release_slot(s0);
-          release_slot(s0 + 1);
+          __syncwarp();
           use += 2;
         }
-        umma_commit(&p_empty[pb]);
       };
       mbar_wait(&x_full, 0, 30);
       tc_fence_after();
@@ -282,7 +298,8 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         if (j + 1 < n_chunks) gemm1(j + 1);
         gemm2(j);
       }
-      umma_commit(&y_full);
+      if (elect_one()) umma_commit(&y_full);
+      __syncwarp();
     }
     __syncwarp();
   } else {

@@ -76,8 +76,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int total_it = p.taps * p.k_blocks;
 
+  // Role warps stay converged; one elected lane issues the TMA / tcgen05 instructions (uniform-register operands).
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ---------------- TMA producer
       for (int it = 0; it < total_it; ++it) {
         const int s = it % kStages;
@@ -87,14 +88,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb = it - tap * p.k_blocks;
         uint8_t* sa = smem + s * kStageBytes;
         uint8_t* sb = sa + kABytes;
-        mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-        tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, t0 + tap + p.tap_shift + p.a_row_offset, seq);
-        tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, tap * (p.n_tiles * BN) + n0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+          tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, t0 + tap + p.tap_shift + p.a_row_offset, seq);
+          tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, tap * (p.n_tiles * BN) + n0);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ---------------- MMA issuer
       constexpr uint32_t idesc = make_idesc_f16(BM, BN, false);
       for (int it = 0; it < total_it; ++it) {
@@ -105,14 +109,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t sa = smem_u32(smem + s * kStageBytes);
         const uint64_t adesc = smem_desc_sw128(sa);
         const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          // advance 16 fp16 (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
-          umma_f16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // advance 16 fp16 (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
+            umma_f16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above have read it
+          if (it == total_it - 1) umma_commit(&tmem_full_bar);   // accumulator complete
         }
-        umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above have read it
+        __syncwarp();
       }
-      umma_commit(&tmem_full_bar);   // accumulator complete
     }
     __syncwarp();
   }

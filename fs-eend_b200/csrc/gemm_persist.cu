@@ -69,8 +69,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // Role warps stay converged and elect one lane only around the TMA / tcgen05 instructions, so descriptors and loop
+  // state live in uniform registers (a single diverged lane makes ptxas wrap each UTCHMMA in an ELECT loop + R2UR moves).
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------------------------ TMA producer
       uint32_t u = 0, n = 0;
       for (int id = blockIdx.x; id < n_items; id += gridDim.x, ++n) {
@@ -84,22 +86,28 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int tap = it / p.k_blocks;
           const int kb = it - tap * p.k_blocks;
           uint8_t* sa = smem + s * kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-          tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, t0 + tap + p.tap_shift + p.a_row_offset, seq);
-          tma_load_2d(sa + kABytes, &tmB, &full_bar[s], kb * BK, tap * (p.n_tiles * BN) + n0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+            tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, t0 + tap + p.tap_shift + p.a_row_offset, seq);
+            tma_load_2d(sa + kABytes, &tmB, &full_bar[s], kb * BK, tap * (p.n_tiles * BN) + n0);
+          }
+          __syncwarp();
         }
         if (p.has_residual) {
           mbar_wait(&stg_free, (n & 1) ^ 1, 72);   // the previous item's stores have drained the staging tile
-          mbar_arrive_expect_tx(&res_full, 4 * gemm_detail::kSubTileBytes);
-          for (int sub = 0; sub < 4; ++sub)
-            tma_load_3d(staging + sub * gemm_detail::kSubTileBytes, &tmR, &res_full, n0 + sub * 64, t0, seq);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&res_full, 4 * gemm_detail::kSubTileBytes);
+            for (int sub = 0; sub < 4; ++sub)
+              tma_load_3d(staging + sub * gemm_detail::kSubTileBytes, &tmR, &res_full, n0 + sub * 64, t0, seq);
+          }
+          __syncwarp();
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
+    {
+      // ------------------------------------------------------------------ MMA issuer (warp-converged)
       constexpr uint32_t idesc = make_idesc_f16(BM, BN, false);
       uint32_t u = 0, n = 0;
       for (int id = blockIdx.x; id < n_items; id += gridDim.x, ++n) {
@@ -114,12 +122,15 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t sa = smem_u32(smem + s * kStageBytes);
           const uint64_t adesc = smem_desc_sw128(sa);
           const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk)
-            umma_f16(tmem_D, adesc + 2 * kk, bdesc + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+            for (int kk = 0; kk < BK / 16; ++kk)
+              umma_f16(tmem_D, adesc + 2 * kk, bdesc + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[s]);
+            if (it == total_it - 1) umma_commit(&tmem_full[acc]);
+          }
+          __syncwarp();
         }
-        umma_commit(&tmem_full[acc]);
       }
     }
     __syncwarp();

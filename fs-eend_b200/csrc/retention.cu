@@ -48,7 +48,6 @@ retention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int lane = tid & 31;
   if (tid == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("[fseend] retention: dynamic smem base not 1024-aligned\n");
     __trap();
@@ -86,14 +85,18 @@ retention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_base_slot;
   const uint32_t tmem_S = tmem_base, tmem_O1 = tmem_base + 128, tmem_O2 = tmem_base + 192;
 
+  // The control warp stays converged and elects one lane around the TMA / tcgen05 instructions (uniform-register operands).
   if (warp == 4) {
-    if (lane == 0) {
+    {
       auto load_kv = [&](int j) {
         const int st = j & 1;
-        mbar_arrive_expect_tx(&k_full[st], kKVBytes);
-        tma_load_5d(smem + kOffK + st * kKVBytes, &tmQ, &k_full[st], 256 + h * 64, s, j * kTile, c, b);
-        mbar_arrive_expect_tx(&v_full[st], kKVBytes);
-        tma_load_5d(smem + kOffV + st * kKVBytes, &tmQ, &v_full[st], 512 + h * 64, s, j * kTile, c, b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[st], kKVBytes);
+          tma_load_5d(smem + kOffK + st * kKVBytes, &tmQ, &k_full[st], 256 + h * 64, s, j * kTile, c, b);
+          mbar_arrive_expect_tx(&v_full[st], kKVBytes);
+          tma_load_5d(smem + kOffV + st * kKVBytes, &tmQ, &v_full[st], 512 + h * 64, s, j * kTile, c, b);
+        }
+        __syncwarp();
       };
       constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, true);
@@ -103,14 +106,20 @@ retention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(&k_full[st], (j >> 1) & 1, 51);
         tc_fence_after();
         const uint64_t kdesc = smem_desc_sw128(smem_u32(smem + kOffK + st * kKVBytes));
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_S, qdesc + 2 * kk, kdesc + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
-        umma_commit(s_full);
+          for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_S, qdesc + 2 * kk, kdesc + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
       };
 
-      mbar_arrive_expect_tx(q_full, kQBytes + (has_cross ? 64 * 64 * 2 : 0));
-      tma_load_5d(smem + kOffQ, &tmQ, q_full, h * 64, s, q0, c, b);
-      if (has_cross) tma_load_3d(smem + kOffP, &tmR, q_full, 0, 0, (n * p.H + h) * p.n_chunks + c);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, kQBytes + (has_cross ? 64 * 64 * 2 : 0));
+        tma_load_5d(smem + kOffQ, &tmQ, q_full, h * 64, s, q0, c, b);
+        if (has_cross) tma_load_3d(smem + kOffP, &tmR, q_full, 0, 0, (n * p.H + h) * p.n_chunks + c);
+      }
+      __syncwarp();
       load_kv(0);
       if (n_kv > 1) load_kv(1);
       mbar_wait(q_full, 0, 50);
@@ -118,8 +127,11 @@ retention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (has_cross) {
         // O2 = Q R'  (R' is [64 e][64 d] row-major = MN-major B operand, K = e)
         const uint64_t rdesc = smem_desc_sw128(smem_u32(smem + kOffP));
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_O2, qdesc + 2 * kk, rdesc + 128 * kk, idesc_pv, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_O2, qdesc + 2 * kk, rdesc + 128 * kk, idesc_pv, kk > 0 ? 1u : 0u);
+        }
+        __syncwarp();
       }
       issue_qk(0);   // its commit (s_full) also covers the cross MMA: R' may be overwritten by P afterwards
 
@@ -128,8 +140,11 @@ retention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(p_ready, j & 1, 52);
         if (j == n_kv - 1) {
           // every MMA reading Q has completed (the rows just consumed S(j)): reuse its buffer for the gate tile
-          mbar_arrive_expect_tx(g_full, kQBytes);
-          tma_load_5d(smem + kOffQ, &tmQ, g_full, 768 + h * 64, s, q0, c, b);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(g_full, kQBytes);
+            tma_load_5d(smem + kOffQ, &tmQ, g_full, 768 + h * 64, s, q0, c, b);
+          }
+          __syncwarp();
         }
         mbar_wait(&v_full[st], (j >> 1) & 1, 53);
         tc_fence_after();
@@ -137,12 +152,15 @@ retention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int n_k16 = (min(valid_cols, kTile) + 15) >> 4;
         const uint32_t p_addr = smem_u32(smem + kOffP);
         const uint64_t vdesc = smem_desc_sw128(smem_u32(smem + kOffV + st * kKVBytes));
-        for (int kk = 0; kk < n_k16; ++kk) {
-          const uint64_t pdesc = smem_desc_sw128(p_addr + (kk >> 2) * (kTile * 128)) + 2 * (kk & 3);
-          umma_f16(tmem_O1, pdesc, vdesc + 128 * kk, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        if (elect_one()) {
+          for (int kk = 0; kk < n_k16; ++kk) {
+            const uint64_t pdesc = smem_desc_sw128(p_addr + (kk >> 2) * (kTile * 128)) + 2 * (kk & 3);
+            umma_f16(tmem_O1, pdesc, vdesc + 128 * kk, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(pv_full);
+          umma_commit(&kv_empty[st]);
         }
-        umma_commit(pv_full);
-        umma_commit(&kv_empty[st]);
+        __syncwarp();
         if (j + 1 < n_kv) issue_qk(j + 1);
         if (j + 2 < n_kv) {
           mbar_wait(&kv_empty[st], (j >> 1) & 1, 54);
