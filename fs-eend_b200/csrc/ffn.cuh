@@ -24,4 +24,8 @@ struct FfnParams {
 void launch_ffn(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmO,
                 const FfnParams& p, int variant, cudaStream_t stream);
 
+// CTA-pair variant (tcgen05 cta_group::2, see ffn_pair.cu): same tmX / tmO / tmW2; tmW1 with box (64, 64).
+void launch_ffn_pair(const CUtensorMap& tmX, const CUtensorMap& tmW1_box64, const CUtensorMap& tmW2,
+                     const CUtensorMap& tmO, const FfnParams& p, cudaStream_t stream);
+
 }  // namespace fseend

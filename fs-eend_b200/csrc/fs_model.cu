@@ -63,6 +63,7 @@ struct WMat {
   int rows = 0, K = 0;
   CUtensorMap tm;     // box (64 k, 256 rows): B operand of the 128x256 GEMM tile
   CUtensorMap tm128;  // box (64 k, 128 rows): 16 KB weight slots of the fused FFN
+  CUtensorMap tm64;   // box (64 k, 64 rows): half-tile of the CTA-pair FFN (each CTA holds half of W1's chunk rows)
   void upload(const std::vector<__half>& h, int rows_, int K_) {
     rows = rows_;
     K = K_;
@@ -74,6 +75,8 @@ struct WMat {
     tm = make_tmap_f16(buf.p, 2, dims, str, box);
     uint32_t box128[2] = {64, 128};
     tm128 = make_tmap_f16(buf.p, 2, dims, str, box128);
+    uint32_t box64[2] = {64, 64};
+    tm64 = make_tmap_f16(buf.p, 2, dims, str, box64);
   }
 };
 
@@ -129,8 +132,8 @@ struct fseend_fs_model {
   CUtensorMap tm_aX, tm_aY, tm_aZ, tm_qkv_d_out, tm_qkv_d_attn, tm_ao_d_attn, tm_qkv_d_spk, tm_ao_d_spk, tm_ao_d, tm_qkv_e_kv, tm_qkv_d_kv, tm_qkv_d_spk_kv, tm_f_d_out, tm_f_d_in;
 
   int spk_mode = 1;  // 0: CUDA-core speaker attention, 1: tcgen05 block-diagonal attention
-  int ffn_mode = 3;  // 0: two GEMM launches (hidden layer through HBM); fused: 1 = SS, 2 = SS + 2-CTA weight multicast,
-                     // 3 = TS (hidden chunk stays in TMEM), 4 = TS + multicast
+  int ffn_mode = 5;  // 0: two GEMM launches (hidden layer through HBM); fused: 1 = SS, 2 = SS + 2-CTA weight multicast,
+                     // 3 = TS (hidden chunk stays in TMEM), 4 = TS + multicast, 5 = TS on a CTA pair (cta_group::2)
   bool profiling = false;
   std::vector<ProfEntry> prof_pending;
   std::map<std::string, std::pair<double, int>> prof_acc;
@@ -489,7 +492,10 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
                                 E.be2, c.ln_eps, last ? static_cast<const int*>(m->len_dev.p) : nullptr);
       const CUtensorMap& tx = last ? m->tm_hB_seq : m->tm_hB;
       const CUtensorMap& to = last ? m->tm_hconv_in : m->tm_hA;
-      L.run("enc.ffn_fused", [&] { launch_ffn(tx, E.w1.tm128, E.w2.tm128, to, fp, m->ffn_mode, st); });
+      L.run("enc.ffn_fused", [&] {
+        if (m->ffn_mode == 5) launch_ffn_pair(tx, E.w1.tm64, E.w2.tm128, to, fp, st);
+        else launch_ffn(tx, E.w1.tm128, E.w2.tm128, to, fp, m->ffn_mode, st);
+      });
     } else {
       {
         GemmParams p = flat_params(Me, c.enc_dim_feedforward, D, EPI_BIAS);
@@ -589,7 +595,10 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     if (m->ffn_mode > 0) {
       FfnParams fp = ffn_params(static_cast<int>(Md), 1, c.dec_dim_feedforward, Dl.b1, Dl.b2, Dl.g22, Dl.be22, c.ln_eps,
                                 nullptr);
-      L.run("dec.ffn_fused", [&] { launch_ffn(m->tm_aZ, Dl.w1.tm128, Dl.w2.tm128, m->tm_aX, fp, m->ffn_mode, st); });
+      L.run("dec.ffn_fused", [&] {
+        if (m->ffn_mode == 5) launch_ffn_pair(m->tm_aZ, Dl.w1.tm64, Dl.w2.tm128, m->tm_aX, fp, st);
+        else launch_ffn(m->tm_aZ, Dl.w1.tm128, Dl.w2.tm128, m->tm_aX, fp, m->ffn_mode, st);
+      });
     } else {
       {
         GemmParams p = flat_params(Md, c.dec_dim_feedforward, D, EPI_BIAS);
@@ -1062,7 +1071,7 @@ int fseend_op_gemm(const void* a_f16, int rows_per_seq, int n_seq, int K, const 
 
 int fseend_fs_set_option(fseend_fs_model* m, const char* key, int value) {
   if (!m || !key) return FSEEND_ERR_INVALID;
-  if (strcmp(key, "ffn") == 0 && value >= 0 && value <= 4) {
+  if (strcmp(key, "ffn") == 0 && value >= 0 && value <= 5) {
     m->ffn_mode = value;
     return FSEEND_OK;
   }
@@ -1079,7 +1088,7 @@ int fseend_op_ffn(const void* x_f16, int rows_per_seq, int n_seq, const void* w1
                   const int* seq_len_dev, int cluster, void* out_f16, void* stream) {
   return guarded([&] {
     if (F % 128 || F < 128) throw std::invalid_argument("F must be a multiple of 128");
-    if (cluster < 1 || cluster > 4) throw std::invalid_argument("variant must be 1..4");
+    if (cluster < 1 || cluster > 5) throw std::invalid_argument("variant must be 1..5");
     if (!fseend_device_ok()) throw std::invalid_argument("sm_100 device required");
     FfnParams p{};
     p.rows_per_seq = rows_per_seq;
@@ -1097,9 +1106,11 @@ int fseend_op_ffn(const void* x_f16, int rows_per_seq, int n_seq, const void* w1
     uint32_t box[2] = {64, 128};
     uint64_t d1[2] = {256, static_cast<uint64_t>(F)}, s1[1] = {256};
     uint64_t d2[2] = {static_cast<uint64_t>(F), 256}, s2[1] = {static_cast<uint64_t>(F)};
-    CUtensorMap tmW1 = make_tmap_f16(w1_f16, 2, d1, s1, box);
+    uint32_t box64[2] = {64, 64};
+    CUtensorMap tmW1 = make_tmap_f16(w1_f16, 2, d1, s1, cluster == 5 ? box64 : box);
     CUtensorMap tmW2 = make_tmap_f16(w2_f16, 2, d2, s2, box);
-    launch_ffn(tmX, tmW1, tmW2, tmO, p, cluster, static_cast<cudaStream_t>(stream));
+    if (cluster == 5) launch_ffn_pair(tmX, tmW1, tmW2, tmO, p, static_cast<cudaStream_t>(stream));
+    else launch_ffn(tmX, tmW1, tmW2, tmO, p, cluster, static_cast<cudaStream_t>(stream));
     CUDA_CHECK(cudaGetLastError());
   });
 }

@@ -78,7 +78,8 @@ int fseend_fs_forward_host(fseend_fs_model* m, const float* x_packed_host, const
 
 /* Tuning switches.  "ffn": 0 = two GEMM launches (hidden activations through HBM); fused FFN kernel:
  * 1 = hidden chunk via smem, 2 = 1 + 2-CTA clusters sharing weight tiles by TMA multicast, 3 = hidden chunk kept in
- * TMEM (A operand from TMEM; default: measured fastest), 4 = 3 + multicast.
+ * TMEM (A operand from TMEM), 4 = 3 + multicast, 5 = 3 on a CTA pair (tcgen05 cta_group::2, M = 256 across two SMs,
+ * each SM holding half of every weight tile; default: measured fastest).
  * "spk": 0 = CUDA-core speaker attention, 1 = tcgen05 block-diagonal attention (default). */
 int fseend_fs_set_option(fseend_fs_model* m, const char* key, int value);
 
@@ -157,7 +158,7 @@ int fseend_op_gemm(const void* a_f16, int rows_per_seq, int n_seq, int K, const 
                    const float* ln_g, const float* ln_b, float ln_eps, const float* pe_proj, int S,
                    const int* seq_len_dev, void* out_f16, void* stream);
 /* OUT = LayerNorm(X + relu(X W1^T + b1) W2^T + b2): X fp16 [n_seq][rows_per_seq][256], W1 fp16 [F][256],
- * W2 fp16 [256][F]; the F-wide hidden activations stay on chip.  cluster = kernel variant 1..4 (see "ffn" option). */
+ * W2 fp16 [256][F]; the F-wide hidden activations stay on chip.  cluster = kernel variant 1..5 (see "ffn" option). */
 int fseend_op_ffn(const void* x_f16, int rows_per_seq, int n_seq, const void* w1_f16, const float* b1,
                   const void* w2_f16, const float* b2, int F, const float* ln_g, const float* ln_b, float ln_eps,
                   const int* seq_len_dev, int cluster, void* out_f16, void* stream);

@@ -174,7 +174,7 @@ def ffn_ref(x, w1, b1, w2, b2, g, b):
     return ln_ref(x.float() + h @ w2.float().T + b2, g, b)
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 3, 4])
+@pytest.mark.parametrize("cluster", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("rows,F", [(300, 2048), (128 * 5, 256), (1, 1024)])
 def test_fused_ffn(N, cluster, rows, F):
     x = rnd(rows, 256, seed=60).half()
@@ -187,7 +187,8 @@ def test_fused_ffn(N, cluster, rows, F):
     assert (out.float() - ref).abs().max().item() < 6e-3
 
 
-def test_fused_ffn_per_sequence_zero_rows(N):
+@pytest.mark.parametrize("cluster", [4, 5])
+def test_fused_ffn_per_sequence_zero_rows(N, cluster):
     n_seq, T, F = 3, 150, 512
     x = rnd(n_seq * T, 256, seed=70).half()
     w1 = rnd(F, 256, scale=1 / 16, seed=71).half()
@@ -195,7 +196,7 @@ def test_fused_ffn_per_sequence_zero_rows(N):
     b1, b2 = rnd(F, seed=73) * 0.5, rnd(256, seed=74) * 0.5
     g, b = 1 + 0.3 * rnd(256, seed=75), 0.1 * rnd(256, seed=76)
     lens = torch.tensor([150, 77, 1], dtype=torch.int32, device=DEV)
-    out = N.op_ffn(x, w1, b1, w2, b2, g, b, n_seq=n_seq, seq_len=lens, cluster=4).view(n_seq, T, 256)
+    out = N.op_ffn(x, w1, b1, w2, b2, g, b, n_seq=n_seq, seq_len=lens, cluster=cluster).view(n_seq, T, 256)
     ref = ffn_ref(x, w1, b1, w2, b2, g, b).view(n_seq, T, 256)
     for i, l in enumerate(lens.tolist()):
         assert (out[i, :l].float() - ref[i, :l]).abs().max().item() < 6e-3

@@ -103,7 +103,7 @@ def test_weight_update_rebuilds_native_model():
     assert (b.cpu() - ref).abs().max().item() < TOL
 
 
-@pytest.mark.parametrize("ffn,spk", [(0, 0), (1, 1), (2, 1), (3, 1), (4, 1)])
+@pytest.mark.parametrize("ffn,spk", [(0, 0), (1, 1), (2, 1), (3, 1), (4, 1), (5, 1)])
 def test_kernel_variants_agree_with_reference(ffn, spk):
     """Every selectable kernel variant (unfused / fused / fused+multicast FFN; CUDA-core / tcgen05 speaker
     attention) meets the same 1e-3 bound."""
