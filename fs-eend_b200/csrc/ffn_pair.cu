@@ -46,8 +46,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  Default .release.cta semantics on purpose: the data handed over
+// is in TMEM / written by TMA and is ordered by tcgen05.fence / the async proxy, not by a generic-proxy release —
+// .release.cluster costs MEMBAR.ALL.GPU + ERRBAR per arrive (20 % of this kernel's issue slots when first measured).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
