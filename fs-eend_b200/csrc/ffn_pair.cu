@@ -20,6 +20,7 @@
 // TransformerEncoderFusionLayer._ff_block + norm22 (FS-EEND/nnet/modules/merge_tfm_encoder.py:373,397-399).
 #include "ffn.cuh"
 #include "ffn_tile.cuh"
+#include "pair.cuh"
 #include "ptx.cuh"
 
 namespace fseend {
@@ -27,6 +28,7 @@ namespace fseend {
 namespace {
 
 using namespace ffn_detail;
+using namespace pair;
 
 constexpr int kRows = 128;
 constexpr int kChunk = 128;                       // hidden units per chunk (across the pair)
@@ -38,90 +40,6 @@ constexpr int kOffLN = kOffW;                     // after the last MMA: b2 | ga
 constexpr int kOffXchg = kOffW + 4096;
 constexpr int kSmemBytes = kXBytes + kSlots * kSlotBytes + 1024;
 constexpr uint32_t kTmemCols = 512;               // Y [0,256), H0 [256,384), H1 [384,512)
-constexpr uint16_t kBoth = 0x3;
-
-// ---- cluster / cta_group::2 primitives
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-  return r;
-}
-// Arrive on a barrier of another CTA of the cluster.  Default .release.cta semantics on purpose: the data handed over
-// is in TMEM / written by TMA and is ordered by tcgen05.fence / the async proxy, not by a generic-proxy release —
-// .release.cluster costs MEMBAR.ALL.GPU + ERRBAR per arrive (20 % of this kernel's issue slots when first measured).
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > FSEEND_WAIT_LIMIT_SPINS) {
-      printf("[fseend] mbarrier wait timeout: tag=%d block=(%d,%d) thread=%d parity=%u\n", tag, blockIdx.x,
-             blockIdx.y, threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-// TMA load whose completion is signalled on an mbarrier of the pair's leader CTA (cluster address)
-__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
-                                                 int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {  // one warp in EACH CTA
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-               "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// M = 256 MMA over the pair, issued by one thread of the leader CTA.  Descriptors / TMEM addresses are CTA-relative
-// and apply to both CTAs: A rows and D lanes [0,128) live in each CTA, B rows [0, N/2) in each CTA's shared memory.
-__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on the barrier at this offset in BOTH CTAs once every MMA issued so far has completed
-__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(smem_u32(bar)), "h"(kBoth)
-      : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 ffn_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,

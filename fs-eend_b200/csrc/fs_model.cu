@@ -462,7 +462,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     p.ln_g = m->g_in.f();
     p.ln_b = m->be_in.f();
     p.ln_eps = c.ln_eps;
-    L.run("enc.gemm_in_ln", [&] { launch_gemm(m->tm_x16, m->w_in.tm, none, m->tm_hA, p, st); });
+    L.run("enc.gemm_in_ln", [&] { p.tmB_half = &m->w_in.tm128; launch_gemm(m->tm_x16, m->w_in.tm, none, m->tm_hA, p, st); });
   }
   // encoder layers: hA -> (attn) -> hB -> (ffn) -> hA
   for (int l = 0; l < c.enc_n_layers; ++l) {
@@ -470,7 +470,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     {
       GemmParams p = flat_params(Me, 3 * D, D, EPI_BIAS);
       p.bias = E.bqkv.f();
-      L.run("enc.gemm_qkv", [&] { launch_gemm(m->tm_hA, E.wqkv.tm, none, m->tm_qkv_e_out, p, st); });
+      L.run("enc.gemm_qkv", [&] { p.tmB_half = &E.wqkv.tm128; launch_gemm(m->tm_hA, E.wqkv.tm, none, m->tm_qkv_e_out, p, st); });
     }
     {
       AttnParams a{B, 1, T, c.n_heads, c.has_mask ? c.mask_delay : (1 << 28), 1.f / sqrtf(64.f), ATTN_CAUSAL, 128};
@@ -483,7 +483,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_g = E.g1.f();
       p.ln_b = E.be1.f();
       p.ln_eps = c.ln_eps;
-      L.run("enc.gemm_out_ln", [&] { launch_gemm(m->tm_ao_e, E.wo.tm, m->tm_hA, m->tm_hB, p, st); });
+      L.run("enc.gemm_out_ln", [&] { p.tmB_half = &E.wo.tm128; p.residual_ptr = m->hA.p; launch_gemm(m->tm_ao_e, E.wo.tm, m->tm_hA, m->tm_hB, p, st); });
     }
     const bool last = (l == c.enc_n_layers - 1);
     if (m->ffn_mode > 0) {
@@ -501,7 +501,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
         GemmParams p = flat_params(Me, c.enc_dim_feedforward, D, EPI_BIAS);
         p.bias = E.b1.f();
         p.relu = 1;
-        L.run("enc.gemm_ffn1", [&] { launch_gemm(m->tm_hB, E.w1.tm, none, m->tm_f_e_out, p, st); });
+        L.run("enc.gemm_ffn1", [&] { p.tmB_half = &E.w1.tm128; launch_gemm(m->tm_hB, E.w1.tm, none, m->tm_f_e_out, p, st); });
       }
       {
         GemmParams p = flat_params(Me, D, c.enc_dim_feedforward, EPI_LN);
@@ -518,9 +518,9 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
           p.seq_len = static_cast<const int*>(m->len_dev.p);
           CUtensorMap tmA = make_tmap_rows3d(m->f_e.p, c.enc_dim_feedforward, c.enc_dim_feedforward, T, B, 128);
           CUtensorMap tmR = make_tmap_rows3d(m->hB.p, D, D, T, B, 128);
-          L.run("enc.gemm_ffn2_ln", [&] { launch_gemm(tmA, E.w2.tm, tmR, m->tm_hconv_in, p, st); });
+          L.run("enc.gemm_ffn2_ln", [&] { p.tmB_half = &E.w2.tm128; launch_gemm(tmA, E.w2.tm, tmR, m->tm_hconv_in, p, st); });
         } else {
-          L.run("enc.gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_e_in, E.w2.tm, m->tm_hB, m->tm_hA, p, st); });
+          L.run("enc.gemm_ffn2_ln", [&] { p.tmB_half = &E.w2.tm128; launch_gemm(m->tm_f_e_in, E.w2.tm, m->tm_hB, m->tm_hA, p, st); });
         }
       }
   
@@ -539,14 +539,14 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     p.tap_shift = -c.conv_padding;
     p.mode = EPI_L2;
     p.bias = m->b_conv.f();
-    L.run("gemm_conv_l2", [&] { launch_gemm(m->tm_hconv_in, m->w_conv.tm, none, m->tm_emb_out, p, st); });
+    L.run("gemm_conv_l2", [&] { p.tmB_half = &m->w_conv.tm128; launch_gemm(m->tm_hconv_in, m->w_conv.tm, none, m->tm_emb_out, p, st); });
   }
   // attractor init -> aX [B][T][S][D]
   {
     GemmParams p = flat_params(Me, D, D, EPI_CONVERT);
     p.S = S;
     p.pe_proj = m->pe_proj.f();
-    L.run("gemm_convert", [&] { launch_gemm(m->tm_emb_in, m->w_cvt.tm, none, m->tm_cvt_out, p, st); });
+    L.run("gemm_convert", [&] { p.tmB_half = &m->w_cvt.tm128; launch_gemm(m->tm_emb_in, m->w_cvt.tm, none, m->tm_cvt_out, p, st); });
   }
   // decoder layers: aX -> time attention -> aY -> speaker attention -> aZ -> FFN -> aX
   for (int l = 0; l < c.dec_n_layers; ++l) {
@@ -554,7 +554,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     {
       GemmParams p = flat_params(Md, 3 * D, D, EPI_BIAS);
       p.bias = Dl.bqkv1.f();
-      L.run("dec.gemm_qkv1", [&] { launch_gemm(m->tm_aX, Dl.wqkv1.tm, none, m->tm_qkv_d_out, p, st); });
+      L.run("dec.gemm_qkv1", [&] { p.tmB_half = &Dl.wqkv1.tm128; launch_gemm(m->tm_aX, Dl.wqkv1.tm, none, m->tm_qkv_d_out, p, st); });
     }
     {
       AttnParams a{B, S, T, c.n_heads, c.mask_delay, 1.f / sqrtf(64.f), ATTN_CAUSAL, 128};
@@ -567,12 +567,12 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_g = Dl.g11.f();
       p.ln_b = Dl.be11.f();
       p.ln_eps = c.ln_eps;
-      L.run("dec.gemm_out1_ln", [&] { launch_gemm(m->tm_ao_d, Dl.wo1.tm, m->tm_aX, m->tm_aY, p, st); });
+      L.run("dec.gemm_out1_ln", [&] { p.tmB_half = &Dl.wo1.tm128; p.residual_ptr = m->aX.p; launch_gemm(m->tm_ao_d, Dl.wo1.tm, m->tm_aX, m->tm_aY, p, st); });
     }
     {
       GemmParams p = flat_params(Md, 3 * D, D, EPI_BIAS);
       p.bias = Dl.bqkv2.f();
-      L.run("dec.gemm_qkv2", [&] { launch_gemm(m->tm_aY, Dl.wqkv2.tm, none, m->tm_qkv_d_out, p, st); });
+      L.run("dec.gemm_qkv2", [&] { p.tmB_half = &Dl.wqkv2.tm128; launch_gemm(m->tm_aY, Dl.wqkv2.tm, none, m->tm_qkv_d_out, p, st); });
     }
     if (m->spk_mode == 1) {
       AttnParams a{1, S, static_cast<int>(Md), c.n_heads, 0, 1.f / sqrtf(64.f), ATTN_BLOCKDIAG, (128 / S) * S};
@@ -590,7 +590,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_g = Dl.g21.f();
       p.ln_b = Dl.be21.f();
       p.ln_eps = c.ln_eps;
-      L.run("dec.gemm_out2_ln", [&] { launch_gemm(m->tm_ao_d, Dl.wo2.tm, m->tm_aY, m->tm_aZ, p, st); });
+      L.run("dec.gemm_out2_ln", [&] { p.tmB_half = &Dl.wo2.tm128; p.residual_ptr = m->aY.p; launch_gemm(m->tm_ao_d, Dl.wo2.tm, m->tm_aY, m->tm_aZ, p, st); });
     }
     if (m->ffn_mode > 0) {
       FfnParams fp = ffn_params(static_cast<int>(Md), 1, c.dec_dim_feedforward, Dl.b1, Dl.b2, Dl.g22, Dl.be22, c.ln_eps,
@@ -604,7 +604,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
         GemmParams p = flat_params(Md, c.dec_dim_feedforward, D, EPI_BIAS);
         p.bias = Dl.b1.f();
         p.relu = 1;
-        L.run("dec.gemm_ffn1", [&] { launch_gemm(m->tm_aZ, Dl.w1.tm, none, m->tm_f_d_out, p, st); });
+        L.run("dec.gemm_ffn1", [&] { p.tmB_half = &Dl.w1.tm128; launch_gemm(m->tm_aZ, Dl.w1.tm, none, m->tm_f_d_out, p, st); });
       }
       {
         GemmParams p = flat_params(Md, D, c.dec_dim_feedforward, EPI_LN);
@@ -613,7 +613,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
         p.ln_g = Dl.g22.f();
         p.ln_b = Dl.be22.f();
         p.ln_eps = c.ln_eps;
-        L.run("dec.gemm_ffn2_ln", [&] { launch_gemm(m->tm_f_d_in, Dl.w2.tm, m->tm_aZ, m->tm_aX, p, st); });
+        L.run("dec.gemm_ffn2_ln", [&] { p.tmB_half = &Dl.w2.tm128; launch_gemm(m->tm_f_d_in, Dl.w2.tm, m->tm_aZ, m->tm_aX, p, st); });
       }
   
     }
@@ -1054,6 +1054,10 @@ int fseend_op_gemm(const void* a_f16, int rows_per_seq, int n_seq, int K, const 
     uint64_t ws[1] = {static_cast<uint64_t>(K)};
     uint32_t wb[2] = {64, 256};
     CUtensorMap tmB = make_tmap_f16(w_f16, 2, wd, ws, wb);
+    uint32_t wb_half[2] = {64, 128};
+    CUtensorMap tmBh = make_tmap_f16(w_f16, 2, wd, ws, wb_half);
+    p.tmB_half = &tmBh;
+    p.residual_ptr = residual_f16;
     CUtensorMap tmO;
     if (mode == EPI_CONVERT) {
       uint64_t dims[3] = {256, static_cast<uint64_t>(S), static_cast<uint64_t>(rows_per_seq) * n_seq};

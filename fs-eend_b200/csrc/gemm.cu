@@ -154,16 +154,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // gemm_persist.cu
 void launch_gemm_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
                          const CUtensorMap& tmO2, const GemmParams& p, cudaStream_t stream);
+// gemm_pair.cu
+bool gemm_pair_supported(const GemmParams& p);
+void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream);
 
+static int env_switch(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : dflt;
+}
 // FSEEND_GEMM_PERSIST=0 selects the one-tile-per-CTA kernel below instead of the persistent one (gemm_persist.cu).
 static bool use_persist() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("FSEEND_GEMM_PERSIST");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
+  static const int v = env_switch("FSEEND_GEMM_PERSIST", 1);
   return v == 1;
 }
+// FSEEND_GEMM_PAIR: 0 = never use the weight-stationary CTA-pair kernel (gemm_pair.cu), 1 = where it pays (default),
+// 2 = wherever it is structurally possible (tests).
+static int pair_mode() { return env_switch("FSEEND_GEMM_PAIR", 1); }   // read per launch: tests flip it
 
 // Measured on B200 (B=64, T=500, S=6): the persistent kernel wins on the wide bias/activation projections
 // (QKV 0.142 -> 0.113 ms) where many output tiles stream per SM; the row-epilogue GEMMs (residual + LayerNorm, L2,
@@ -172,24 +178,21 @@ static bool persist_pays(const GemmParams& p) {
   const int items = p.n_seq * p.tiles_per_seq * p.n_tiles;
   return (p.mode == EPI_BIAS || p.mode == EPI_GLU) && items >= 296;
 }
-
-void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
-                 const GemmParams& p, cudaStream_t stream) {
-  if (use_persist() && persist_pays(p)) {
-    launch_gemm_persist(tmA, tmB, tmR, tmO, tmO, p, stream);
-    return;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    attr_set = true;
-  }
-  const int grid = p.n_seq * p.tiles_per_seq * p.n_tiles;
-  gemm_kernel<<<grid, 256, kSmemBytes, stream>>>(tmA, tmB, tmR, tmO, tmO, p);
+// The pair kernel needs the weight n-tile to stay resident (K <= 256, one tap) and at least a few row-tile pairs per
+// cluster to amortise loading it.
+static bool pair_pays(const GemmParams& p) {
+  if (pair_mode() == 0 || !gemm_pair_supported(p)) return false;
+  if (pair_mode() == 2) return true;
+  const int items = (p.n_seq * p.tiles_per_seq + 1) / 2 * p.n_tiles;
+  return items >= 148;
 }
 
 void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
                   const CUtensorMap& tmO2, const GemmParams& p, cudaStream_t stream) {
+  if (pair_pays(p)) {
+    launch_gemm_pair(tmA, tmO, p, stream);
+    return;
+  }
   if (use_persist() && persist_pays(p)) {
     launch_gemm_persist(tmA, tmB, tmR, tmO, tmO2, p, stream);
     return;
@@ -201,6 +204,11 @@ void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   }
   const int grid = p.n_seq * p.tiles_per_seq * p.n_tiles;
   gemm_kernel<<<grid, 256, kSmemBytes, stream>>>(tmA, tmB, tmR, tmO, tmO2, p);
+}
+
+void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
+                 const GemmParams& p, cudaStream_t stream) {
+  launch_gemm2(tmA, tmB, tmR, tmO, tmO, p, stream);
 }
 
 }  // namespace fseend

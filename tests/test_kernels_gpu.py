@@ -97,6 +97,38 @@ def test_gemm_convert_broadcast(N):
     assert (out.float() - ref).abs().max().item() < 5e-3
 
 
+def test_gemm_k256_residual_layernorm_odd_tiles(N):
+    a = rnd(128 * 7 + 5, 256, seed=25).half()                # 8 row tiles -> 4 pairs; 7*128+5 rows: ragged last tile
+    w = rnd(256, 256, scale=1 / 16, seed=26).half()
+    res = rnd(128 * 7 + 5, 256, seed=27).half()
+    bias, g, b = rnd(256, seed=28), 1 + 0.3 * rnd(256, seed=29), 0.1 * rnd(256, seed=30)
+    out = N.op_gemm(a, w, N.EPI_LN, bias=bias, residual=res, ln_g=g, ln_b=b)
+    ref = ln_ref(a.float() @ w.float().T + bias + res.float(), g, b)
+    assert (out.float() - ref).abs().max().item() < 5e-3
+    a3 = a[: 128 * 3 - 1]                                     # odd tile count: the pair kernel's last CTA idles
+    out = N.op_gemm(a3, w, N.EPI_LN, bias=bias, residual=res[: a3.shape[0]], ln_g=g, ln_b=b)
+    assert (out.float() - ref[: a3.shape[0]]).abs().max().item() < 5e-3
+
+
+def test_gemm_many_tiles_wide(N):
+    """More row-tile pairs than clusters and three n-tiles: every cluster loops over several items."""
+    a = rnd(128 * 201, 256, seed=31).half()
+    w = rnd(768, 256, scale=1 / 16, seed=32).half()
+    bias = rnd(768, seed=33)
+    out = N.op_gemm(a, w, N.EPI_BIAS, bias=bias)
+    ref = a.float() @ w.float().T + bias
+    assert (out.float() - ref).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("case", ["bias_relu_ragged_rows", "layernorm_zero_rows_beyond_len", "convert_broadcast",
+                                  "k256_residual_layernorm_odd_tiles", "many_tiles_wide", "k384_layernorm"])
+def test_gemm_pair_kernel_forced(N, monkeypatch, case):
+    """FSEEND_GEMM_PAIR=2 routes every structurally eligible GEMM (one tap, K <= 256) through the weight-stationary
+    CTA-pair kernel, whatever its size; K = 384 checks the fallback."""
+    monkeypatch.setenv("FSEEND_GEMM_PAIR", "2")
+    globals()["test_gemm_" + case](N)
+
+
 def attn_ref(qkv, mask_delay, scale=0.125):
     B, T, S, _ = qkv.shape
     x = qkv.float().permute(0, 2, 1, 3).reshape(B * S, T, 3, 4, 64)
