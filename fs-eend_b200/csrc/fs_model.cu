@@ -483,7 +483,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_g = E.g1.f();
       p.ln_b = E.be1.f();
       p.ln_eps = c.ln_eps;
-      L.run("enc.gemm_out_ln", [&] { p.tmB_half = &E.wo.tm128; p.residual_ptr = m->hA.p; launch_gemm(m->tm_ao_e, E.wo.tm, m->tm_hA, m->tm_hB, p, st); });
+      L.run("enc.gemm_out_ln", [&] { p.tmB_half = &E.wo.tm128; launch_gemm(m->tm_ao_e, E.wo.tm, m->tm_hA, m->tm_hB, p, st); });
     }
     const bool last = (l == c.enc_n_layers - 1);
     if (m->ffn_mode > 0) {
@@ -567,7 +567,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_g = Dl.g11.f();
       p.ln_b = Dl.be11.f();
       p.ln_eps = c.ln_eps;
-      L.run("dec.gemm_out1_ln", [&] { p.tmB_half = &Dl.wo1.tm128; p.residual_ptr = m->aX.p; launch_gemm(m->tm_ao_d, Dl.wo1.tm, m->tm_aX, m->tm_aY, p, st); });
+      L.run("dec.gemm_out1_ln", [&] { p.tmB_half = &Dl.wo1.tm128; launch_gemm(m->tm_ao_d, Dl.wo1.tm, m->tm_aX, m->tm_aY, p, st); });
     }
     {
       GemmParams p = flat_params(Md, 3 * D, D, EPI_BIAS);
@@ -590,7 +590,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_g = Dl.g21.f();
       p.ln_b = Dl.be21.f();
       p.ln_eps = c.ln_eps;
-      L.run("dec.gemm_out2_ln", [&] { p.tmB_half = &Dl.wo2.tm128; p.residual_ptr = m->aY.p; launch_gemm(m->tm_ao_d, Dl.wo2.tm, m->tm_aY, m->tm_aZ, p, st); });
+      L.run("dec.gemm_out2_ln", [&] { p.tmB_half = &Dl.wo2.tm128; launch_gemm(m->tm_ao_d, Dl.wo2.tm, m->tm_aY, m->tm_aZ, p, st); });
     }
     if (m->ffn_mode > 0) {
       FfnParams fp = ffn_params(static_cast<int>(Md), 1, c.dec_dim_feedforward, Dl.b1, Dl.b2, Dl.g22, Dl.be22, c.ln_eps,
@@ -1057,7 +1057,7 @@ int fseend_op_gemm(const void* a_f16, int rows_per_seq, int n_seq, int K, const 
     uint32_t wb_half[2] = {64, 128};
     CUtensorMap tmBh = make_tmap_f16(w_f16, 2, wd, ws, wb_half);
     p.tmB_half = &tmBh;
-    p.residual_ptr = residual_f16;
+   
     CUtensorMap tmO;
     if (mode == EPI_CONVERT) {
       uint64_t dims[3] = {256, static_cast<uint64_t>(S), static_cast<uint64_t>(rows_per_seq) * n_seq};

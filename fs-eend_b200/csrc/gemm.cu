@@ -156,7 +156,8 @@ void launch_gemm_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
                          const CUtensorMap& tmO2, const GemmParams& p, cudaStream_t stream);
 // gemm_pair.cu
 bool gemm_pair_supported(const GemmParams& p);
-void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream);
+void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmR, const CUtensorMap& tmO, const GemmParams& p,
+                      cudaStream_t stream);
 
 static int env_switch(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -190,7 +191,7 @@ static bool pair_pays(const GemmParams& p) {
 void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
                   const CUtensorMap& tmO2, const GemmParams& p, cudaStream_t stream) {
   if (pair_pays(p)) {
-    launch_gemm_pair(tmA, tmO, p, stream);
+    launch_gemm_pair(tmA, tmR, tmO, p, stream);
     return;
   }
   if (use_persist() && persist_pays(p)) {

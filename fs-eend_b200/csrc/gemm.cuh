@@ -44,8 +44,6 @@ struct GemmParams {
   const int* seq_len;    // optional [n_seq]: EPI_LN rows t >= seq_len[b] are written as zeros
   const CUtensorMap* tmB_half = nullptr;   // optional: the weight with box (64,128) — enables the weight-stationary
                                            // CTA-pair kernel (gemm_pair.cu) for EPI_BIAS / EPI_LN, one tap, K <= 256
-  const void* residual_ptr = nullptr;      // optional: the residual as a dense fp16 [n_seq][rows_per_seq][N] buffer
-                                           // (what tmR describes); the pair kernel reads residual rows directly
 };
 
 // tmA: 3-D (K, rows_per_seq, n_seq) box (64,128,1);  tmB: 2-D (K, taps*N) box (64,256);

@@ -8,11 +8,13 @@
 //   warp 0     : TMA producer (both CTAs): resident W half once, then A k-blocks through a 5-stage ring; completion is
 //                signalled on the LEADER's barriers.
 //   warp 1     : tcgen05 issuer (leader CTA only), two 256-column TMEM accumulators.
-//   warps 2-9  : epilogue of this CTA's 128 rows, two threads per row (128 columns each).  Register-resident: the
-//                residual row is fetched from global memory before the accumulator is awaited, results are packed to
-//                fp16 in registers, and the staging tile is only touched once the PREVIOUS item's TMA store has
-//                drained it — so the store of item i overlaps the TMEM reads and math of item i+1 (the generic
-//                epilogue waits for each store; that wait was 29 % of this kernel when first measured).
+//   warps 2-9  : epilogue of this CTA's 128 rows, two threads per row (128 columns each).  Results are packed to fp16
+//                in registers and the staging tile is only touched once the PREVIOUS item's TMA store has drained it,
+//                so the store of item i overlaps the TMEM reads and math of item i+1.
+// The residual of the LayerNorm GEMMs is added BY THE TENSOR CORE: the residual tile streams through the same ring as
+// the activations and is multiplied by a 64 x 64 identity (4 KB per CTA) into the accumulator (four N = 64 MMA groups
+// per item; fp16 x 1.0 accumulates exactly in fp32).  That keeps the residual on the deep TMA prefetch path instead of
+// a strided per-thread global load or a second staging buffer that shared memory has no room for.
 // Epilogues: EPI_BIAS (+ReLU/Swish) and EPI_LN (bias, optional residual, zero rows beyond seq_len).
 #include "gemm.cuh"
 #include "gemm_epilogue.cuh"
@@ -32,16 +34,20 @@ constexpr int kMaxKBlocks = 4;                            // resident W half: up
 constexpr int kOffW = 0;
 constexpr int kOffA = kMaxKBlocks * kKBlockBytes;         // 64 KB
 constexpr int kOffStage = kOffA + kStages * kKBlockBytes; // 144 KB
-constexpr int kSmemBytes = kOffStage + 4 * gemm_detail::kSubTileBytes;   // + 64 KB staging = 208 KB
+constexpr int kOffIdent = kOffStage + 4 * gemm_detail::kSubTileBytes;    // + 64 KB staging
+constexpr int kIdentBytes = 32 * 128;                     // this CTA's 32 rows of the 64 x 64 identity, [32][64 k]
+constexpr int kSmemBytes = kOffIdent + kIdentBytes;       // 212 KB
+constexpr int kResBlocks = 4;                             // residual k-blocks per item (N = 256)
 constexpr uint32_t kTmemCols = 512;
 
-// kLn: EPI_LN (else EPI_BIAS); kRes: residual added before the LayerNorm.  Compile-time so that each variant keeps its
-// working set in registers (a runtime-mode version spilled ~60 registers to local memory, and with the shared-memory
-// carve-out this kernel needs, local memory lives in L2).
+// kLn: EPI_LN (else EPI_BIAS); kRes: residual accumulated by identity MMAs.  Compile-time so that each variant keeps
+// its working set in registers (a runtime-mode version spilled ~60 registers to local memory, and with the
+// shared-memory carve-out this kernel needs, local memory lives in L2).
 template <bool kLn, bool kRes>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-                 const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+                 const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t w_full, a_full[kStages], a_empty[kStages], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
@@ -84,6 +90,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmBh);
     tma_prefetch_desc(&tmO);
   }
+  if (kRes) {
+    // rows [32 rank, +32) of the 64 x 64 identity as a K-major 128B-swizzled B tile (N = 64 across the pair)
+    for (int i = tid; i < 32 * 8; i += blockDim.x) {
+      const int row = i >> 3, chunk = i & 7;
+      const int one = static_cast<int>(rank) * 32 + row - chunk * 8;   // position of the 1.0 inside this 8-half chunk
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (one >= 0 && one < 8) reinterpret_cast<uint16_t*>(&v)[one] = 0x3C00;   // fp16 1.0
+      *reinterpret_cast<uint4*>(smem + kOffIdent + sw128_offset(row, chunk)) = v;
+    }
+    fence_proxy_async_smem();
+  }
   if (warp == 1) tmem_alloc_pair(&tmem_base_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -117,6 +134,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
       }
+      for (int rb = 0; kRes && rb < kResBlocks; ++rb, ++u) {   // residual tile: 4 more [128][64] blocks
+        const int s = u % kStages;
+        mbar_wait(&a_empty[s], ((u / kStages) & 1) ^ 1, 172);
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(&a_full[s], 2 * kKBlockBytes);
+          tma_load_3d_pair(smem + kOffA + s * kKBlockBytes, &tmR, a_full_leader + s * 8, n0 + rb * 64, t0, seq);
+        }
+        __syncwarp();
+      }
     }
   } else if (warp == 1) {
     if (leader) {
@@ -140,7 +166,24 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kk = 0; kk < BK / 16; ++kk)
               umma2_f16(tmem_D, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
             umma2_commit(&a_empty[s]);
-            if (kb == p.k_blocks - 1) umma2_commit(&tmem_full[acc]);
+            if (!kRes && kb == p.k_blocks - 1) umma2_commit(&tmem_full[acc]);
+          }
+          __syncwarp();
+        }
+        for (int rb = 0; kRes && rb < kResBlocks; ++rb, ++u) {
+          // D[:, 64 rb .. +64) += R[:, 64 rb .. +64) * I64
+          constexpr uint32_t idesc_r = make_idesc_f16(2 * BM, 64, false);
+          const int s = u % kStages;
+          mbar_wait(&a_full[s], (u / kStages) & 1, 178);
+          tc_fence_after();
+          const uint64_t adesc = smem_desc_sw128(smem_u32(smem + kOffA + s * kKBlockBytes));
+          const uint64_t idesc_tile = smem_desc_sw128(smem_u32(smem + kOffIdent));
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk)
+              umma2_f16(tmem_D + rb * 64, adesc + 2 * kk, idesc_tile + 2 * kk, idesc_r, 1u);
+            umma2_commit(&a_empty[s]);
+            if (rb == kResBlocks - 1) umma2_commit(&tmem_full[acc]);
           }
           __syncwarp();
         }
@@ -159,8 +202,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     load_epi_params(epi_params, p, n0, et, 256);   // this cluster's n-tile never changes
     sync();
     constexpr bool ln = kLn;
-    constexpr bool use_res = kLn && kRes;
-    const int N = p.n_tiles * BN;
     uint32_t n = 0;
     for (int mp = first; mp < m_pairs; mp += cnt, ++n) {
       const int m_tile = 2 * mp + static_cast<int>(rank);
@@ -168,22 +209,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int t0 = (m_tile % p.tiles_per_seq) * BM;
       const bool valid = m_tile < m_tiles;      // CTA-uniform
       const int acc = n & 1;
-      // this thread's 128 output columns as packed fp16 pairs; holds the residual row until it is consumed
-      uint32_t pk[64];
-      if (use_res) {
-        const bool row_ok = valid && (t0 + r) < p.rows_per_seq;
-        const uint4* rp = reinterpret_cast<const uint4*>(
-            reinterpret_cast<const __half*>(p.residual_ptr) +
-            (static_cast<size_t>(seq) * p.rows_per_seq + t0 + r) * N + n0 + half * 128);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint4 v = row_ok ? __ldg(rp + i) : make_uint4(0u, 0u, 0u, 0u);
-          pk[4 * i + 0] = v.x;
-          pk[4 * i + 1] = v.y;
-          pk[4 * i + 2] = v.z;
-          pk[4 * i + 3] = v.w;
-        }
-      }
+      uint32_t pk[ln ? 1 : 64];   // EPI_BIAS: this thread's 128 output columns as packed fp16 pairs
       mbar_wait(&tmem_full[acc], (n >> 1) & 1, 176);
       tc_fence_after();
       if (valid) {
@@ -207,8 +233,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int i = 0; i < 16; ++i) pk[c * 16 + i] = pack_half2(a[2 * i], a[2 * i + 1]);
           }
         } else {
-          // pass 1: z = acc + bias (+ residual) is written back over the accumulator (fp32, TMEM writes are cheap) so
-          // that the residual registers die here; row statistics by Chan's merge of 32-column chunks
+          // pass 1: row statistics of z = acc + bias (the residual is already in the accumulator); Chan's merge of
+          // 32-column chunks, then of the two half rows
           RowStats st{0.f, 0.f, 0.f};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -216,20 +242,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             smem_vec32(epi_params.bias + half * 128 + c * 32, aux);
 #pragma unroll
             for (int i = 0; i < 32; ++i) a[i] += aux[i];
-            if (use_res) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk[c * 16 + i]));
-                a[2 * i] += f.x;
-                a[2 * i + 1] += f.y;
-              }
-            }
-            {
-              uint32_t zr[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) zr[i] = __float_as_uint(a[i]);
-              tmem_st32(trow + c * 32, zr);
-            }
             float sum = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) sum += a[i];
@@ -246,8 +258,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             st.mean += delta * (32.f / nn);
             st.n = nn;
           }
-          tmem_st_wait();
           xchg[half * 128 + r] = make_float4(st.n, st.mean, st.m2, 0.f);
+          if (store_thread) tma_store_wait_read0();   // the previous item's stores have drained the staging tile
           sync();
           const float4 o = xchg[(half ^ 1) * 128 + r];
           sync();
@@ -255,36 +267,43 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const float mean = 0.5f * (st.mean + o.y);
           const float rstd = rsqrtf((st.m2 + o.z + dm * dm * 64.f) * (1.f / 256.f) + p.ln_eps);
           const bool zero_row = p.seq_len != nullptr && (t0 + r) >= p.seq_len[seq];
-          // pass 2: normalise, affine, pack
+          // pass 2: normalise, affine, pack straight into the staging tile (free since the sync above)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             tmem_ld32_sync(trow + c * 32, a);
+            smem_vec32(epi_params.bias + half * 128 + c * 32, aux);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] += aux[i];
             smem_vec32(epi_params.g + half * 128 + c * 32, aux);
 #pragma unroll
             for (int i = 0; i < 32; ++i) a[i] = (a[i] - mean) * rstd * aux[i];
             smem_vec32(epi_params.b + half * 128 + c * 32, aux);
 #pragma unroll
             for (int i = 0; i < 32; ++i) a[i] = zero_row ? 0.f : a[i] + aux[i];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[c * 16 + i] = pack_half2(a[2 * i], a[2 * i + 1]);
+            staging_write32(staging, r, half * 4 + c, a);
           }
+          fence_proxy_async_smem();
         }
       }
       tc_fence_before();
       mbar_arrive_cluster(tmem_empty_leader + acc * 8);   // this thread's TMEM reads of the accumulator are complete
-      if (store_thread) tma_store_wait_read0();            // the previous item's stores have drained the staging tile
-      sync();
-      if (valid) {
+      if (!ln) {
+        if (store_thread) tma_store_wait_read0();          // the previous item's stores have drained the staging tile
+        sync();
+        if (valid) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int cg = half * 4 + c;                       // 32-column chunk of the 256-wide tile
-          uint8_t* sub = staging + (cg >> 1) * kSubTileBytes;
+          for (int c = 0; c < 4; ++c) {
+            const int cg = half * 4 + c;                     // 32-column chunk of the 256-wide tile
+            uint8_t* sub = staging + (cg >> 1) * kSubTileBytes;
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(sub + sw128_offset(r, (cg & 1) * 4 + q)) =
-                make_uint4(pk[c * 16 + 4 * q], pk[c * 16 + 4 * q + 1], pk[c * 16 + 4 * q + 2], pk[c * 16 + 4 * q + 3]);
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(sub + sw128_offset(r, (cg & 1) * 4 + q)) = make_uint4(
+                  pk[c * 16 + 4 * q], pk[c * 16 + 4 * q + 1], pk[c * 16 + 4 * q + 2], pk[c * 16 + 4 * q + 3]);
+          }
+          fence_proxy_async_smem();
         }
-        fence_proxy_async_smem();
+      } else if (!valid) {
+        if (store_thread) tma_store_wait_read0();
       }
       sync();
       if (store_thread && valid) {
@@ -306,10 +325,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 bool gemm_pair_supported(const GemmParams& p) {
   if (p.tmB_half == nullptr || p.taps != 1 || p.k_blocks < 1 || p.k_blocks > kMaxKBlocks) return false;
   if (p.mode == EPI_BIAS) return true;
-  return p.mode == EPI_LN && p.ln2_g == nullptr && (!p.has_residual || p.residual_ptr != nullptr);
+  return p.mode == EPI_LN && p.ln2_g == nullptr;
 }
 
-void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmO, const GemmParams& p, cudaStream_t stream) {
+void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmR, const CUtensorMap& tmO, const GemmParams& p,
+                      cudaStream_t stream) {
   static int num_sms = 0;
   if (!num_sms) {
     cudaFuncSetAttribute(gemm_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -323,9 +343,9 @@ void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmO, const Gemm
   const int items = m_pairs * p.n_tiles;                 // >= n_tiles: every n-tile gets at least one cluster
   const int clusters = items < num_sms / 2 ? items : num_sms / 2;
   const dim3 grid(2 * clusters), block(320);
-  if (p.mode == EPI_BIAS) gemm_pair_kernel<false, false><<<grid, block, kSmemBytes, stream>>>(tmA, *p.tmB_half, tmO, p);
-  else if (p.has_residual) gemm_pair_kernel<true, true><<<grid, block, kSmemBytes, stream>>>(tmA, *p.tmB_half, tmO, p);
-  else gemm_pair_kernel<true, false><<<grid, block, kSmemBytes, stream>>>(tmA, *p.tmB_half, tmO, p);
+  if (p.mode == EPI_BIAS) gemm_pair_kernel<false, false><<<grid, block, kSmemBytes, stream>>>(tmA, *p.tmB_half, tmR, tmO, p);
+  else if (p.has_residual) gemm_pair_kernel<true, true><<<grid, block, kSmemBytes, stream>>>(tmA, *p.tmB_half, tmR, tmO, p);
+  else gemm_pair_kernel<true, false><<<grid, block, kSmemBytes, stream>>>(tmA, *p.tmB_half, tmR, tmO, p);
 }
 
 }  // namespace fseend
