@@ -274,7 +274,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             tmem_ld32(tmem_S + 32, a1);
             tmem_ld_wait();
           }
-          float mx = -INFINITY;
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             if (hmode[hh] == 1) {
@@ -285,13 +285,20 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
               }
             }
             if (hmode[hh] != 2) {
+              // four independent FMNMX3 chains (a single running max is a 64-deep dependent chain)
 #pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[hh * 32 + i]));
+              for (int i = 0; i < 32; i += 8) {
+                mx4[0] = fmax3(mx4[0], __uint_as_float(sv[hh * 32 + i + 0]), __uint_as_float(sv[hh * 32 + i + 1]));
+                mx4[1] = fmax3(mx4[1], __uint_as_float(sv[hh * 32 + i + 2]), __uint_as_float(sv[hh * 32 + i + 3]));
+                mx4[2] = fmax3(mx4[2], __uint_as_float(sv[hh * 32 + i + 4]), __uint_as_float(sv[hh * 32 + i + 5]));
+                mx4[3] = fmax3(mx4[3], __uint_as_float(sv[hh * 32 + i + 6]), __uint_as_float(sv[hh * 32 + i + 7]));
+              }
             }
           }
-          m_new = fmaxf(m_run, mx);
+          m_new = fmax3(m_run, fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
           const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * sl;
           alpha = (m_new == m_run) ? 1.f : ex2(m_run * sl - m_scaled);   // m_run = -inf -> 0
+          float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             if (hmode[hh] == 2) {
@@ -307,13 +314,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
                   const int c = hh * 32 + q * 8 + 2 * t;
                   const float p0 = ex2(fmaf(__uint_as_float(sv[c]), sl, -m_scaled));
                   const float p1 = ex2(fmaf(__uint_as_float(sv[c + 1]), sl, -m_scaled));
-                  psum += p0 + p1;
+                  ps4[t] += p0 + p1;           // four independent partial sums
                   e[t] = pack_half2(p0, p1);
                 }
                 *reinterpret_cast<uint4*>(ptile + sw128_offset(r, hh * 4 + q)) = make_uint4(e[0], e[1], e[2], e[3]);
               }
             }
           }
+          psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
         } else {
           // no row of this warp sees any column of this tile (upper part of a diagonal tile): P = 0
 #pragma unroll

@@ -179,13 +179,17 @@ static bool persist_pays(const GemmParams& p) {
   const int items = p.n_seq * p.tiles_per_seq * p.n_tiles;
   return (p.mode == EPI_BIAS || p.mode == EPI_GLU) && items >= 296;
 }
-// The pair kernel needs the weight n-tile to stay resident (K <= 256, one tap) and at least a few row-tile pairs per
-// cluster to amortise loading it.
+// The pair kernel needs the weight n-tile to stay resident (K <= 256, one tap) and about one row-tile pair per cluster
+// to amortise loading it (FSEEND_GEMM_PAIR_MIN overrides the item threshold).
 static bool pair_pays(const GemmParams& p) {
   if (pair_mode() == 0 || !gemm_pair_supported(p)) return false;
   if (pair_mode() == 2) return true;
   const int items = (p.n_seq * p.tiles_per_seq + 1) / 2 * p.n_tiles;
-  return items >= 148;
+  static const int min_items = [] {
+    const char* e = getenv("FSEEND_GEMM_PAIR_MIN");
+    return e ? atoi(e) : 74;   // one item per cluster: still ahead of the one-tile kernel (enc out-proj 23 -> 19 us)
+  }();
+  return items >= min_items;
 }
 
 void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,

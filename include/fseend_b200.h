@@ -80,7 +80,9 @@ int fseend_fs_forward_host(fseend_fs_model* m, const float* x_packed_host, const
  * 1 = hidden chunk via smem, 2 = 1 + 2-CTA clusters sharing weight tiles by TMA multicast, 3 = hidden chunk kept in
  * TMEM (A operand from TMEM), 4 = 3 + multicast, 5 = 3 on a CTA pair (tcgen05 cta_group::2, M = 256 across two SMs,
  * each SM holding half of every weight tile; default: measured fastest).
- * "spk": 0 = CUDA-core speaker attention, 1 = tcgen05 block-diagonal attention (default). */
+ * "spk": 0 = CUDA-core speaker attention, 1 = tcgen05 block-diagonal attention (default).
+ * "host_chunks": fseend_fs_forward_host splits the batch into this many chunks of whole sequences and overlaps the
+ * host->device copy of chunk i+1 with the kernels of chunk i (0 = automatic, 1 = no overlap, <= 8). */
 int fseend_fs_set_option(fseend_fs_model* m, const char* key, int value);
 
 /* Per-kernel timing of the next forward calls (CUDA events around every launch; off by default).

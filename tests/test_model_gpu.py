@@ -60,6 +60,27 @@ def test_host_buffer_entry_point_matches_device_entry_point():
     assert torch.equal(dev_logits.cpu(), host_logits)
 
 
+@pytest.mark.parametrize("chunks", [1, 2, 4])
+def test_host_entry_point_chunked_copy_compute_overlap(chunks):
+    """forward_host splits the batch into chunks of whole sequences (copy of chunk i+1 under the kernels of chunk i);
+    the chunks share one padded T, so logits / emb / attractors land exactly where the unchunked call puts them."""
+    sd, src, lens, S, cfg, g = load_case("ragged_S6")
+    m = make_model(sd)
+    src4 = (list(src) * 4)[:4]                      # 4 ragged sequences, longest not in the first chunk
+    src4 = [src4[1], src4[0], src4[3], src4[2]] if len(src4[0]) >= len(src4[1]) else src4
+    lens4 = [len(t) for t in src4]
+    x = torch.cat(src4).contiguous()
+    nat = m.native()
+    ref_l, ref_e, ref_a = nat.forward(x.cuda(), lens4, S, want_emb=True, want_att=True)
+    nat.set_option("host_chunks", chunks)
+    l, e, a = nat.forward_host(x.pin_memory(), lens4, S, want_emb=True, want_att=True)
+    nat.set_option("host_chunks", 0)
+    for b, n in enumerate(lens4):                   # rows beyond a sequence's length are padding
+        assert (l[b, :n] - ref_l.cpu()[b, :n]).abs().max().item() < 5e-4
+        assert (e[b, :n] - ref_e.cpu()[b, :n]).abs().max().item() < 5e-4
+        assert (a[b, :n] - ref_a.cpu()[b, :n]).abs().max().item() < 5e-4
+
+
 def test_full_size_properties_B64_T500_S6():
     """BASELINE.json configs[1] shape.  (1) batch invariance: a sequence inside a batch of 64 gives the
     same logits as alone; (2) the oracle agrees on one sequence; (3) causality: perturbing frames >= 300
