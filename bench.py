@@ -87,45 +87,82 @@ def measured_peaks():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled from a thread every ~2 ms (a timed
+    region of a few hundred ms is over before an `nvidia-smi -lms` child process has even started); falls back to
+    `nvidia-smi` polling when the NVML binding is missing."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mx, self.reasons = index, [], 0, set()
+        self._stop = threading.Event()
+        self._thread = None
+        self.source = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except (ValueError, IndexError):
+                pass
+        return self.index
+
+    def _nvml_loop(self, nv, h):
+        masks = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
+                 else nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap",
+                                         getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4))}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for n, m in masks.items():
+                    if r & m:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _smi_loop(self):
+        fields = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self._physical_index()), f"--query-gpu={fields}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                p = [x.strip() for x in out.strip().split(",")]
+                self.sm.append(int(p[0]))
+                self.mx = max(self.mx, int(p[1]))
+                for n, v in zip(self.NAMES, p[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                time.sleep(0.05)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self._thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.source = "nvidia-smi"
+            self._thread = threading.Thread(target=self._smi_loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            p = [x.strip() for x in r.split(",")]
-            if len(p) < 6:
-                continue
-            try:
-                sm.append(int(p[0]))
-                mx = max(mx, int(p[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, p[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=6)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx or None,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -350,8 +387,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -20,6 +20,7 @@
 #include "../../include/fseend_b200.h"
 #include "attn.cuh"
 #include "elementwise.cuh"
+#include "embloss.cuh"
 #include "ffn.cuh"
 #include "gemm.cuh"
 #include "tmap.h"
@@ -1245,6 +1246,30 @@ int fseend_op_prep_input(const float* x_packed, const int* cu_seqlens_dev, int B
     if (Kpad % 2 || Kpad < Din) throw std::invalid_argument("Kpad must be even and >= Din");
     launch_prep_input(x_packed, cu_seqlens_dev, B, Tmax, Din, Kpad, scale, shift, static_cast<__half*>(out_f16),
                       static_cast<cudaStream_t>(stream));
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+size_t fseend_op_embloss_workspace_bytes(int B, int T) {
+  return sizeof(float) * static_cast<size_t>(embloss_num_partials(B, T));
+}
+
+int fseend_op_embloss(const float* emb_f32, const float* labels, const int* seq_len_dev, int B, int T, int S,
+                      double divisor, float* workspace, float* loss_dev, void* stream) {
+  return guarded([&] {
+    if (B < 1 || T < 1 || S < 1 || S > 16) throw std::invalid_argument("embloss: need B,T >= 1 and 1 <= S <= 16");
+    if (!(divisor > 0.0)) throw std::invalid_argument("embloss: divisor must be positive");
+    if ((reinterpret_cast<uintptr_t>(emb_f32) & 15) != 0) throw std::invalid_argument("embloss: emb must be 16-byte aligned");
+    if (!fseend_device_ok()) throw std::invalid_argument("sm_100 device required");
+    EmbLossParams p{};
+    p.emb = emb_f32;
+    p.labels = labels;
+    p.seq_len = seq_len_dev;
+    p.partials = workspace;
+    p.B = B;
+    p.T = T;
+    p.S = S;
+    launch_embloss(p, divisor, loss_dev, static_cast<cudaStream_t>(stream));
     CUDA_CHECK(cudaGetLastError());
   });
 }

@@ -46,7 +46,7 @@ EXPORTS = [
     "fseend_ls_stream_enc_step", "fseend_ls_stream_dec_step", "fseend_op_gemm",
     "fseend_op_gemm_ex", "fseend_op_retention", "fseend_op_dwconv_bn_swish", "fseend_op_ret_step",
     "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
-    "fseend_op_prep_input",
+    "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes",
 ]
 
 
@@ -135,6 +135,10 @@ def lib() -> C.CDLL:
     L.fseend_op_head.argtypes = [vp, vp, ip, ip, vp, vp, vp, vp]
     L.fseend_op_prep_input.restype = ip
     L.fseend_op_prep_input.argtypes = [vp, vp, ip, ip, ip, ip, vp, vp, vp, vp]
+    L.fseend_op_embloss_workspace_bytes.restype = C.c_size_t
+    L.fseend_op_embloss_workspace_bytes.argtypes = [ip, ip]
+    L.fseend_op_embloss.restype = ip
+    L.fseend_op_embloss.argtypes = [vp, vp, vp, ip, ip, ip, C.c_double, vp, vp, vp]
     _lib = L
     return L
 
@@ -496,3 +500,24 @@ def op_ret_step(qkvg: torch.Tensor, state: torch.Tensor, t: int) -> torch.Tensor
     out = torch.empty(qkvg.shape[0], 256, device=qkvg.device, dtype=torch.float16)
     _check(lib().fseend_op_ret_step(_ptr(qkvg), _ptr(state), qkvg.shape[0], t, _ptr(out), _stream()))
     return out
+
+
+def op_embloss(emb: torch.Tensor, labels: torch.Tensor, seq_len: Optional[torch.Tensor] = None,
+               divisor: Optional[float] = None) -> torch.Tensor:
+    """Embedding-consistency loss.  emb: fp32 [B, T, 256]; labels: fp32 [B, T, S] zero padded; seq_len: int32 [B] on the
+    device (LS-EEND masking) or None (FS-EEND: every padded row counts).  Returns a 0-dim fp32 CUDA tensor."""
+    _require_cuda(emb, labels, seq_len)
+    if emb.dtype != torch.float32 or labels.dtype != torch.float32:
+        raise FseendError("emb and labels must be float32")
+    B, T, D = emb.shape
+    if D != 256 or tuple(labels.shape[:2]) != (B, T):
+        raise FseendError("emb must be [B, T, 256] and labels [B, T, S]")
+    S = labels.shape[2]
+    if divisor is None:
+        divisor = float(B) * T * T
+    L = lib()
+    ws = torch.empty(int(L.fseend_op_embloss_workspace_bytes(B, T)) // 4, device=emb.device, dtype=torch.float32)
+    loss = torch.empty((), device=emb.device, dtype=torch.float32)
+    _check(L.fseend_op_embloss(_ptr(emb), _ptr(labels), _ptr(seq_len), B, T, S, float(divisor), _ptr(ws), _ptr(loss),
+                               _stream()))
+    return loss

@@ -207,5 +207,27 @@ class OnlineConformerRetentionDADiarization(nn.Module):
         return [o[:l] for o, l in zip(y, lens)]
 
     def forward(self, src, tgt, ilens):
-        raise NotImplementedError("LS-EEND training forward (masked emb-consistency loss, reference :74-122) and "
-                                  "backward are SURVEY §8(f) N1/N2 — round 2")
+        """Reference :74-122 (eval-mode arithmetic): logits, the length-masked embedding-consistency loss (one kernel,
+        csrc/embloss.cu), embeddings, attractors[1:n_spk].  Gradients are not produced (backward = SURVEY §8(f) N1)."""
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "fseend_b200 round 1 implements the forward hot path only; training backward is SURVEY §8(f) N1")
+        from fseend_b200.native import op_embloss
+        with torch.no_grad():
+            n_speakers = [t.shape[1] for t in tgt]
+            max_nspks = max(n_speakers)
+            x, lens = self._pack(src, ilens)
+            y, emb, att = self.native().forward(x, lens, max_nspks, want_emb=True, want_att=True)
+            seq_len = max(lens)
+            dev = y.device
+            labels = torch.zeros(len(tgt), seq_len, max_nspks, device=dev, dtype=torch.float32)
+            for b, t in enumerate(tgt):
+                n = min(t.shape[0], seq_len)
+                labels[b, :n, :t.shape[1]] = t[:n].to(device=dev, dtype=torch.float32)
+            lens_dev = torch.tensor(lens, device=dev, dtype=torch.int32)
+            emb_consis_loss = op_embloss(emb[:, :seq_len].contiguous(), labels, seq_len=lens_dev,
+                                         divisor=float(sum(l * l for l in lens)))
+            output = [o[:l, :n] for o, l, n in zip(y, lens, n_speakers)]
+            emb = [e[:l] for e, l in zip(emb, lens)]
+            attractors = [a[:l, 1:n] for a, l, n in zip(att, lens, n_speakers)]
+        return output, emb_consis_loss, emb, attractors

@@ -14,7 +14,17 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from fseend_b200.native import op_embloss
 from ..modules.merge_tfm_encoder import TransformerEncoder, TransformerEncoderFusionLayer
+
+
+def _pad_labels(tgt, lens, T, max_nspks, dev):
+    """list of (T_i, n_spk_i) activity matrices -> zero-padded fp32 [B, T, max_nspks] on the device."""
+    labels = torch.zeros(len(tgt), T, max_nspks, device=dev, dtype=torch.float32)
+    for b, t in enumerate(tgt):
+        n = min(t.shape[0], T)
+        labels[b, :n, :t.shape[1]] = t[:n].to(device=dev, dtype=torch.float32)
+    return labels
 
 
 class PositionalEncoding(nn.Module):
@@ -154,17 +164,10 @@ class OnlineTransformerDADiarization(nn.Module):
             max_nspks = max(n_speakers)
             x, lens = self._pack(src, ilens)
             y, emb, att = self.native().forward(x, lens, max_nspks, want_emb=True, want_att=True)
-            # embedding-consistency loss (reference :46-57); padded rows t >= ilen are part of the mean, as there
-            dev = y.device
-            attn_map = emb.matmul(emb.transpose(-1, -2))
-            attn_norm = torch.norm(emb, dim=-1, keepdim=True)
-            attn_map = attn_map / (attn_norm.matmul(attn_norm.transpose(-1, -2)) + 1e-6)
-            tgt_pad = [F.pad(t.to(dev, torch.float32), (0, max_nspks - t.shape[1]), "constant", 0) for t in tgt]
-            tgt_pad = nn.utils.rnn.pad_sequence(tgt_pad, padding_value=0, batch_first=True)
-            label_map = tgt_pad.matmul(tgt_pad.transpose(-1, -2))
-            tgt_norm = torch.norm(tgt_pad, dim=-1, keepdim=True)
-            label_map = label_map / (tgt_norm.matmul(tgt_norm.transpose(-1, -2)) + 1e-6)
-            emb_consis_loss = F.mse_loss(attn_map, label_map)
+            # embedding-consistency loss (reference :46-57) in one kernel (csrc/embloss.cu); padded rows t >= ilen
+            # are part of the mean, as in the reference
+            labels = _pad_labels(tgt, lens, y.shape[1], max_nspks, y.device)
+            emb_consis_loss = op_embloss(emb, labels)
             output = [o[:l, :n] for o, l, n in zip(y, lens, n_speakers)]
             emb = [e[:l] for e, l in zip(emb, lens)]
             attractors = [a[:l, 1:n] for a, l, n in zip(att, lens, n_speakers)]

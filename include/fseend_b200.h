@@ -176,6 +176,15 @@ int fseend_op_head(const void* emb_f16, const void* att_f16, int n_frames, int S
 int fseend_op_prep_input(const float* x_packed, const int* cu_seqlens_dev, int B, int Tmax, int Din, int Kpad,
                          const float* scale, const float* shift, void* out_f16, void* stream);
 
+/* Embedding-consistency loss (reference FS model file :46-57; LS model file :92-113):
+ *   *loss_dev = sum_{b,i,j} ( <e_i,e_j>/(|e_i||e_j| + 1e-6) - <l_i,l_j>/(|l_i||l_j| + 1e-6) )^2 / divisor
+ * emb fp32 [B][T][256] (16-byte aligned), labels fp32 [B][T][S] zero padded, S <= 16.  seq_len_dev NULL: all T rows of
+ * every sequence count (FS-EEND: divisor = B*T*T); otherwise only rows/cols < seq_len[b] (LS-EEND: divisor = sum len^2).
+ * workspace: fseend_op_embloss_workspace_bytes(B, T) bytes of device memory.  Deterministic (fixed-order reduction). */
+size_t fseend_op_embloss_workspace_bytes(int B, int T);
+int fseend_op_embloss(const float* emb_f32, const float* labels, const int* seq_len_dev, int B, int T, int S,
+                      double divisor, float* workspace, float* loss_dev, void* stream);
+
 /* GEMM with the LS-EEND epilogues: mode 0 (+bias, act 0 none / 1 ReLU / 2 swish), 4 (GLU: N/2 outputs), 1 (LayerNorm),
  * 5 (y = residual + alpha*(acc+bias); out = ln_g ? LN(y) : y); out2 (optional) = LayerNorm(out; ln2_g, ln2_b). */
 int fseend_op_gemm_ex(const void* a_f16, int rows_per_seq, int n_seq, int K, const void* w_f16, int N, int mode, int act,

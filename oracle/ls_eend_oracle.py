@@ -238,6 +238,36 @@ def test(sd: SD, src: Sequence[Tensor], ilens: Sequence[int], max_nspks: int, cf
     return [o[:l] for o, l in zip(y, ilens)], [e[:l] for e, l in zip(emb, ilens)], [a[:l] for a, l in zip(att, ilens)]
 
 
+def masked_emb_consistency_loss(emb: Tensor, tgt: Sequence[Tensor], ilens: Sequence[int], max_nspks: int) -> Tensor:
+    """Length-masked emb-consistency loss.  LS:model:92-113: rows >= ilen are zeroed, the squared error is summed over
+    (B, T, T) and divided by sum(ilen^2).  emb: (B, T, D) with T = max(ilens)."""
+    mask = pad_sequence([torch.ones(l) for l in ilens], 0.0).unsqueeze(-1)
+    e = emb * mask
+    amap = e @ e.transpose(-1, -2)
+    n = torch.linalg.vector_norm(e, dim=-1, keepdim=True)
+    amap = amap / (n @ n.transpose(-1, -2) + 1e-6)
+    tp = pad_sequence([torch.nn.functional.pad(t, (0, max_nspks - t.shape[1])) for t in tgt], 0.0)
+    lmap = tp @ tp.transpose(-1, -2)
+    tn = torch.linalg.vector_norm(tp, dim=-1, keepdim=True)
+    lmap = lmap / (tn @ tn.transpose(-1, -2) + 1e-6)
+    return ((amap - lmap) ** 2).sum() / float(sum(l * l for l in ilens))
+
+
+def forward(sd: SD, src: Sequence[Tensor], tgt: Sequence[Tensor], ilens: Sequence[int], cfg: Cfg, quant=_ident):
+    """OnlineConformerRetentionDADiarization.forward (eval-mode arithmetic).  LS:model:74-122."""
+    n_speakers = [t.shape[1] for t in tgt]
+    S = max(n_speakers)
+    emb = encoder(sd, src, cfg, quant)
+    T = max(ilens)
+    emb = conv_l2(sd, emb, ilens, cfg, quant)
+    att = decoder(sd, emb, S, cfg, quant)
+    att = att / torch.linalg.vector_norm(att, dim=-1, keepdim=True)
+    loss = masked_emb_consistency_loss(emb[:, :T], tgt, ilens, S)
+    y = (quant(emb)[:, :, None, :] * quant(att)).sum(dim=-1)
+    out = [o[:l, :n] for o, l, n in zip(y, ilens, n_speakers)]
+    return out, loss, [e[:l] for e, l in zip(emb, ilens)], [a[:l, 1:n] for a, l, n in zip(att, ilens, n_speakers)]
+
+
 # ----------------------------------------------------------------------------- one-step path (a13)
 
 class StreamState:

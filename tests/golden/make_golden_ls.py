@@ -75,8 +75,29 @@ def streaming_predict(model, feat, max_nspks):
     return torch.cat(preds, dim=1).squeeze(0)
 
 
+def forward_loss_golden():
+    """Training-signature forward (eval arithmetic) with labels: the length-masked emb-consistency loss (LS:model:92-113)."""
+    sd = O.random_state_dict(seed=0, trained_like=True)
+    ref = build_ref(sd)
+    lens = [700, 433]
+    S = 6
+    src, lens = FO.synthetic_features(len(lens), max(lens), lens=lens)
+    g = torch.Generator().manual_seed(123)
+    tgt = [(torch.rand(l, n, generator=g) > 0.6).float() for l, n in zip(lens, (S, S - 2))]
+    with torch.no_grad():
+        out, loss, emb, att = ref(src, tgt, lens)
+    rec = {"emb_consis_loss": np.array(loss.item(), dtype=np.float64), "fwd_logits_0": out[0].numpy(),
+           "fwd_logits_1": out[1].numpy(), "att_shape_1": np.array(att[1].shape)}
+    np.savez_compressed(os.path.join(HERE, "ls_forward_loss_S6.npz"), **rec)
+    print("ls_forward_loss_S6: loss", loss.item(), [tuple(o.shape) for o in out], tuple(att[1].shape))
+
+
 def main():
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "forward_loss":
+        forward_loss_golden()
+        return
+    forward_loss_golden()
     for name, (wseed, trained, lens, S) in CASES.items():
         sd = O.random_state_dict(seed=wseed, trained_like=trained)
         ref = build_ref(sd)

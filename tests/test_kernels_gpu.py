@@ -234,3 +234,44 @@ def test_fused_ffn_per_sequence_zero_rows(N, cluster):
         assert (out[i, :l].float() - ref[i, :l]).abs().max().item() < 6e-3
         if l < T:
             assert out[i, l:].abs().max().item() == 0
+
+
+def _embloss_ref(emb, labels, lens=None):
+    """torch fp64 restatement of FS:model:46-57 (lens None) / LS:model:92-113 (masked) on the given tensors."""
+    e, l = emb.double(), labels.double()
+    if lens is not None:
+        mask = (torch.arange(e.shape[1], device=e.device)[None, :] < torch.as_tensor(lens, device=e.device)[:, None])
+        e, l = e * mask[..., None], l * mask[..., None]
+    en, ln = e.norm(dim=-1, keepdim=True), l.norm(dim=-1, keepdim=True)
+    amap = e @ e.transpose(-1, -2) / (en @ en.transpose(-1, -2) + 1e-6)
+    lmap = l @ l.transpose(-1, -2) / (ln @ ln.transpose(-1, -2) + 1e-6)
+    sq = ((amap - lmap) ** 2).sum()
+    return (sq / (sum(int(x) ** 2 for x in lens) if lens is not None else e.shape[0] * e.shape[1] ** 2)).item()
+
+
+@pytest.mark.parametrize("B,T,S,masked", [(3, 500, 6, False), (2, 128, 4, False), (4, 333, 10, True), (1, 1, 1, False),
+                                          (2, 700, 16, True), (5, 129, 5, True)])
+def test_embloss_kernel(N, B, T, S, masked):
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + T)
+    emb = torch.nn.functional.normalize(torch.randn(B, T, 256, generator=g), dim=-1).to(DEV)
+    labels = (torch.rand(B, T, S, generator=g) > 0.6).float().to(DEV)
+    lens = None
+    if masked:
+        lens = [T] + [max(1, T - 37 * (b + 1)) for b in range(B - 1)]
+        for b, l in enumerate(lens):
+            labels[b, l:] = 0
+    seq = torch.tensor(lens, device=DEV, dtype=torch.int32) if masked else None
+    div = float(sum(l * l for l in lens)) if masked else None
+    loss = N.op_embloss(emb, labels, seq_len=seq, divisor=div)
+    loss2 = N.op_embloss(emb, labels, seq_len=seq, divisor=div)
+    ref = _embloss_ref(emb, labels, lens)
+    assert loss.item() == loss2.item()                      # fixed-order reduction: bit-reproducible
+    assert abs(loss.item() - ref) < 2e-4 * max(1.0, abs(ref)), (loss.item(), ref)
+
+
+def test_embloss_rejects_bad_arguments(N):
+    emb = torch.zeros(1, 8, 256, device=DEV)
+    with pytest.raises(N.FseendError):
+        N.op_embloss(emb, torch.zeros(1, 8, 17, device=DEV))          # S > 16
+    with pytest.raises(N.FseendError):
+        N.op_embloss(emb.half(), torch.zeros(1, 8, 4, device=DEV))    # fp32 only

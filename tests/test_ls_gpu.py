@@ -169,6 +169,21 @@ def test_ls_logits_vs_reference_golden(name):
     assert med < 1e-3 and p95 < 1e-2 and mx < 0.15
 
 
+def test_ls_forward_api_and_masked_emb_consistency_loss():
+    """forward(src, tgt, ilens) vs the real reference's forward (golden): logits sliced [:ilen, :n_spk], attractors
+    [:ilen, 1:n_spk], length-masked loss (LS:model:92-113) from the tcgen05 loss kernel."""
+    from test_oracle_ls import ls_forward_loss_case
+    sd, src, tgt, lens, g = ls_forward_loss_case()
+    m = make_ls_model(sd)
+    out, loss, emb, att = m([s.cuda() for s in src], tgt, lens)
+    print(f"LS masked emb-consistency loss: {loss.item():.6f} vs reference {float(g['emb_consis_loss']):.6f}")
+    assert abs(loss.item() - float(g["emb_consis_loss"])) < 1e-3
+    for i in range(2):
+        err = np.abs(out[i].cpu().numpy() - g[f"fwd_logits_{i}"])
+        assert out[i].shape == g[f"fwd_logits_{i}"].shape and np.median(err) < 1e-3 and err.max() < 0.15
+    assert tuple(att[1].shape) == tuple(g["att_shape_1"]) and emb[1].shape == (lens[1], 256)
+
+
 def test_ls_one_step_fused_stream_vs_reference_golden():
     """Fused native frame loop vs the reference's streaming_predict output (golden, one-step/recurrent path)."""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ls_stream_T48_S4.npz"))

@@ -41,6 +41,26 @@ def test_ls_oracle_matches_reference(name):
         assert np.abs(emb[i].numpy()[::stride] - g[f"emb_{i}"]).max() < 3e-4
 
 
+def ls_forward_loss_case():
+    """Inputs of tests/golden/make_golden_ls.py::forward_loss_golden."""
+    sd = O.random_state_dict(seed=0, trained_like=True)
+    lens, S = [700, 433], 6
+    src, lens = FO.synthetic_features(len(lens), max(lens), lens=lens)
+    gen = torch.Generator().manual_seed(123)
+    tgt = [(torch.rand(l, n, generator=gen) > 0.6).float() for l, n in zip(lens, (S, S - 2))]
+    return sd, src, tgt, lens, np.load(os.path.join(GOLD, "ls_forward_loss_S6.npz"))
+
+
+def test_ls_oracle_forward_and_masked_emb_loss():
+    sd, src, tgt, lens, g = ls_forward_loss_case()
+    with torch.no_grad():
+        out, loss, emb, att = O.forward(sd, src, tgt, lens, O.Cfg())
+    assert abs(loss.item() - float(g["emb_consis_loss"])) < 1e-5
+    for i in range(2):
+        assert np.abs(out[i].numpy() - g[f"fwd_logits_{i}"]).max() < 3e-4
+    assert tuple(att[1].shape) == tuple(g["att_shape_1"])
+
+
 def test_ls_oracle_one_step_matches_reference_stream():
     g = np.load(os.path.join(GOLD, "ls_stream_T48_S4.npz"))
     sd = O.random_state_dict(seed=3)
