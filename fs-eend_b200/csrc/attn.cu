@@ -18,6 +18,20 @@
 //               straight from its row-major [kv][64] tile).  S (TMEM) and P (smem) are double-buffered.
 // Causality skips KV tiles above the diagonal; warps whose rows see nothing of a diagonal half-tile skip its
 // exponentials.
+//
+// Softmax details: (1) LAZY rescaling — a row's reference maximum only moves when the running maximum outgrows it by
+// more than 2^kTau, so P = 2^(s - m_ref) <= 2^kTau and the O rescale round trip through TMEM almost never happens after
+// the first tile; (2) exp2 on packed fp16 pairs (one MUFU op per two probabilities; P is consumed as fp16 anyway);
+// (3) the item epilogue (O / l -> fp16 -> global) is deferred until after the softmax of the next item's first tile
+// and goes through a warp-private transpose in the free P buffer, so no CTA-level barrier and no wait for the last PV.
+//
+// Measured alternatives (B200, B=64 T=500 S=6, profiles/r01_attention_study.md): eight softmax warps with two threads
+// per row exchanging maxima through spare TMEM columns; three small strictly serial CTAs per SM with P kept in TMEM as
+// the A operand of the PV MMA.  Both were correct and no faster: with five 64-wide KV tiles per item the kernel is
+// bound by the per-tile handshake chain (MMA commit -> mbarrier -> TMEM read -> ... -> arrive -> MMA issue), not by
+// TMEM bandwidth, MUFU, DRAM or the tensor pipe.
+#include <stdlib.h>
+
 #include "attn.cuh"
 #include "ptx.cuh"
 
@@ -38,6 +52,7 @@ constexpr int kOffP = kOffKV + kStages * kStageBytes;      // 2 buffers
 constexpr int kOffBar = kOffP + 2 * kPBytes;               // mbarriers + tmem slot at the tail of dynamic smem
 constexpr int kSmemBytes = kOffBar + 256;                  // 112 KB + 256 B
 constexpr uint32_t kTmemCols = 256;        // S0 [0,64), S1 [64,128), O [128,192)
+constexpr float kTau = 8.f;                // lazy-rescale threshold (log2 units): P <= 2^8
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -45,18 +60,13 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
+// two exponentials per MUFU op: packed fp16 in, packed fp16 out
+__device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ __half2 as_half2(uint32_t x) { return *reinterpret_cast<__half2*>(&x); }
 
 // One work item: coordinates and KV extent.
 struct Item {
@@ -65,10 +75,26 @@ struct Item {
 __device__ __forceinline__ Item decode_item(const AttnParams& p, int id) {
   Item it;
   if (p.mode == ATTN_CAUSAL) {
+    // Item order (L2 locality): the query tiles of one (sequence, head) are adjacent, heaviest first, so the CTAs that
+    // share its K/V run at the same time and K/V come from DRAM once (ordering all heavy tiles of the whole batch first
+    // re-read K/V from DRAM for every query tile: 663 MB instead of 370 MB per launch at B=64, S=6).  The lightest tile
+    // (qt = 0) of every (sequence, head) goes to a second phase at the end, so the tail of the persistent loop is made
+    // of the cheapest items.  The grid size is chosen coprime to n_qt - 1 (launch_attn), so the static round-robin
+    // hands every CTA an even mix of tile weights.
     const int n_qt = (p.T + kTile - 1) / kTile;
-    const int per_qt = p.H * p.B * p.S;
-    const int qt = n_qt - 1 - id / per_qt;          // heaviest (latest) query tiles first
-    const int rest = id % per_qt;
+    const int n_sh = p.H * p.B * p.S;
+    const int heavy = n_qt - 1;
+    int qt, rest;
+    if (p.order == 0) {
+      qt = n_qt - 1 - id / n_sh;
+      rest = id % n_sh;
+    } else if (id < n_sh * heavy) {
+      rest = id / heavy;
+      qt = n_qt - 1 - (id - rest * heavy);
+    } else {
+      rest = id - n_sh * heavy;
+      qt = 0;
+    }
     it.h = rest % p.H;
     const int z = rest / p.H;
     it.b = z / p.S;
@@ -91,7 +117,7 @@ __device__ __forceinline__ Item decode_item(const AttnParams& p, int id) {
 
 __global__ void __launch_bounds__(192, 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-            const __grid_constant__ CUtensorMap tmO, const AttnParams p, const int n_items) {
+            __half* __restrict__ out, const AttnParams p, const int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars + 0;      // [2]
@@ -127,7 +153,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     fence_barrier_init();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    tma_prefetch_desc(&tmO);
   }
   if (warp == 5) tmem_alloc(tmem_base_slot, kTmemCols);
   tc_fence_before();
@@ -224,11 +249,65 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const int r = tid;                 // query row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     const float sl = p.scale * 1.4426950408889634f;
+    // Item epilogue, DEFERRED by one KV tile: the O rows of item n are read out, normalised and stored after the
+    // softmax of the first tile of item n+1 (whose S = Q K^T was issued right behind the last PV of item n), so the
+    // softmax warps never sit waiting for the last PV to retire.
+    bool pend = false;
+    float pend_inv = 0.f;
+    __half* pend_base = nullptr;    // output address of row 0 of the pending tile (this head's 64 columns)
+    int pend_rows = 0;              // rows of the tile that exist (sequence end / block-diagonal tile_rows)
+    const size_t out_stride = p.mode == ATTN_CAUSAL ? static_cast<size_t>(p.S) * 256 : 256;   // between tile rows
+    auto flush_pending = [&](uint32_t pend_gl) {   // pend_gl: last KV tile (running count) of the pending item
+      mbar_wait(&pv_done[pend_gl & 1], (pend_gl >> 1) & 1, 23);   // every MMA of the pending item has completed
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tmem_O + lane_base, o0);
+      tmem_ld32(tmem_O + lane_base + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free);          // O has been read out: the next item's first PV may overwrite it
+      // Normalise, pack to fp16 and transpose through this warp's own 4 KB slice of the free P buffer (the one the
+      // pending item's last PV read; its next writer is this same warp, for the following KV tile, so __syncwarp
+      // ordering is enough): thread r parks its 128-byte row, then 8 lanes store one row, so every global store
+      // instruction covers four whole 128-byte lines (a 16-byte store per thread at a row stride costs 32 LSU passes).
+      uint8_t* stg = smem + kOffP + (pend_gl & 1) * kPBytes;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_half2(__uint_as_float(o0[q * 8 + 0]) * pend_inv, __uint_as_float(o0[q * 8 + 1]) * pend_inv);
+        u.y = pack_half2(__uint_as_float(o0[q * 8 + 2]) * pend_inv, __uint_as_float(o0[q * 8 + 3]) * pend_inv);
+        u.z = pack_half2(__uint_as_float(o0[q * 8 + 4]) * pend_inv, __uint_as_float(o0[q * 8 + 5]) * pend_inv);
+        u.w = pack_half2(__uint_as_float(o0[q * 8 + 6]) * pend_inv, __uint_as_float(o0[q * 8 + 7]) * pend_inv);
+        *reinterpret_cast<uint4*>(stg + sw128_offset(r, q)) = u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_half2(__uint_as_float(o1[q * 8 + 0]) * pend_inv, __uint_as_float(o1[q * 8 + 1]) * pend_inv);
+        u.y = pack_half2(__uint_as_float(o1[q * 8 + 2]) * pend_inv, __uint_as_float(o1[q * 8 + 3]) * pend_inv);
+        u.z = pack_half2(__uint_as_float(o1[q * 8 + 4]) * pend_inv, __uint_as_float(o1[q * 8 + 5]) * pend_inv);
+        u.w = pack_half2(__uint_as_float(o1[q * 8 + 6]) * pend_inv, __uint_as_float(o1[q * 8 + 7]) * pend_inv);
+        *reinterpret_cast<uint4*>(stg + sw128_offset(r, 4 + q)) = u;
+      }
+      __syncwarp();
+      {
+        const int lane = tid & 31, sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = warp * 32 + i * 4 + sub;           // row of the tile handled by this lane in pass i
+          const uint4 u = *reinterpret_cast<const uint4*>(stg + sw128_offset(rr, ch));
+          if (rr < pend_rows) *reinterpret_cast<uint4*>(pend_base + static_cast<size_t>(rr) * out_stride + ch * 8) = u;
+        }
+      }
+      __syncwarp();
+      pend = false;
+    };
     uint32_t g = 0, n = 0;
     for (int id = blockIdx.x; id < n_items; id += gridDim.x, ++n) {
       const Item it = decode_item(p, id);
       const int q0 = it.q0;
-      float m_run = -INFINITY, l_run = 0.f;
+      // reference maximum in scaled log2 units (lazy: moves only when outgrown by more than kTau) and row sum
+      float m_ref = -INFINITY, l_run = 0.f;
 
       for (int j = 0; j < it.n_kv; ++j) {
         const uint32_t gj = g + j;
@@ -257,7 +336,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
         mbar_wait(&s_full[pb], (gj >> 1) & 1, 20);
         tc_fence_after();
-        float m_new = m_run, alpha = 1.f, psum = 0.f;
+        float alpha = 1.f, psum = 0.f;
         if (gj >= 2) mbar_wait(&pv_done[pb], ((gj - 2) >> 1) & 1, 21);   // PV(g-2) has consumed this P buffer
         // Per 32-column half of the tile, warp-uniformly: 0 = every row of the warp sees all 32 columns,
         // 1 = mixed (per-element compare), 2 = no row sees any of them (skip the exponentials, P = 0).
@@ -295,10 +374,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
               }
             }
           }
-          m_new = fmax3(m_run, fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-          const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * sl;
-          alpha = (m_new == m_run) ? 1.f : ex2(m_run * sl - m_scaled);   // m_run = -inf -> 0
-          float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+          const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl;   // -inf stays -inf
+          if (m_tile > m_ref + kTau) {           // also the first visible tile of the row (m_ref = -inf)
+            alpha = ex2(m_ref - m_tile);         // m_ref = -inf -> 0
+            m_ref = m_tile;
+          }
+          const float m_sub = (m_ref == -INFINITY) ? 0.f : m_ref;
+          // P = 2^(s*sl - m_ref) as packed fp16 pairs; the row sum is taken from the rounded values the PV MMA
+          // consumes: groups of 8 in fp16, then fp32
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             if (hmode[hh] == 2) {
@@ -312,24 +395,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                   const int c = hh * 32 + q * 8 + 2 * t;
-                  const float p0 = ex2(fmaf(__uint_as_float(sv[c]), sl, -m_scaled));
-                  const float p1 = ex2(fmaf(__uint_as_float(sv[c + 1]), sl, -m_scaled));
-                  ps4[t] += p0 + p1;           // four independent partial sums
-                  e[t] = pack_half2(p0, p1);
+                  e[t] = ex2_h2(pack_half2(fmaf(__uint_as_float(sv[c]), sl, -m_sub),
+                                           fmaf(__uint_as_float(sv[c + 1]), sl, -m_sub)));
                 }
                 *reinterpret_cast<uint4*>(ptile + sw128_offset(r, hh * 4 + q)) = make_uint4(e[0], e[1], e[2], e[3]);
+                const float2 f = __half22float2(__hadd2(__hadd2(as_half2(e[0]), as_half2(e[1])),
+                                                        __hadd2(as_half2(e[2]), as_half2(e[3]))));
+                psum += f.x + f.y;
               }
             }
           }
-          psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
         } else {
           // no row of this warp sees any column of this tile (upper part of a diagonal tile): P = 0
 #pragma unroll
           for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(ptile + sw128_offset(r, q)) = make_uint4(0, 0, 0, 0);
         }
         if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-          // some row of this warp raised its running max: rescale the warp's 32 O rows in TMEM.  O must be quiescent:
-          // PV(j-1) (the last MMA issued so far that writes O) has to be complete.
+          // rare: some row of this warp moved its reference maximum: rescale the warp's 32 O rows in TMEM.  O must be
+          // quiescent: PV(j-1) (the last MMA issued so far that writes O) has to be complete.
           mbar_wait(&pv_done[(gj - 1) & 1], ((gj - 1) >> 1) & 1, 22);
           tc_fence_after();
 #pragma unroll
@@ -344,46 +427,25 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           tmem_st_wait();
         }
         l_run = l_run * alpha + psum;
-        m_run = m_new;
 
         fence_proxy_async_smem();   // P visible to the tensor-core (async) proxy
         tc_fence_before();          // order our tcgen05.ld/st before the MMAs issued after the barrier
         mbar_arrive(&p_ready[pb]);
+        if (j == 0 && pend) flush_pending(g - 1);   // previous item's epilogue, overlapped with this item's QK^T / PV
       }
       g += it.n_kv;
-      // ---- item epilogue: O / l -> fp16 -> staging -> TMA store.  Every MMA of this item has completed once the
-      // last PV has, so both P buffers are free; the next item's first P goes to buffer g & 1, so stage in the other.
-      const uint32_t gl = g - 1;
-      mbar_wait(&pv_done[gl & 1], (gl >> 1) & 1, 23);
-      tc_fence_after();
-      uint8_t* stage = smem + kOffP + ((g & 1) ^ 1) * kPBytes;
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tmem_O + lane_base + c * 32, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_half2(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
-          u.y = pack_half2(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
-          u.z = pack_half2(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
-          u.w = pack_half2(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(stage + sw128_offset(r, c * 4 + q)) = u;
-        }
+      // ---- remember this item's epilogue (see flush_pending)
+      pend = true;
+      pend_inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      if (p.mode == ATTN_CAUSAL) {
+        pend_base = out + ((static_cast<size_t>(it.b) * p.T + q0) * p.S + it.s) * 256 + it.h * 64;
+        pend_rows = min(kTile, p.T - q0);
+      } else {
+        pend_base = out + static_cast<size_t>(q0) * 256 + it.h * 64;
+        pend_rows = min(p.tile_rows, p.T - q0);
       }
-      tc_fence_before();
-      mbar_arrive(o_free);          // O has been read out: the next item's first PV may overwrite it
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (tid == 0) {
-        tma_store_4d(&tmO, stage, it.h * 64, it.s, q0, it.b);   // box rows = 128 (causal) or tile_rows (block-diagonal)
-        tma_store_commit();
-        tma_store_wait_read0();     // the staging buffer may be rewritten (as P) two tiles from now
-      }
-      named_bar_sync(1, 128);
     }
+    if (pend) flush_pending(g - 1);
   }
 
   tc_fence_before();
@@ -393,7 +455,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
 }  // namespace
 
-void launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const CUtensorMap& tmO, const AttnParams& p,
+void launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmKV, __half* out, const AttnParams& p,
                  cudaStream_t stream) {
   static int num_sms = 0;
   if (!num_sms) {
@@ -405,8 +467,15 @@ void launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const CUtensor
   int n_items;
   if (p.mode == ATTN_CAUSAL) n_items = ((p.T + kTile - 1) / kTile) * p.H * p.B * p.S;
   else n_items = ((p.T + p.tile_rows - 1) / p.tile_rows) * p.H;
-  const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
-  attn_kernel<<<grid, 192, kSmemBytes, stream>>>(tmQ, tmKV, tmO, p, n_items);
+  int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
+  AttnParams pp = p;
+  if (const char* e = getenv("FSEEND_ATTN_ORDER")) pp.order = atoi(e);
+  if (p.mode == ATTN_CAUSAL && pp.order == 1) {
+    const int heavy = (p.T + kTile - 1) / kTile - 1;
+    auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+    while (heavy > 1 && grid > 1 && gcd(grid, heavy) != 1) --grid;   // see decode_item
+  }
+  attn_kernel<<<grid, 192, kSmemBytes, stream>>>(tmQ, tmKV, out, pp, n_items);
 }
 
 }  // namespace fseend

@@ -6,6 +6,7 @@
 //    its own frame.  T = total rows, tile_rows = (128 / S) * S rows per CTA.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace fseend {
@@ -18,13 +19,14 @@ struct AttnParams {
   float scale;       // applied to q.k (hd^-0.5)
   int mode;          // AttnMode
   int tile_rows;     // block-diagonal: rows per CTA
+  int order = 0;     // causal item order: 0 = all heavy query tiles of the batch first (default: measured faster),
+                     // 1 = (sequence, head)-major (K/V read from DRAM once; FSEEND_ATTN_ORDER=1)
 };
 
 // causal:     tmQ 4-D (768, S, T, B) box (64,1,128,1), tmKV same tensor with box (64,1,64,1);
-//             tmO 4-D (256, S, T, B) box (64,1,128,1)
-// block-diag: tmQ 4-D (768, 1, rows, 1) box (64,1,128,1), tmKV box (64,1,64,1); tmO 4-D (256, 1, rows, 1) box
-//             (64,1,tile_rows,1)
-void launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const CUtensorMap& tmO, const AttnParams& p,
+//             out fp16 [B][T][S][256]
+// block-diag: tmQ 4-D (768, 1, rows, 1) box (64,1,128,1), tmKV box (64,1,64,1); out fp16 [rows][256]
+void launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmKV, __half* out, const AttnParams& p,
                  cudaStream_t stream);
 
 }  // namespace fseend

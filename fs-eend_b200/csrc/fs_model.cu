@@ -503,7 +503,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     }
     {
       AttnParams a{B, 1, T, c.n_heads, c.has_mask ? c.mask_delay : (1 << 28), 1.f / sqrtf(64.f), ATTN_CAUSAL, 128};
-      L.run("enc.attn_causal", [&] { launch_attn(m->tm_qkv_e_attn, m->tm_qkv_e_kv, m->tm_ao_e_attn, a, st); });
+      L.run("enc.attn_causal", [&] { launch_attn(m->tm_qkv_e_attn, m->tm_qkv_e_kv, static_cast<__half*>(m->ao_e.p), a, st); });
     }
     {
       GemmParams p = flat_params(Me, D, D, EPI_LN);
@@ -587,7 +587,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     }
     {
       AttnParams a{B, S, T, c.n_heads, c.mask_delay, 1.f / sqrtf(64.f), ATTN_CAUSAL, 128};
-      L.run("dec.attn_causal", [&] { launch_attn(m->tm_qkv_d_attn, m->tm_qkv_d_kv, m->tm_ao_d_attn, a, st); });
+      L.run("dec.attn_causal", [&] { launch_attn(m->tm_qkv_d_attn, m->tm_qkv_d_kv, static_cast<__half*>(m->ao_d.p), a, st); });
     }
     {
       GemmParams p = flat_params(Md, D, D, EPI_LN);
@@ -605,7 +605,7 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
     }
     if (m->spk_mode == 1) {
       AttnParams a{1, S, static_cast<int>(Md), c.n_heads, 0, 1.f / sqrtf(64.f), ATTN_BLOCKDIAG, (128 / S) * S};
-      L.run("dec.spk_attn", [&] { launch_attn(m->tm_qkv_d_spk, m->tm_qkv_d_spk_kv, m->tm_ao_d_spk, a, st); });
+      L.run("dec.spk_attn", [&] { launch_attn(m->tm_qkv_d_spk, m->tm_qkv_d_spk_kv, static_cast<__half*>(m->ao_d.p), a, st); });
     } else {
       L.run("dec.spk_attn", [&] {
         launch_spk_attn(static_cast<const __half*>(m->qkv_d.p), static_cast<__half*>(m->ao_d.p),
@@ -841,7 +841,7 @@ int stream_step(fseend_fs_stream* s, const float* x_t, float* logits, cudaStream
     }
     {
       AttnParams a{1, S, static_cast<int>(Rd), c.n_heads, 0, scale, ATTN_BLOCKDIAG, (128 / S) * S};
-      launch_attn(s->tm_qkv_spk, s->tm_qkv_spk_kv, s->tm_ao_spk, a, st);
+      launch_attn(s->tm_qkv_spk, s->tm_qkv_spk_kv, static_cast<__half*>(s->ao.p), a, st);
     }
     {
       GemmParams p = flat_params(Rd, D, D, EPI_LN);
@@ -900,11 +900,12 @@ int fseend_version(void) { return FSEEND_VERSION; }
 const char* fseend_last_error(void) { return g_last_error.c_str(); }
 
 int fseend_device_ok(void) {
-  int dev = 0;
-  cudaDeviceProp prop;
+  // cudaDeviceGetAttribute is a cheap query (cudaGetDeviceProperties costs milliseconds per call, which dominated the
+  // single-kernel entry points)
+  int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
-  return prop.major == 10 ? 1 : 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
 }
 
 int fseend_fs_create(const fseend_fs_config* cfg, int n_tensors, const char* const* names, const float* const* data,
@@ -1199,7 +1200,7 @@ int fseend_op_causal_attn(const void* qkv_f16, int B, int T, int S, int H, int m
     CUtensorMap tkv = make_tmap_f16(qkv_f16, 4, dq, sq, bkv);
     CUtensorMap to = make_tmap_f16(out_f16, 4, d_o, so, box);
     AttnParams a{B, S, T, H, mask_delay, scale, ATTN_CAUSAL, 128};
-    launch_attn(tq, tkv, to, a, static_cast<cudaStream_t>(stream));
+    launch_attn(tq, tkv, static_cast<__half*>(out_f16), a, static_cast<cudaStream_t>(stream));
     CUDA_CHECK(cudaGetLastError());
   });
 }
@@ -1217,7 +1218,7 @@ int fseend_op_spk_attn_tc(const void* qkv_f16, int n_frames, int S, float scale,
     CUtensorMap tkv = make_tmap_f16(qkv_f16, 4, dq, sq, bkv);
     CUtensorMap to = make_tmap_f16(out_f16, 4, d_o, so, bo);
     AttnParams a{1, S, static_cast<int>(rows), 4, 0, scale, ATTN_BLOCKDIAG, (128 / S) * S};
-    launch_attn(tq, tkv, to, a, static_cast<cudaStream_t>(stream));
+    launch_attn(tq, tkv, static_cast<__half*>(out_f16), a, static_cast<cudaStream_t>(stream));
     CUDA_CHECK(cudaGetLastError());
   });
 }

@@ -37,6 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
         "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH,
     ] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd[1:1] = os.environ.get("FSEEND_NVCC_FLAGS", "").split()   # e.g. -DFSEEND_WAIT_LIMIT_SPINS=1000000 (debug)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
