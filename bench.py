@@ -51,6 +51,7 @@ def algorithmic_flops(name: str, Bn: int, Tn: int, Sn: int) -> float:
         "dec.gemm_out1_ln": 2.0 * Md * D * D,
         "dec.gemm_qkv2": 2.0 * Md * D * 3 * D,
         "dec.spk_attn": 4.0 * 64 * H * Sn * Sn * Me,
+        "dec.spk_fused": 2.0 * Md * D * 3 * D + 4.0 * 64 * H * Sn * Sn * Me,
         "dec.gemm_out2_ln": 2.0 * Md * D * D,
         "dec.gemm_ffn1": 2.0 * Md * D * FF,
         "dec.gemm_ffn2_ln": 2.0 * Md * D * FF,

@@ -23,6 +23,7 @@
 #include "embloss.cuh"
 #include "ffn.cuh"
 #include "gemm.cuh"
+#include "spkfuse.cuh"
 #include "tmap.h"
 
 namespace fseend {
@@ -142,7 +143,8 @@ struct fseend_fs_model {
   CUtensorMap tm_hconv_in, tm_hB_seq, tm_emb_out, tm_emb_in, tm_cvt_out;
   CUtensorMap tm_aX, tm_aY, tm_aZ, tm_qkv_d_out, tm_qkv_d_attn, tm_ao_d_attn, tm_qkv_d_spk, tm_ao_d_spk, tm_ao_d, tm_qkv_e_kv, tm_qkv_d_kv, tm_qkv_d_spk_kv, tm_f_d_out, tm_f_d_in;
 
-  int spk_mode = 1;  // 0: CUDA-core speaker attention, 1: tcgen05 block-diagonal attention
+  int spk_mode = 2;  // 0: CUDA-core speaker attention, 1: tcgen05 block-diagonal attention (both after a QKV GEMM),
+                     // 2: QKV projection + attention fused in one kernel (spkfuse.cu)
   int ffn_mode = 5;  // 0: two GEMM launches (hidden layer through HBM); fused: 1 = SS, 2 = SS + 2-CTA weight multicast,
                      // 3 = TS (hidden chunk stays in TMEM), 4 = TS + multicast, 5 = TS on a CTA pair (cta_group::2)
   bool profiling = false;
@@ -598,19 +600,25 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
       p.ln_eps = c.ln_eps;
       L.run("dec.gemm_out1_ln", [&] { p.tmB_half = &Dl.wo1.tm128; launch_gemm(m->tm_ao_d, Dl.wo1.tm, m->tm_aX, m->tm_aY, p, st); });
     }
-    {
-      GemmParams p = flat_params(Md, 3 * D, D, EPI_BIAS);
-      p.bias = Dl.bqkv2.f();
-      L.run("dec.gemm_qkv2", [&] { p.tmB_half = &Dl.wqkv2.tm128; launch_gemm(m->tm_aY, Dl.wqkv2.tm, none, m->tm_qkv_d_out, p, st); });
-    }
-    if (m->spk_mode == 1) {
-      AttnParams a{1, S, static_cast<int>(Md), c.n_heads, 0, 1.f / sqrtf(64.f), ATTN_BLOCKDIAG, (128 / S) * S};
-      L.run("dec.spk_attn", [&] { launch_attn(m->tm_qkv_d_spk, m->tm_qkv_d_spk_kv, static_cast<__half*>(m->ao_d.p), a, st); });
+    if (m->spk_mode == 2) {
+      SpkFuseParams sp{static_cast<int>(Md), S, (128 / S) * S, 1.f / sqrtf(64.f), Dl.bqkv2.f(),
+                       static_cast<__half*>(m->ao_d.p)};
+      L.run("dec.spk_fused", [&] { launch_spkfuse(m->tm_aY, Dl.wqkv2.tm64, sp, st); });
     } else {
-      L.run("dec.spk_attn", [&] {
-        launch_spk_attn(static_cast<const __half*>(m->qkv_d.p), static_cast<__half*>(m->ao_d.p),
-                        static_cast<int>(Me), S, 1.f / sqrtf(64.f), st);
-      });
+      {
+        GemmParams p = flat_params(Md, 3 * D, D, EPI_BIAS);
+        p.bias = Dl.bqkv2.f();
+        L.run("dec.gemm_qkv2", [&] { p.tmB_half = &Dl.wqkv2.tm128; launch_gemm(m->tm_aY, Dl.wqkv2.tm, none, m->tm_qkv_d_out, p, st); });
+      }
+      if (m->spk_mode == 1) {
+        AttnParams a{1, S, static_cast<int>(Md), c.n_heads, 0, 1.f / sqrtf(64.f), ATTN_BLOCKDIAG, (128 / S) * S};
+        L.run("dec.spk_attn", [&] { launch_attn(m->tm_qkv_d_spk, m->tm_qkv_d_spk_kv, static_cast<__half*>(m->ao_d.p), a, st); });
+      } else {
+        L.run("dec.spk_attn", [&] {
+          launch_spk_attn(static_cast<const __half*>(m->qkv_d.p), static_cast<__half*>(m->ao_d.p),
+                          static_cast<int>(Me), S, 1.f / sqrtf(64.f), st);
+        });
+      }
     }
     {
       GemmParams p = flat_params(Md, D, D, EPI_LN);
@@ -835,13 +843,8 @@ int stream_step(fseend_fs_stream* s, const float* x_t, float* logits, cudaStream
       launch_gemm(s->tm_ao_d, Dl.wo1.tm, s->tm_a0, s->tm_a1, p, st);
     }
     {
-      GemmParams p = flat_params(Rd, 3 * D, D, EPI_BIAS);
-      p.bias = Dl.bqkv2.f();
-      launch_gemm(s->tm_a1, Dl.wqkv2.tm, none, s->tm_qkv_d, p, st);
-    }
-    {
-      AttnParams a{1, S, static_cast<int>(Rd), c.n_heads, 0, scale, ATTN_BLOCKDIAG, (128 / S) * S};
-      launch_attn(s->tm_qkv_spk, s->tm_qkv_spk_kv, static_cast<__half*>(s->ao.p), a, st);
+      SpkFuseParams sp{static_cast<int>(Rd), S, (128 / S) * S, scale, Dl.bqkv2.f(), static_cast<__half*>(s->ao.p)};
+      launch_spkfuse(s->tm_a1, Dl.wqkv2.tm64, sp, st);
     }
     {
       GemmParams p = flat_params(Rd, D, D, EPI_LN);
@@ -1141,7 +1144,7 @@ int fseend_fs_set_option(fseend_fs_model* m, const char* key, int value) {
     m->ffn_mode = value;
     return FSEEND_OK;
   }
-  if (strcmp(key, "spk") == 0 && value >= 0 && value <= 1) {
+  if (strcmp(key, "spk") == 0 && value >= 0 && value <= 2) {
     m->spk_mode = value;
     return FSEEND_OK;
   }
@@ -1247,6 +1250,22 @@ int fseend_op_prep_input(const float* x_packed, const int* cu_seqlens_dev, int B
     if (Kpad % 2 || Kpad < Din) throw std::invalid_argument("Kpad must be even and >= Din");
     launch_prep_input(x_packed, cu_seqlens_dev, B, Tmax, Din, Kpad, scale, shift, static_cast<__half*>(out_f16),
                       static_cast<cudaStream_t>(stream));
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int fseend_op_spk_qkv_attn(const void* x_f16, const void* w_f16, const float* bias, int n_frames, int S, float scale,
+                           void* out_f16, void* stream) {
+  return guarded([&] {
+    if (S < 1 || S > 16) throw std::invalid_argument("S must be in [1,16]");
+    if (!fseend_device_ok()) throw std::invalid_argument("sm_100 device required");
+    const uint64_t rows = 1ull * n_frames * S;
+    CUtensorMap tmX = make_tmap_rows3d(x_f16, 256, 256, rows, 1, 128);
+    uint64_t dw[2] = {256, 768}, sw[1] = {256};
+    uint32_t bw[2] = {64, 64};
+    CUtensorMap tmW = make_tmap_f16(w_f16, 2, dw, sw, bw);
+    SpkFuseParams sp{static_cast<int>(rows), S, (128 / S) * S, scale, bias, static_cast<__half*>(out_f16)};
+    launch_spkfuse(tmX, tmW, sp, static_cast<cudaStream_t>(stream));
     CUDA_CHECK(cudaGetLastError());
   });
 }

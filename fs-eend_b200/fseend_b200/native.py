@@ -46,7 +46,7 @@ EXPORTS = [
     "fseend_ls_stream_enc_step", "fseend_ls_stream_dec_step", "fseend_op_gemm",
     "fseend_op_gemm_ex", "fseend_op_retention", "fseend_op_dwconv_bn_swish", "fseend_op_ret_step",
     "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
-    "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes",
+    "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes", "fseend_op_spk_qkv_attn",
 ]
 
 
@@ -135,6 +135,8 @@ def lib() -> C.CDLL:
     L.fseend_op_head.argtypes = [vp, vp, ip, ip, vp, vp, vp, vp]
     L.fseend_op_prep_input.restype = ip
     L.fseend_op_prep_input.argtypes = [vp, vp, ip, ip, ip, ip, vp, vp, vp, vp]
+    L.fseend_op_spk_qkv_attn.restype = ip
+    L.fseend_op_spk_qkv_attn.argtypes = [vp, vp, vp, ip, ip, fp, vp, vp]
     L.fseend_op_embloss_workspace_bytes.restype = C.c_size_t
     L.fseend_op_embloss_workspace_bytes.argtypes = [ip, ip]
     L.fseend_op_embloss.restype = ip
@@ -420,6 +422,15 @@ def op_spk_attn(qkv: torch.Tensor, scale: float = 0.125, tensor_core: bool = Fal
     out = torch.empty(F, S, 256, device=qkv.device, dtype=torch.float16)
     fn = lib().fseend_op_spk_attn_tc if tensor_core else lib().fseend_op_spk_attn
     _check(fn(_ptr(qkv), F, S, scale, _ptr(out), _stream()))
+    return out
+
+
+def op_spk_qkv_attn(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, scale: float = 0.125) -> torch.Tensor:
+    """x: fp16 [frames, S, 256]; w: fp16 [768, 256] (in_proj_weight); bias: fp32 [768] -> fp16 [frames, S, 256]."""
+    _require_cuda(x, w, bias)
+    F, S, _ = x.shape
+    out = torch.empty(F, S, 256, device=x.device, dtype=torch.float16)
+    _check(lib().fseend_op_spk_qkv_attn(_ptr(x), _ptr(w), _ptr(bias), F, S, scale, _ptr(out), _stream()))
     return out
 
 

@@ -80,7 +80,8 @@ int fseend_fs_forward_host(fseend_fs_model* m, const float* x_packed_host, const
  * 1 = hidden chunk via smem, 2 = 1 + 2-CTA clusters sharing weight tiles by TMA multicast, 3 = hidden chunk kept in
  * TMEM (A operand from TMEM), 4 = 3 + multicast, 5 = 3 on a CTA pair (tcgen05 cta_group::2, M = 256 across two SMs,
  * each SM holding half of every weight tile; default: measured fastest).
- * "spk": 0 = CUDA-core speaker attention, 1 = tcgen05 block-diagonal attention (default).
+ * "spk": speaker-axis attention: 0 = QKV GEMM + CUDA-core attention, 1 = QKV GEMM + tcgen05 block-diagonal attention,
+ * 2 = projection and attention fused in one kernel (default).
  * "host_chunks": fseend_fs_forward_host splits the batch into this many chunks of whole sequences and overlaps the
  * host->device copy of chunk i+1 with the kernels of chunk i (0 = automatic, 1 = no overlap, <= 8). */
 int fseend_fs_set_option(fseend_fs_model* m, const char* key, int value);
@@ -171,6 +172,11 @@ int fseend_op_causal_attn(const void* qkv_f16, int B, int T, int S, int H, int m
  * tcgen05 block-diagonal variant (the one the model uses). */
 int fseend_op_spk_attn(const void* qkv_f16, int n_frames, int S, float scale, void* out_f16, void* stream);
 int fseend_op_spk_attn_tc(const void* qkv_f16, int n_frames, int S, float scale, void* out_f16, void* stream);
+/* The model's speaker-axis attention: QKV projection (in_proj weight fp16 [768][256], bias fp32 [768]) fused with the
+ * attention over the S slots of each frame; x fp16 [n_frames][S][256] -> out fp16 [n_frames][S][256] (heads concatenated,
+ * before the out-projection).  Reference: _sa_block2 of TransformerEncoderFusionLayer (merge_tfm_encoder.py:366-372). */
+int fseend_op_spk_qkv_attn(const void* x_f16, const void* w_f16, const float* bias, int n_frames, int S, float scale,
+                           void* out_f16, void* stream);
 int fseend_op_head(const void* emb_f16, const void* att_f16, int n_frames, int S, float* logits, float* emb_f32,
                    float* att_f32, void* stream);
 int fseend_op_prep_input(const float* x_packed, const int* cu_seqlens_dev, int B, int Tmax, int Din, int Kpad,

@@ -275,3 +275,19 @@ def test_embloss_rejects_bad_arguments(N):
         N.op_embloss(emb, torch.zeros(1, 8, 17, device=DEV))          # S > 16
     with pytest.raises(N.FseendError):
         N.op_embloss(emb.half(), torch.zeros(1, 8, 4, device=DEV))    # fp32 only
+
+
+@pytest.mark.parametrize("frames,S", [(500, 6), (37, 4), (300, 10), (9, 16), (130, 5), (1, 1)])
+def test_spk_qkv_attn_fused(N, frames, S):
+    """Fused QKV projection + speaker-axis attention vs torch fp32 on the same fp16 operands (q, k, v stay fp32 inside
+    the kernel, so it is compared against the unrounded projection)."""
+    x = rnd(frames, S, 256, seed=frames).half()
+    w = rnd(768, 256, scale=1 / 16, seed=2).half()
+    b = rnd(768, seed=3) * 0.2
+    out = N.op_spk_qkv_attn(x, w, b)
+    qkv = x.float() @ w.float().T + b
+    q, k, v = (t.reshape(frames, S, 4, 64).transpose(1, 2) for t in qkv.split(256, dim=-1))
+    att = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v
+    ref = att.transpose(1, 2).reshape(frames, S, 256)
+    assert out.shape == ref.shape
+    assert (out.float() - ref).abs().max().item() < 4e-3
