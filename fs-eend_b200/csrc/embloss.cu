@@ -87,7 +87,9 @@ embloss_kernel(const EmbLossParams p) {
   __shared__ __align__(16) float lab_j[kTile * kMaxS];
   __shared__ float warp_sum[4];
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the shared array: pointer arithmetic through uintptr_t would hide the shared
+  // address space from the compiler and turn every access below into a generic load / store
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* tile_i = smem;
   uint8_t* tile_j = smem + kOperandBytes;
 

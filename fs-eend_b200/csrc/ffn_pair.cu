@@ -50,7 +50,9 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float b1_smem[2][kChunk];
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the shared array: pointer arithmetic through uintptr_t would hide the shared
+  // address space from the compiler and turn every access below into a generic load / store
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;

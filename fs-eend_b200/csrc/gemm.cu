@@ -41,7 +41,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __shared__ __align__(16) gemm_detail::EpiParams epi_params;
   __shared__ __align__(16) float4 xchg[2 * 128];
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the shared array: pointer arithmetic through uintptr_t would hide the shared
+  // address space from the compiler and turn every access below into a generic load / store
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* staging = smem;  // aliases the pipeline stages; only touched after every MMA has completed
 
   const int tid = threadIdx.x;
