@@ -339,6 +339,51 @@ dwconv_bn_swish_kernel(const __half* __restrict__ u, const float* __restrict__ w
   }
 }
 
+// Batch variant for K = 16 (the published LS-EEND configuration): block = 32 frames x 256 channels of one sequence,
+// 256 threads; thread = (channel pair, 16-frame half).  The 31 input frames a thread needs are read once (coalesced
+// half2 loads: consecutive threads = consecutive channel pairs) and kept in registers with static indices; 16 x 16
+// FMAs per channel.  HBM-bound: read + write of the [n_seq][T][256] fp16 activations (the first version walked 64
+// frames serially per thread with a shifting register window: 189 us at B=16, T=2000 against ~10 us of traffic).
+__global__ void __launch_bounds__(256)
+dwconv16_bn_swish_kernel(const __half* __restrict__ u, const float* __restrict__ w, const float* __restrict__ sc,
+                         const float* __restrict__ sh, int T, __half* __restrict__ out) {
+  constexpr int K = 16, F = 16;                       // taps; output frames per thread
+  const int n = blockIdx.y, cp = threadIdx.x & 127, c = cp * 2;
+  const int t0 = blockIdx.x * 32 + (threadIdx.x >> 7) * F;
+  if (t0 >= T) return;
+  float w0[K], w1[K];
+#pragma unroll
+  for (int k = 0; k < K; k += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(w + c * K + k);
+    const float4 b = *reinterpret_cast<const float4*>(w + (c + 1) * K + k);
+    w0[k] = a.x; w0[k + 1] = a.y; w0[k + 2] = a.z; w0[k + 3] = a.w;
+    w1[k] = b.x; w1[k + 1] = b.y; w1[k + 2] = b.z; w1[k + 3] = b.w;
+  }
+  const float s0 = sc[c], s1 = sc[c + 1], h0 = sh[c], h1 = sh[c + 1];
+  const __half2* up = reinterpret_cast<const __half2*>(u + static_cast<size_t>(n) * T * 256 + c);
+  float2 x[F + K - 1];                                // x[i] = input frame t0 - (K-1) + i (zero before the start)
+#pragma unroll
+  for (int i = 0; i < F + K - 1; ++i) {
+    const int t = t0 - (K - 1) + i;
+    x[i] = (t >= 0 && t < T) ? __half22float2(up[static_cast<size_t>(t) * 128]) : make_float2(0.f, 0.f);
+  }
+  __half2* op = reinterpret_cast<__half2*>(out + static_cast<size_t>(n) * T * 256 + c);
+#pragma unroll
+  for (int j = 0; j < F; ++j) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      a0 = fmaf(w0[k], x[j + k].x, a0);
+      a1 = fmaf(w1[k], x[j + k].y, a1);
+    }
+    a0 = fmaf(a0, s0, h0);
+    a1 = fmaf(a1, s1, h1);
+    a0 = a0 / (1.f + __expf(-a0));
+    a1 = a1 / (1.f + __expf(-a1));
+    if (t0 + j < T) op[static_cast<size_t>(t0 + j) * 128] = __floats2half2_rn(a0, a1);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Recurrent retention step (LS:ret:126-144, decay = 1): per (sequence, head) the fp32 state kv (64 x 64) becomes
 // kv * sqrt(t)/sqrt(t+1) + k^T v / sqrt(t+1)  (t = frames already seen), out = q kv -> group norm (eps 1e-6) ->
@@ -416,6 +461,10 @@ void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int
 int launch_dwconv_bn_swish(const __half* u, const float* w, const float* sc, const float* sh, int n_seq, int T, int K,
                            __half* hist, __half* out, cudaStream_t stream) {
   if (K < 1 || K > 32) return -1;
+  if (K == 16 && hist == nullptr && T >= 32) {
+    dwconv16_bn_swish_kernel<<<dim3((T + 31) / 32, n_seq), 256, 0, stream>>>(u, w, sc, sh, T, out);
+    return 0;
+  }
   dwconv_bn_swish_kernel<<<dim3((T + 63) / 64, n_seq), 128, 0, stream>>>(u, w, sc, sh, T, K, hist, out);
   return 0;
 }
