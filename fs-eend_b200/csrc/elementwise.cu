@@ -385,6 +385,31 @@ dwconv16_bn_swish_kernel(const __half* __restrict__ u, const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// Post-processing of the speaker-activity posteriors (reference: train/utils/make_rttm.py:10-15 and metrics.py:58-60):
+// decision = pred > threshold, then a median filter of odd width `median` along time with zero padding
+// (scipy.signal.medfilt(pred, (median, 1))).  On 0/1 input the median is a majority vote: 1 iff more than median/2 of
+// the window are 1.  pred: [T][C] fp32, out: [T][C] uint8.  One thread per (t, c); the window re-reads hit L1/L2
+// (HBM-bound: T*C*4 bytes in, T*C bytes out).  Bit-exact with the reference: the only arithmetic is the comparison.
+__global__ void __launch_bounds__(256)
+decide_median_kernel(const float* __restrict__ pred, int T, int C, float threshold, int median,
+                     unsigned char* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(T) * C) return;
+  const int t = static_cast<int>(i / C), c = static_cast<int>(i % C);
+  if (median <= 1) {
+    out[i] = pred[i] > threshold ? 1 : 0;
+    return;
+  }
+  const int half = median / 2;
+  int ones = 0;
+  for (int k = -half; k <= half; ++k) {
+    const int tt = t + k;
+    if (tt >= 0 && tt < T) ones += pred[static_cast<long long>(tt) * C + c] > threshold ? 1 : 0;
+  }
+  out[i] = ones > half ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Recurrent retention step (LS:ret:126-144, decay = 1): per (sequence, head) the fp32 state kv (64 x 64) becomes
 // kv * sqrt(t)/sqrt(t+1) + k^T v / sqrt(t+1)  (t = frames already seen), out = q kv -> group norm (eps 1e-6) ->
 // * swish(g).  qkvg: [n_seq][1024] fp16 (q | k*hd^-.5 | v | g); state: [n_seq][4][64][64] fp32; out: [n_seq][256].
@@ -452,6 +477,13 @@ void launch_head(const __half* emb, const __half* att, int n_frames, int S, floa
 void launch_step_attn(const __half* qkv, __half* kcache, __half* vcache, int n_seq, int cap, int pos, float scale,
                       __half* out, cudaStream_t stream) {
   step_attn_kernel<<<dim3(n_seq, 4), 128, 0, stream>>>(qkv, kcache, vcache, cap, pos, scale, out);
+}
+
+void launch_decide_median(const float* pred, int T, int C, float threshold, int median, unsigned char* out,
+                          cudaStream_t stream) {
+  const long long n = static_cast<long long>(T) * C;
+  if (n == 0) return;
+  decide_median_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(pred, T, C, threshold, median, out);
 }
 
 void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int pos, cudaStream_t stream) {

@@ -30,6 +30,9 @@ void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int
 // u/out: [n_seq][T][256] fp16; hist: optional [n_seq][K-1][256] one-step cache (updated when T == 1).
 int launch_dwconv_bn_swish(const __half* u, const float* w, const float* sc, const float* sh, int n_seq, int T, int K,
                            __half* hist, __half* out, cudaStream_t stream);
+// decisions[t][c] = median filter (odd width, zero padded, along t) of (pred[t][c] > threshold); pred [T][C] fp32.
+void launch_decide_median(const float* pred, int T, int C, float threshold, int median, unsigned char* out,
+                          cudaStream_t stream);
 // Recurrent retention step for frame index t (0-based): state [n_seq][4][64][64] fp32 updated in place.
 void launch_ret_step(const __half* qkvg, float* state, int n_seq, int t, __half* out, cudaStream_t stream);
 

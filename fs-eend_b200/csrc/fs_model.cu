@@ -1270,6 +1270,16 @@ int fseend_op_spk_qkv_attn(const void* x_f16, const void* w_f16, const float* bi
   });
 }
 
+int fseend_op_decide_median(const float* pred, int T, int C, float threshold, int median, unsigned char* decisions,
+                            void* stream) {
+  return guarded([&] {
+    if (T < 0 || C < 1) throw std::invalid_argument("decide_median: need T >= 0, C >= 1");
+    if (median > 1 && (median % 2) == 0) throw std::invalid_argument("decide_median: the median width must be odd");
+    launch_decide_median(pred, T, C, threshold, median, decisions, static_cast<cudaStream_t>(stream));
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
 size_t fseend_op_embloss_workspace_bytes(int B, int T) {
   return sizeof(float) * static_cast<size_t>(embloss_num_partials(B, T));
 }

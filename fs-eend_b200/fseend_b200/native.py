@@ -46,7 +46,7 @@ EXPORTS = [
     "fseend_ls_stream_enc_step", "fseend_ls_stream_dec_step", "fseend_op_gemm",
     "fseend_op_gemm_ex", "fseend_op_retention", "fseend_op_dwconv_bn_swish", "fseend_op_ret_step",
     "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
-    "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes", "fseend_op_spk_qkv_attn",
+    "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes", "fseend_op_spk_qkv_attn", "fseend_op_decide_median",
 ]
 
 
@@ -137,6 +137,8 @@ def lib() -> C.CDLL:
     L.fseend_op_prep_input.argtypes = [vp, vp, ip, ip, ip, ip, vp, vp, vp, vp]
     L.fseend_op_spk_qkv_attn.restype = ip
     L.fseend_op_spk_qkv_attn.argtypes = [vp, vp, vp, ip, ip, fp, vp, vp]
+    L.fseend_op_decide_median.restype = ip
+    L.fseend_op_decide_median.argtypes = [vp, ip, ip, fp, ip, vp, vp]
     L.fseend_op_embloss_workspace_bytes.restype = C.c_size_t
     L.fseend_op_embloss_workspace_bytes.argtypes = [ip, ip]
     L.fseend_op_embloss.restype = ip
@@ -532,3 +534,14 @@ def op_embloss(emb: torch.Tensor, labels: torch.Tensor, seq_len: Optional[torch.
     _check(L.fseend_op_embloss(_ptr(emb), _ptr(labels), _ptr(seq_len), B, T, S, float(divisor), _ptr(ws), _ptr(loss),
                                _stream()))
     return loss
+
+
+def op_decide_median(pred: torch.Tensor, threshold: float = 0.5, median: int = 11) -> torch.Tensor:
+    """pred: CUDA fp32 [T, C] posteriors -> uint8 [T, C] decisions = medfilt(pred > threshold, (median, 1))."""
+    _require_cuda(pred)
+    if pred.dtype != torch.float32 or pred.dim() != 2:
+        raise FseendError("pred must be float32 [T, C]")
+    T, Cn = pred.shape
+    out = torch.empty(T, Cn, device=pred.device, dtype=torch.uint8)
+    _check(lib().fseend_op_decide_median(_ptr(pred), T, Cn, float(threshold), int(median), _ptr(out), _stream()))
+    return out

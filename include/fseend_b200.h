@@ -191,6 +191,13 @@ size_t fseend_op_embloss_workspace_bytes(int B, int T);
 int fseend_op_embloss(const float* emb_f32, const float* labels, const int* seq_len_dev, int B, int T, int S,
                       double divisor, float* workspace, float* loss_dev, void* stream);
 
+/* Post-processing in front of the RTTM writer (reference train/utils/make_rttm.py:10-15, metrics.py:58-60):
+ * decisions[t][c] = medfilt(pred > threshold, (median, 1))[t][c] — threshold, then a zero-padded median filter of odd
+ * width along time (median <= 1: no filter).  pred fp32 [T][C] (sigmoid posteriors), decisions uint8 [T][C], both on the
+ * device.  Bit-exact with the reference (the only arithmetic is the comparison). */
+int fseend_op_decide_median(const float* pred, int T, int C, float threshold, int median, unsigned char* decisions,
+                            void* stream);
+
 /* GEMM with the LS-EEND epilogues: mode 0 (+bias, act 0 none / 1 ReLU / 2 swish), 4 (GLU: N/2 outputs), 1 (LayerNorm),
  * 5 (y = residual + alpha*(acc+bias); out = ln_g ? LN(y) : y); out2 (optional) = LayerNorm(out; ln2_g, ln2_b). */
 int fseend_op_gemm_ex(const void* a_f16, int rows_per_seq, int n_seq, int K, const void* w_f16, int N, int mode, int act,
