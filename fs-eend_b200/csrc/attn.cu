@@ -455,8 +455,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
 }  // namespace
 
+// attn2.cu: two query tiles per CTA, 128-key KV tiles (causal mode)
+void launch_attn2(const CUtensorMap& tmQ, const CUtensorMap& tmKV, __half* out, const AttnParams& p,
+                  cudaStream_t stream);
+
 void launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmKV, __half* out, const AttnParams& p,
                  cudaStream_t stream) {
+  if (p.mode == ATTN_CAUSAL) {
+    const char* e = getenv("FSEEND_ATTN");     // 1 = one query tile per CTA (this file), default = attn2.cu
+    if (!(e && e[0] == '1')) {
+      launch_attn2(tmQ, tmKV, out, p, stream);
+      return;
+    }
+  }
   static int num_sms = 0;
   if (!num_sms) {
     cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -468,6 +479,7 @@ void launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmKV, __half* out, c
   if (p.mode == ATTN_CAUSAL) n_items = ((p.T + kTile - 1) / kTile) * p.H * p.B * p.S;
   else n_items = ((p.T + p.tile_rows - 1) / p.tile_rows) * p.H;
   int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
+  if (const char* e = getenv("FSEEND_ATTN_GRID")) grid = atoi(e) < grid ? atoi(e) : grid;   // experiments
   AttnParams pp = p;
   if (const char* e = getenv("FSEEND_ATTN_ORDER")) pp.order = atoi(e);
   if (p.mode == ATTN_CAUSAL && pp.order == 1) {
