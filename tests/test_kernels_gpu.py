@@ -140,12 +140,41 @@ def attn_ref(qkv, mask_delay, scale=0.125):
     return o.transpose(1, 2).reshape(B, S, T, 256).permute(0, 2, 1, 3)
 
 
-@pytest.mark.parametrize("B,T,S,md", [(2, 300, 1, 0), (1, 500, 3, 0), (2, 130, 2, 2), (1, 64, 1, 0), (1, 257, 1, 300)])
+ATTN_SHAPES = [(2, 300, 1, 0), (1, 500, 3, 0), (2, 130, 2, 2), (1, 64, 1, 0), (1, 257, 1, 300), (1, 700, 2, 0),
+               (3, 1000, 1, 5), (1, 129, 1, 0)]
+
+
+@pytest.mark.parametrize("B,T,S,md", ATTN_SHAPES)
 def test_causal_attention(N, B, T, S, md):
+    """Default kernel (attn2.cu: pairs of query tiles; odd and even tile counts, look-ahead, no-mask)."""
     qkv = rnd(B, T, S, 768, seed=25 + T).half()
     out = N.op_causal_attn(qkv, mask_delay=md)
     ref = attn_ref(qkv, md)
     assert (out.float() - ref).abs().max().item() < 4e-3
+
+
+@pytest.mark.parametrize("B,T,S,md", ATTN_SHAPES)
+def test_causal_attention_one_tile_kernel(N, monkeypatch, B, T, S, md):
+    """FSEEND_ATTN=1: the one-query-tile-per-item kernel (attn.cu)."""
+    monkeypatch.setenv("FSEEND_ATTN", "1")
+    qkv = rnd(B, T, S, 768, seed=25 + T).half()
+    out = N.op_causal_attn(qkv, mask_delay=md)
+    assert (out.float() - attn_ref(qkv, md)).abs().max().item() < 4e-3
+
+
+@pytest.mark.parametrize("variant", ["", "1"])
+def test_causal_attention_large_scores_exercise_lazy_rescale(N, monkeypatch, variant):
+    """Scores with a spread of ~±60 in log2 units: the running maximum outgrows the lazy reference by more than 2^8
+    many times per row, so the rare path (rescale O in TMEM, the row sum and the P chunks already written) runs."""
+    if variant:
+        monkeypatch.setenv("FSEEND_ATTN", variant)
+    qkv = rnd(2, 400, 2, 768, seed=77)
+    qkv[..., :512] *= 4.0                      # q and k: scores ~ N(0, 16^2) before the 1/8 scale
+    qkv = qkv.half()
+    out = N.op_causal_attn(qkv)
+    ref = attn_ref(qkv, 0)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < 2e-2
 
 
 @pytest.mark.parametrize("S", [4, 6, 10, 16])
