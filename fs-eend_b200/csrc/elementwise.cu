@@ -197,8 +197,9 @@ head_kernel(const __half* __restrict__ emb, const __half* __restrict__ att, int 
 // grid (n_seq, 4 heads), 128 threads: keys are strided over threads, partial softmax states merged through smem.
 __global__ void __launch_bounds__(128)
 step_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache, int cap,
-                 int pos, float scale, __half* __restrict__ out) {
+                 int pos_arg, const int* __restrict__ pos_dev, float scale, __half* __restrict__ out) {
   const int n = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int pos = pos_dev ? *pos_dev : pos_arg;   // device-resident frame counter: the launch is CUDA-graph replayable
   __shared__ float q_s[64];
   __shared__ float red_m[128], red_l[128];
   __shared__ float red_o[4][64];
@@ -269,8 +270,10 @@ step_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __
 }
 
 // rows [n_seq] of width 256 copied (or zero-filled when src == nullptr) into hist[n][pos]
-__global__ void hist_append_kernel(const __half* __restrict__ src, __half* __restrict__ hist, int cap, int pos) {
+__global__ void hist_append_kernel(const __half* __restrict__ src, __half* __restrict__ hist, int cap, int pos_arg,
+                                   const int* __restrict__ pos_dev) {
   const int n = blockIdx.x;
+  const int pos = pos_dev ? *pos_dev : pos_arg;
   const uint32_t* s = src ? reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(n) * 256) : nullptr;
   uint32_t* d = reinterpret_cast<uint32_t*>(hist + (static_cast<size_t>(n) * cap + pos) * 256);
   d[threadIdx.x] = s ? s[threadIdx.x] : 0u;
@@ -475,8 +478,21 @@ void launch_head(const __half* emb, const __half* att, int n_frames, int S, floa
 }
 
 void launch_step_attn(const __half* qkv, __half* kcache, __half* vcache, int n_seq, int cap, int pos, float scale,
-                      __half* out, cudaStream_t stream) {
-  step_attn_kernel<<<dim3(n_seq, 4), 128, 0, stream>>>(qkv, kcache, vcache, cap, pos, scale, out);
+                      __half* out, cudaStream_t stream, const int* pos_dev) {
+  step_attn_kernel<<<dim3(n_seq, 4), 128, 0, stream>>>(qkv, kcache, vcache, cap, pos, pos_dev, scale, out);
+}
+
+// counters[i] += inc[i] (i < 4): advances the device-resident frame counters at the end of a streaming step
+__global__ void advance_counters_kernel(int* counters, int4 inc) {
+  if (threadIdx.x == 0) {
+    counters[0] += inc.x;
+    counters[1] += inc.y;
+    counters[2] += inc.z;
+    counters[3] += inc.w;
+  }
+}
+void launch_advance_counters(int* counters, int i0, int i1, int i2, int i3, cudaStream_t stream) {
+  advance_counters_kernel<<<1, 32, 0, stream>>>(counters, make_int4(i0, i1, i2, i3));
 }
 
 void launch_decide_median(const float* pred, int T, int C, float threshold, int median, unsigned char* out,
@@ -486,8 +502,9 @@ void launch_decide_median(const float* pred, int T, int C, float threshold, int 
   decide_median_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(pred, T, C, threshold, median, out);
 }
 
-void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int pos, cudaStream_t stream) {
-  hist_append_kernel<<<n_seq, 128, 0, stream>>>(src, hist, cap, pos);
+void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int pos, cudaStream_t stream,
+                        const int* pos_dev) {
+  hist_append_kernel<<<n_seq, 128, 0, stream>>>(src, hist, cap, pos, pos_dev);
 }
 
 int launch_dwconv_bn_swish(const __half* u, const float* w, const float* sc, const float* sh, int n_seq, int T, int K,

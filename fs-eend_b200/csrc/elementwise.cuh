@@ -21,10 +21,14 @@ void launch_head(const __half* emb, const __half* att, int n_frames, int S, floa
 
 // Streaming step: append this frame's K/V (from qkv [n_seq][768]) to the caches [n_seq][cap][256] at `pos`, then
 // attend the single query row over keys 0..pos.  out: [n_seq][256] fp16.
+// pos_dev (optional): device int holding `pos` (then `pos` is ignored): the launch can be replayed from a CUDA graph.
 void launch_step_attn(const __half* qkv, __half* kcache, __half* vcache, int n_seq, int cap, int pos, float scale,
-                      __half* out, cudaStream_t stream);
+                      __half* out, cudaStream_t stream, const int* pos_dev = nullptr);
+// counters[i] += inc_i: device-resident frame counters of a streaming step
+void launch_advance_counters(int* counters, int i0, int i1, int i2, int i3, cudaStream_t stream);
 // hist[n][pos][:] = src[n][:] (or zeros when src == nullptr); hist: [n_seq][cap][256] fp16.
-void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int pos, cudaStream_t stream);
+void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int pos, cudaStream_t stream,
+                        const int* pos_dev = nullptr);
 
 // Conformer conv-module middle: causal depthwise conv (K <= 32 taps, weight [256][K]) -> BN(eval) affine -> swish.
 // u/out: [n_seq][T][256] fp16; hist: optional [n_seq][K-1][256] one-step cache (updated when T == 1).

@@ -177,6 +177,21 @@ struct fseend_fs_stream {
   DevBuf hist, x16, h0, h1, qkv, ao, a0, a1, a2, emb, cu;
   CUtensorMap tm_x16, tm_h0, tm_h1, tm_qkv_e, tm_ao_e, tm_hist, tm_emb_out, tm_emb_in, tm_cvt_out, tm_a0, tm_a1, tm_a2,
       tm_qkv_d, tm_ao_d, tm_qkv_spk, tm_qkv_spk_kv, tm_ao_spk;
+  // CUDA-graph replay of the steady-state step: every per-frame quantity a kernel needs (encoder frame index,
+  // decoder frame index) lives in `ctr` on the device and is advanced by the last node of the step, the frame is
+  // staged through x_in and the logits through y_out, so one instantiated graph serves every frame.
+  DevBuf ctr, x_in, y_out;                 // int[4]: {encoder frame index, decoder frame index, -, -}
+  cudaGraphExec_t graph_step = nullptr;    // frame in, logits out (steady state)
+  cudaGraphExec_t graph_flush = nullptr;   // flush step (zero conv input), logits out
+  int graph_cap = 0;                       // cache capacity the graphs were captured for
+  int eager_decodes = 0;                   // decoder steps run eagerly so far (first ones: lazy kernel attributes)
+  bool use_graph = true;
+  cudaStream_t cap_stream = nullptr;       // private capture stream
+  ~fseend_fs_stream() {
+    if (graph_step) cudaGraphExecDestroy(graph_step);
+    if (graph_flush) cudaGraphExecDestroy(graph_flush);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+  }
 };
 
 namespace fseend {
@@ -717,6 +732,11 @@ void stream_init(fseend_fs_stream* s, fseend_fs_model* m, int B, int S) {
     s->cu.alloc((B + 1) * sizeof(int));
     CUDA_CHECK(cudaMemcpy(s->cu.p, cu.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice));
   }
+  s->ctr.alloc(4 * sizeof(int));
+  CUDA_CHECK(cudaMemset(s->ctr.p, 0, 4 * sizeof(int)));
+  s->x_in.alloc(1ull * B * c.in_size * sizeof(float));
+  s->y_out.alloc(1ull * B * S * sizeof(float));
+  if (const char* e = getenv("FSEEND_STREAM_GRAPH")) s->use_graph = e[0] != '0';
   s->tm_x16 = rows_map(s->x16, m->Kin, B, 1);
   s->tm_h0 = rows_map(s->h0, D, B, 1);
   s->tm_h1 = rows_map(s->h1, D, B, 1);
@@ -747,20 +767,20 @@ void stream_init(fseend_fs_stream* s, fseend_fs_model* m, int B, int S) {
   stream_alloc(s, 1024);
 }
 
-// One frame.  x_t: device fp32 [B][in_size], or nullptr for a flush step (the reference's dummy_conv_input).
-// Returns 1 and writes logits [B][S] when the look-ahead conv has a full window, else 0.
-int stream_step(fseend_fs_stream* s, const float* x_t, float* logits, cudaStream_t st) {
+// The kernels of one frame.  Every per-frame index is read from the device counters (ctr[0] = encoder frame index,
+// ctr[1] = decoder frame index), so the same launch sequence is valid for every frame and can be replayed from a CUDA
+// graph.  x_in: staged frame (nullptr: flush step, zero conv input); decode: the look-ahead window is full.
+void stream_launch(fseend_fs_stream* s, const float* x_in, bool decode, float* y_out, cudaStream_t st) {
   fseend_fs_model* m = s->m;
   const fseend_fs_config& c = m->cfg;
   const int D = c.n_units, B = s->B, S = s->S;
-  if (B * S > 128) throw std::invalid_argument("streaming supports B * max_nspks <= 128");
-  if (s->t + 1 > s->cap) stream_alloc(s, s->cap * 2);
   const float scale = 1.f / sqrtf(64.f);
   CUtensorMap none = s->tm_h0;
-  const int pos = s->t;          // index of this frame in the encoder history
-  if (x_t) {
-    launch_prep_input(x_t, static_cast<const int*>(s->cu.p), B, 1, c.in_size, m->Kin, m->bn_scale.f(), m->bn_shift.f(),
-                      static_cast<__half*>(s->x16.p), st);
+  const int* enc_pos = static_cast<const int*>(s->ctr.p);
+  const int* dec_pos = enc_pos + 1;
+  if (x_in) {
+    launch_prep_input(x_in, static_cast<const int*>(s->cu.p), B, 1, c.in_size, m->Kin, m->bn_scale.f(),
+                      m->bn_shift.f(), static_cast<__half*>(s->x16.p), st);
     {
       GemmParams p = flat_params(B, D, m->Kin, EPI_LN);
       p.bias = m->b_in.f();
@@ -778,7 +798,8 @@ int stream_step(fseend_fs_stream* s, const float* x_t, float* logits, cudaStream
       }
       // the streaming encoder attends over every past frame (causal by construction, FS:stream_mod:28-35)
       launch_step_attn(static_cast<const __half*>(s->qkv.p), static_cast<__half*>(s->enc_k[l]->p),
-                       static_cast<__half*>(s->enc_v[l]->p), B, s->cap, pos, scale, static_cast<__half*>(s->ao.p), st);
+                       static_cast<__half*>(s->enc_v[l]->p), B, s->cap, 0, scale, static_cast<__half*>(s->ao.p), st,
+                       enc_pos);
       {
         GemmParams p = flat_params(B, D, D, EPI_LN);
         p.bias = E.bo.f();
@@ -791,18 +812,17 @@ int stream_step(fseend_fs_stream* s, const float* x_t, float* logits, cudaStream
       FfnParams fp = ffn_params(B, 1, c.enc_dim_feedforward, E.b1, E.b2, E.g2, E.be2, c.ln_eps, nullptr);
       launch_ffn(s->tm_h1, E.w1.tm128, E.w2.tm128, s->tm_h0, fp, 3, st);
     }
-    launch_hist_append(static_cast<const __half*>(s->h0.p), static_cast<__half*>(s->hist.p), B, s->cap, pos, st);
+    launch_hist_append(static_cast<const __half*>(s->h0.p), static_cast<__half*>(s->hist.p), B, s->cap, 0, st, enc_pos);
   } else {
-    launch_hist_append(nullptr, static_cast<__half*>(s->hist.p), B, s->cap, pos, st);
+    launch_hist_append(nullptr, static_cast<__half*>(s->hist.p), B, s->cap, 0, st, enc_pos);
   }
-  s->t += 1;
+  if (!decode) {
+    launch_advance_counters(static_cast<int*>(s->ctr.p), 1, 0, 0, 0, st);
+    return;
+  }
   const int K = c.conv_kernel, center = K / 2;
-  if (s->t < center + 1) {
-    CUDA_CHECK(cudaGetLastError());
-    return 0;
-  }
-  const int cidx = s->t - (center + 1);     // output frame index; its window is hist[cidx - center .. cidx + center]
   {
+    // output frame index cidx = ctr[1]; its window is hist[cidx - center .. cidx + center]
     GemmParams p{};
     p.rows_per_seq = 1;
     p.n_seq = B;
@@ -811,7 +831,8 @@ int stream_step(fseend_fs_stream* s, const float* x_t, float* logits, cudaStream
     p.k_blocks = D / 64;
     p.taps = K;
     p.tap_shift = -center;
-    p.a_row_offset = cidx;
+    p.a_row_offset = 0;
+    p.a_row_offset_dev = dec_pos;
     p.mode = EPI_L2;
     p.bias = m->b_conv.f();
     launch_gemm(s->tm_hist, m->w_conv.tm, none, s->tm_emb_out, p, st);
@@ -831,8 +852,8 @@ int stream_step(fseend_fs_stream* s, const float* x_t, float* logits, cudaStream
       launch_gemm(s->tm_a0, Dl.wqkv1.tm, none, s->tm_qkv_d, p, st);
     }
     launch_step_attn(static_cast<const __half*>(s->qkv.p), static_cast<__half*>(s->dec_k[l]->p),
-                     static_cast<__half*>(s->dec_v[l]->p), static_cast<int>(Rd), s->cap, cidx, scale,
-                     static_cast<__half*>(s->ao.p), st);
+                     static_cast<__half*>(s->dec_v[l]->p), static_cast<int>(Rd), s->cap, 0, scale,
+                     static_cast<__half*>(s->ao.p), st, dec_pos);
     {
       GemmParams p = flat_params(Rd, D, D, EPI_LN);
       p.bias = Dl.bo1.f();
@@ -859,9 +880,65 @@ int stream_step(fseend_fs_stream* s, const float* x_t, float* logits, cudaStream
                               nullptr);
     launch_ffn(s->tm_a2, Dl.w1.tm128, Dl.w2.tm128, s->tm_a0, fp, 3, st);
   }
-  launch_head(static_cast<const __half*>(s->emb.p), static_cast<const __half*>(s->a0.p), B, S, logits, nullptr, nullptr,
+  launch_head(static_cast<const __half*>(s->emb.p), static_cast<const __half*>(s->a0.p), B, S, y_out, nullptr, nullptr,
               st);
+  launch_advance_counters(static_cast<int*>(s->ctr.p), 1, 1, 0, 0, st);
+}
+
+// One frame.  x_t: device fp32 [B][in_size], or nullptr for a flush step (the reference's dummy_conv_input).
+// Returns 1 and writes logits [B][S] when the look-ahead conv has a full window, else 0.
+// Steady-state frames replay an instantiated CUDA graph (33 kernel nodes): the per-frame cost is one graph launch plus
+// two small device copies instead of 33 launches (FSEEND_STREAM_GRAPH=0 keeps the eager launches).
+int stream_step(fseend_fs_stream* s, const float* x_t, float* logits, cudaStream_t st) {
+  fseend_fs_model* m = s->m;
+  const fseend_fs_config& c = m->cfg;
+  const int B = s->B, S = s->S;
+  if (B * S > 128) throw std::invalid_argument("streaming supports B * max_nspks <= 128");
+  if (s->t + 1 > s->cap) stream_alloc(s, s->cap * 2);      // (synchronises; graphs are re-captured for the new buffers)
+  const int center = c.conv_kernel / 2;
+  const bool decode = s->t + 1 >= center + 1;
+  float* x_in = x_t ? static_cast<float*>(s->x_in.p) : nullptr;
+  if (x_t)
+    CUDA_CHECK(cudaMemcpyAsync(x_in, x_t, 1ull * B * c.in_size * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  float* y_out = static_cast<float*>(s->y_out.p);
+
+  if (s->graph_cap != s->cap) {      // caches were (re)allocated: captured pointers are stale
+    if (s->graph_step) cudaGraphExecDestroy(s->graph_step);
+    if (s->graph_flush) cudaGraphExecDestroy(s->graph_flush);
+    s->graph_step = s->graph_flush = nullptr;
+    s->graph_cap = s->cap;
+  }
+  cudaGraphExec_t* slot = x_t ? &s->graph_step : &s->graph_flush;
+  // the first decoder steps run eagerly (lazy per-kernel attribute setup must not happen inside a capture)
+  const bool graphable = s->use_graph && decode && s->eager_decodes >= 2;
+  if (graphable && *slot == nullptr) {
+    // captured on a private stream (the caller's may be the legacy default stream, which cannot capture); the
+    // instantiated graph is launched on the caller's stream
+    cudaGraph_t g = nullptr;
+    if (!s->cap_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      stream_launch(s, x_in, true, y_out, s->cap_stream);
+    } catch (...) {
+      cudaStreamEndCapture(s->cap_stream, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    CUDA_CHECK(cudaStreamEndCapture(s->cap_stream, &g));
+    cudaError_t e = cudaGraphInstantiate(slot, g, 0);
+    cudaGraphDestroy(g);
+    CUDA_CHECK(e);
+  }
+  if (graphable) {
+    CUDA_CHECK(cudaGraphLaunch(*slot, st));
+  } else {
+    stream_launch(s, x_in, decode, y_out, st);
+    if (decode) s->eager_decodes += 1;
+  }
+  s->t += 1;
   CUDA_CHECK(cudaGetLastError());
+  if (!decode) return 0;
+  CUDA_CHECK(cudaMemcpyAsync(logits, y_out, 1ull * B * S * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 1;
 }
 

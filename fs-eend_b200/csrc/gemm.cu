@@ -82,6 +82,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0) {
     {
       // ---------------- TMA producer
+      const int a_row_offset = p.a_row_offset + (p.a_row_offset_dev ? *p.a_row_offset_dev : 0);
       for (int it = 0; it < total_it; ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
@@ -92,7 +93,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint8_t* sb = sa + kABytes;
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-          tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, t0 + tap + p.tap_shift + p.a_row_offset, seq);
+          tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, t0 + tap + p.tap_shift + a_row_offset, seq);
           tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, tap * (p.n_tiles * BN) + n0);
         }
         __syncwarp();
@@ -196,11 +197,12 @@ static bool pair_pays(const GemmParams& p) {
 
 void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
                   const CUtensorMap& tmO2, const GemmParams& p, cudaStream_t stream) {
-  if (pair_pays(p)) {
+  const bool plain_only = p.a_row_offset_dev != nullptr;   // only gemm_kernel reads the device-resident row offset
+  if (!plain_only && pair_pays(p)) {
     launch_gemm_pair(tmA, tmR, tmO, p, stream);
     return;
   }
-  if (use_persist() && persist_pays(p)) {
+  if (!plain_only && use_persist() && persist_pays(p)) {
     launch_gemm_persist(tmA, tmB, tmR, tmO, tmO2, p, stream);
     return;
   }

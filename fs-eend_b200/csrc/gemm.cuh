@@ -42,6 +42,7 @@ struct GemmParams {
   const float* ln2_b;
   const float* pe_proj;  // [S][256]
   const int* seq_len;    // optional [n_seq]: EPI_LN rows t >= seq_len[b] are written as zeros
+  const int* a_row_offset_dev = nullptr;   // optional: device int added to a_row_offset (graph-replayable streaming conv)
   const CUtensorMap* tmB_half = nullptr;   // optional: the weight with box (64,128) — enables the weight-stationary
                                            // CTA-pair kernel (gemm_pair.cu) for EPI_BIAS / EPI_LN, one tap, K <= 256
 };
