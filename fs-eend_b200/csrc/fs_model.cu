@@ -23,6 +23,7 @@
 #include "embloss.cuh"
 #include "ffn.cuh"
 #include "gemm.cuh"
+#include "loss.cuh"
 #include "spkfuse.cuh"
 #include "tmap.h"
 
@@ -1343,6 +1344,30 @@ int fseend_op_spk_qkv_attn(const void* x_f16, const void* w_f16, const float* bi
     CUtensorMap tmW = make_tmap_f16(w_f16, 2, dw, sw, bw);
     SpkFuseParams sp{static_cast<int>(rows), S, (128 / S) * S, scale, bias, static_cast<__half*>(out_f16)};
     launch_spkfuse(tmX, tmW, sp, static_cast<cudaStream_t>(stream));
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int fseend_op_label_prepare(const float* labels, int B, int T, int n_spk, int* perm, float* labels_out, void* stream) {
+  return guarded([&] {
+    if (B < 1 || T < 1) throw std::invalid_argument("label_prepare: need B, T >= 1");
+    if (launch_label_prepare(labels, B, T, n_spk, perm, labels_out, static_cast<cudaStream_t>(stream)) != 0)
+      throw std::invalid_argument("label_prepare: n_spk must be in [1, 14]");
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+size_t fseend_op_bce_loss_workspace_bytes(int B, int T) {
+  return sizeof(float) * static_cast<size_t>(B) * static_cast<size_t>(bce_loss_chunks(T));
+}
+
+int fseend_op_bce_loss(const float* logits, int ld_logits, const float* target, int ld_target, int B, int T,
+                       const int* lens_dev, const int* n_cls_dev, int label_delay, float* workspace, float* loss_dev,
+                       void* stream) {
+  return guarded([&] {
+    if (B < 1 || T < 1 || label_delay < 0) throw std::invalid_argument("bce_loss: need B, T >= 1, label_delay >= 0");
+    launch_bce_loss(logits, ld_logits, target, ld_target, B, T, lens_dev, n_cls_dev, label_delay, workspace, loss_dev,
+                    static_cast<cudaStream_t>(stream));
     CUDA_CHECK(cudaGetLastError());
   });
 }

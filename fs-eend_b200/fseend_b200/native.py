@@ -46,7 +46,8 @@ EXPORTS = [
     "fseend_ls_stream_enc_step", "fseend_ls_stream_dec_step", "fseend_op_gemm",
     "fseend_op_gemm_ex", "fseend_op_retention", "fseend_op_dwconv_bn_swish", "fseend_op_ret_step",
     "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
-    "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes", "fseend_op_spk_qkv_attn", "fseend_op_decide_median",
+    "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes", "fseend_op_spk_qkv_attn", "fseend_op_decide_median", "fseend_op_label_prepare",
+    "fseend_op_bce_loss", "fseend_op_bce_loss_workspace_bytes",
 ]
 
 
@@ -137,6 +138,12 @@ def lib() -> C.CDLL:
     L.fseend_op_prep_input.argtypes = [vp, vp, ip, ip, ip, ip, vp, vp, vp, vp]
     L.fseend_op_spk_qkv_attn.restype = ip
     L.fseend_op_spk_qkv_attn.argtypes = [vp, vp, vp, ip, ip, fp, vp, vp]
+    L.fseend_op_label_prepare.restype = ip
+    L.fseend_op_label_prepare.argtypes = [vp, ip, ip, ip, vp, vp, vp]
+    L.fseend_op_bce_loss_workspace_bytes.restype = C.c_size_t
+    L.fseend_op_bce_loss_workspace_bytes.argtypes = [ip, ip]
+    L.fseend_op_bce_loss.restype = ip
+    L.fseend_op_bce_loss.argtypes = [vp, ip, vp, ip, ip, ip, vp, vp, ip, vp, vp, vp]
     L.fseend_op_decide_median.restype = ip
     L.fseend_op_decide_median.argtypes = [vp, ip, ip, fp, ip, vp, vp]
     L.fseend_op_embloss_workspace_bytes.restype = C.c_size_t
@@ -545,3 +552,34 @@ def op_decide_median(pred: torch.Tensor, threshold: float = 0.5, median: int = 1
     out = torch.empty(T, Cn, device=pred.device, dtype=torch.uint8)
     _check(lib().fseend_op_decide_median(_ptr(pred), T, Cn, float(threshold), int(median), _ptr(out), _stream()))
     return out
+
+
+def op_label_prepare(labels: torch.Tensor):
+    """labels: CUDA fp32 [B, T, n_spk] 0/1 -> (labels_out [B, T, n_spk + 2], perm int32 [B, n_spk])."""
+    _require_cuda(labels)
+    if labels.dtype != torch.float32 or labels.dim() != 3:
+        raise FseendError("labels must be float32 [B, T, n_spk]")
+    B, T, Cn = labels.shape
+    out = torch.empty(B, T, Cn + 2, device=labels.device, dtype=torch.float32)
+    perm = torch.empty(B, Cn, device=labels.device, dtype=torch.int32)
+    _check(lib().fseend_op_label_prepare(_ptr(labels), B, T, Cn, _ptr(perm), _ptr(out), _stream()))
+    return out, perm
+
+
+def op_bce_loss(logits: torch.Tensor, target: torch.Tensor, lens: torch.Tensor, n_cls: torch.Tensor,
+                label_delay: int = 0) -> torch.Tensor:
+    """logits [B, T, Cy], target [B, T, Ct] CUDA fp32 (padded); lens, n_cls int32 [B] on the device."""
+    _require_cuda(logits, target, lens, n_cls)
+    if logits.dtype != torch.float32 or target.dtype != torch.float32:
+        raise FseendError("logits and target must be float32")
+    if lens.dtype != torch.int32 or n_cls.dtype != torch.int32:
+        raise FseendError("lens and n_cls must be int32")
+    B, T, Cy = logits.shape
+    if tuple(target.shape[:2]) != (B, T):
+        raise FseendError("target must be [B, T, C]")
+    L = lib()
+    ws = torch.empty(max(1, int(L.fseend_op_bce_loss_workspace_bytes(B, T)) // 4), device=logits.device, dtype=torch.float32)
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    _check(L.fseend_op_bce_loss(_ptr(logits), Cy, _ptr(target), target.shape[2], B, T, _ptr(lens), _ptr(n_cls),
+                                int(label_delay), _ptr(ws), _ptr(loss), _stream()))
+    return loss

@@ -191,6 +191,20 @@ size_t fseend_op_embloss_workspace_bytes(int B, int T);
 int fseend_op_embloss(const float* emb_f32, const float* labels, const int* seq_len_dev, int B, int T, int S,
                       double divisor, float* workspace, float* loss_dev, void* stream);
 
+/* Training / validation step label pipeline (reference train/oln_tfm_enc_dec.py:51-76): speaker columns of the padded
+ * 0/1 activity labels [B][T][n_spk] re-ordered by first appearance (stable for ties; never-active speakers last), a
+ * silence column in front (1 - max) and a "no speaker" column of zeros behind: labels_out [B][T][n_spk + 2];
+ * perm [B][n_spk] = source column of speaker k.  n_spk <= 14.  All pointers device pointers. */
+int fseend_op_label_prepare(const float* labels, int B, int T, int n_spk, int* perm, float* labels_out, void* stream);
+/* standard_loss (reference train/utils/loss.py:119-125): sum_b [ sum_{t=delay}^{len_b-1} sum_{c<n_cls_b}
+ * BCEWithLogits(logits[b][t][c], target[b][t-delay][c]) / n_cls_b ] / (sum_b len_b - delay * B).
+ * logits [B][T][ld_logits], target [B][T][ld_target] fp32, lens / n_cls device int [B];
+ * workspace: fseend_op_bce_loss_workspace_bytes(B, T).  Deterministic (fixed-order reduction). */
+size_t fseend_op_bce_loss_workspace_bytes(int B, int T);
+int fseend_op_bce_loss(const float* logits, int ld_logits, const float* target, int ld_target, int B, int T,
+                       const int* lens_dev, const int* n_cls_dev, int label_delay, float* workspace, float* loss_dev,
+                       void* stream);
+
 /* Post-processing in front of the RTTM writer (reference train/utils/make_rttm.py:10-15, metrics.py:58-60):
  * decisions[t][c] = medfilt(pred > threshold, (median, 1))[t][c] — threshold, then a zero-padded median filter of odd
  * width along time (median <= 1: no filter).  pred fp32 [T][C] (sigmoid posteriors), decisions uint8 [T][C], both on the
