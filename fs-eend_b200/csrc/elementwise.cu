@@ -417,8 +417,10 @@ decide_median_kernel(const float* __restrict__ pred, int T, int C, float thresho
 // kv * sqrt(t)/sqrt(t+1) + k^T v / sqrt(t+1)  (t = frames already seen), out = q kv -> group norm (eps 1e-6) ->
 // * swish(g).  qkvg: [n_seq][1024] fp16 (q | k*hd^-.5 | v | g); state: [n_seq][4][64][64] fp32; out: [n_seq][256].
 __global__ void __launch_bounds__(64)
-ret_step_kernel(const __half* __restrict__ qkvg, float* __restrict__ state, int t, __half* __restrict__ out) {
+ret_step_kernel(const __half* __restrict__ qkvg, float* __restrict__ state, int t_arg, const int* __restrict__ t_dev,
+                __half* __restrict__ out) {
   const int n = blockIdx.x, h = blockIdx.y, d = threadIdx.x;   // thread d owns column d of the state
+  const int t = t_dev ? *t_dev : t_arg;                        // device-resident frame counter (CUDA-graph replay)
   __shared__ float q_s[64], k_s[64], red[2];
   const __half* row = qkvg + static_cast<size_t>(n) * 1024 + h * 64;
   q_s[d] = __half2float(row[d]);
@@ -518,8 +520,9 @@ int launch_dwconv_bn_swish(const __half* u, const float* w, const float* sc, con
   return 0;
 }
 
-void launch_ret_step(const __half* qkvg, float* state, int n_seq, int t, __half* out, cudaStream_t stream) {
-  ret_step_kernel<<<dim3(n_seq, 4), 64, 0, stream>>>(qkvg, state, t, out);
+void launch_ret_step(const __half* qkvg, float* state, int n_seq, int t, __half* out, cudaStream_t stream,
+                     const int* t_dev) {
+  ret_step_kernel<<<dim3(n_seq, 4), 64, 0, stream>>>(qkvg, state, t, t_dev, out);
 }
 
 }  // namespace fseend

@@ -38,6 +38,8 @@ int launch_dwconv_bn_swish(const __half* u, const float* w, const float* sc, con
 void launch_decide_median(const float* pred, int T, int C, float threshold, int median, unsigned char* out,
                           cudaStream_t stream);
 // Recurrent retention step for frame index t (0-based): state [n_seq][4][64][64] fp32 updated in place.
-void launch_ret_step(const __half* qkvg, float* state, int n_seq, int t, __half* out, cudaStream_t stream);
+// t_dev (optional): device int holding t (then `t` is ignored).
+void launch_ret_step(const __half* qkvg, float* state, int n_seq, int t, __half* out, cudaStream_t stream,
+                     const int* t_dev = nullptr);
 
 }  // namespace fseend

@@ -38,6 +38,16 @@ for _ in range(n): st.step(xt)
 torch.cuda.synchronize()
 lat = (time.perf_counter() - t0) / n
 out["ls_one_step_B1_S10"] = {"ms_per_frame": lat * 1e3, "real_time_factor": lat / 0.1}
+if os.environ.get("FSEEND_EXTRA_LONG"):
+    # BASELINE configs[4]: one hour of audio (T = 36000 frames of 100 ms), single GPU, frame by frame incl. the flush
+    st.reset()
+    feats = torch.randn(36000, 345, device="cuda")
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for t in range(36000): st.step(feats[t:t + 1])
+    for _ in range(9): st.step(None)
+    torch.cuda.synchronize()
+    tot = time.perf_counter() - t0
+    out["ls_streaming_1hour_T36000_S10"] = {"seconds": tot, "ms_per_frame": tot / 36000 * 1e3, "real_time_factor": tot / 3600.0}
 # FS streaming latency at t ~ 500 and t ~ 2000 (attention over the growing cache)
 fs = OnlineTransformerDADiarization(n_speakers=4, in_size=345, n_units=256, n_heads=4, enc_n_layers=4, dec_n_layers=2,
         dropout=0.1, has_mask=True, max_seqlen=500, dec_dim_feedforward=2048).cuda().eval()
