@@ -413,6 +413,23 @@ decide_median_kernel(const float* __restrict__ pred, int T, int C, float thresho
 }
 
 // ---------------------------------------------------------------------------------------------
+// Feature front-end tail (reference datasets/feature.py:103-133, called at :259-261 / :348-352): frame splicing with
+// +-context zero-padded neighbours followed by frame subsampling.  y [T][F] fp32 -> out [ceil(T / sub)][(2 ctx + 1) F]:
+// out[j][k * F + f] = y[j * sub - ctx + k][f] (0 outside [0, T)).  Pure data movement (HBM-bound, bit-exact); doing it
+// on the device lets the host ship the 23-dim log-mel frames instead of the 345-dim spliced ones.
+__global__ void __launch_bounds__(256)
+splice_subsample_kernel(const float* __restrict__ y, int T, int F, int ctx, int sub, int T_out,
+                        float* __restrict__ out) {
+  const int W = (2 * ctx + 1) * F;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(T_out) * W) return;
+  const int j = static_cast<int>(i / W), c = static_cast<int>(i % W);
+  const int k = c / F, f = c - k * F;
+  const int t = j * sub - ctx + k;
+  out[i] = (t >= 0 && t < T) ? y[static_cast<long long>(t) * F + f] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Recurrent retention step (LS:ret:126-144, decay = 1): per (sequence, head) the fp32 state kv (64 x 64) becomes
 // kv * sqrt(t)/sqrt(t+1) + k^T v / sqrt(t+1)  (t = frames already seen), out = q kv -> group norm (eps 1e-6) ->
 // * swish(g).  qkvg: [n_seq][1024] fp16 (q | k*hd^-.5 | v | g); state: [n_seq][4][64][64] fp32; out: [n_seq][256].
@@ -495,6 +512,13 @@ __global__ void advance_counters_kernel(int* counters, int4 inc) {
 }
 void launch_advance_counters(int* counters, int i0, int i1, int i2, int i3, cudaStream_t stream) {
   advance_counters_kernel<<<1, 32, 0, stream>>>(counters, make_int4(i0, i1, i2, i3));
+}
+
+void launch_splice_subsample(const float* y, int T, int F, int ctx, int sub, float* out, cudaStream_t stream) {
+  const int T_out = (T + sub - 1) / sub;
+  const long long n = static_cast<long long>(T_out) * (2 * ctx + 1) * F;
+  if (n == 0) return;
+  splice_subsample_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(y, T, F, ctx, sub, T_out, out);
 }
 
 void launch_decide_median(const float* pred, int T, int C, float threshold, int median, unsigned char* out,

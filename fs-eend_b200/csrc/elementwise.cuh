@@ -34,6 +34,8 @@ void launch_hist_append(const __half* src, __half* hist, int n_seq, int cap, int
 // u/out: [n_seq][T][256] fp16; hist: optional [n_seq][K-1][256] one-step cache (updated when T == 1).
 int launch_dwconv_bn_swish(const __half* u, const float* w, const float* sc, const float* sh, int n_seq, int T, int K,
                            __half* hist, __half* out, cudaStream_t stream);
+// out[j][k * F + f] = y[j * sub - ctx + k][f] (zero outside the signal); out: [ceil(T / sub)][(2 ctx + 1) * F] fp32.
+void launch_splice_subsample(const float* y, int T, int F, int ctx, int sub, float* out, cudaStream_t stream);
 // decisions[t][c] = median filter (odd width, zero padded, along t) of (pred[t][c] > threshold); pred [T][C] fp32.
 void launch_decide_median(const float* pred, int T, int C, float threshold, int median, unsigned char* out,
                           cudaStream_t stream);

@@ -1372,6 +1372,16 @@ int fseend_op_bce_loss(const float* logits, int ld_logits, const float* target, 
   });
 }
 
+int fseend_op_splice_subsample(const float* feat, int T, int F, int context_size, int subsampling, float* out,
+                               void* stream) {
+  return guarded([&] {
+    if (T < 0 || F < 1 || context_size < 0 || subsampling < 1)
+      throw std::invalid_argument("splice_subsample: need T >= 0, F >= 1, context_size >= 0, subsampling >= 1");
+    launch_splice_subsample(feat, T, F, context_size, subsampling, out, static_cast<cudaStream_t>(stream));
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
 int fseend_op_decide_median(const float* pred, int T, int C, float threshold, int median, unsigned char* decisions,
                             void* stream) {
   return guarded([&] {

@@ -46,7 +46,7 @@ EXPORTS = [
     "fseend_ls_stream_enc_step", "fseend_ls_stream_dec_step", "fseend_op_gemm",
     "fseend_op_gemm_ex", "fseend_op_retention", "fseend_op_dwconv_bn_swish", "fseend_op_ret_step",
     "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
-    "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes", "fseend_op_spk_qkv_attn", "fseend_op_decide_median", "fseend_op_label_prepare",
+    "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes", "fseend_op_spk_qkv_attn", "fseend_op_decide_median", "fseend_op_label_prepare", "fseend_op_splice_subsample",
     "fseend_op_bce_loss", "fseend_op_bce_loss_workspace_bytes",
 ]
 
@@ -144,6 +144,8 @@ def lib() -> C.CDLL:
     L.fseend_op_bce_loss_workspace_bytes.argtypes = [ip, ip]
     L.fseend_op_bce_loss.restype = ip
     L.fseend_op_bce_loss.argtypes = [vp, ip, vp, ip, ip, ip, vp, vp, ip, vp, vp, vp]
+    L.fseend_op_splice_subsample.restype = ip
+    L.fseend_op_splice_subsample.argtypes = [vp, ip, ip, ip, ip, vp, vp]
     L.fseend_op_decide_median.restype = ip
     L.fseend_op_decide_median.argtypes = [vp, ip, ip, fp, ip, vp, vp]
     L.fseend_op_embloss_workspace_bytes.restype = C.c_size_t
@@ -583,3 +585,15 @@ def op_bce_loss(logits: torch.Tensor, target: torch.Tensor, lens: torch.Tensor, 
     _check(L.fseend_op_bce_loss(_ptr(logits), Cy, _ptr(target), target.shape[2], B, T, _ptr(lens), _ptr(n_cls),
                                 int(label_delay), _ptr(ws), _ptr(loss), _stream()))
     return loss
+
+
+def op_splice_subsample(feat: torch.Tensor, context_size: int = 7, subsampling: int = 10) -> torch.Tensor:
+    """feat: CUDA fp32 [T, F] -> [ceil(T / subsampling), (2 * context_size + 1) * F] (splice then subsample)."""
+    _require_cuda(feat)
+    if feat.dtype != torch.float32 or feat.dim() != 2:
+        raise FseendError("feat must be float32 [T, F]")
+    T, F = feat.shape
+    out = torch.empty((T + subsampling - 1) // subsampling, (2 * context_size + 1) * F, device=feat.device,
+                      dtype=torch.float32)
+    _check(lib().fseend_op_splice_subsample(_ptr(feat), T, F, int(context_size), int(subsampling), _ptr(out), _stream()))
+    return out

@@ -205,6 +205,12 @@ int fseend_op_bce_loss(const float* logits, int ld_logits, const float* target, 
                        const int* lens_dev, const int* n_cls_dev, int label_delay, float* workspace, float* loss_dev,
                        void* stream);
 
+/* Feature front-end tail (reference datasets/feature.py: splice :111-133 then subsample :103-108, as called at
+ * :259-261 / :348-352): feat fp32 [T][F] (e.g. 23-dim log-mel) -> out fp32 [ceil(T / subsampling)][(2 context_size + 1) F],
+ * out[j][k F + f] = feat[j subsampling - context_size + k][f], zero outside the signal.  Device pointers; bit-exact. */
+int fseend_op_splice_subsample(const float* feat, int T, int F, int context_size, int subsampling, float* out,
+                               void* stream);
+
 /* Post-processing in front of the RTTM writer (reference train/utils/make_rttm.py:10-15, metrics.py:58-60):
  * decisions[t][c] = medfilt(pred > threshold, (median, 1))[t][c] — threshold, then a zero-padded median filter of odd
  * width along time (median <= 1: no filter).  pred fp32 [T][C] (sigmoid posteriors), decisions uint8 [T][C], both on the
