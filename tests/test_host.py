@@ -107,3 +107,18 @@ def test_copy_params_from_masked_to_streaming_covers_every_tensor():
         assert torch.equal(v, msd[mk]), k
     unused = {k for k in msd if k not in used}
     assert all(k.startswith(("dec.encoder", "dec.encoder_norm")) or ".norm12." in k for k in unused), unused
+
+
+def test_bench_flop_model_matches_survey_figures():
+    """28.33 GFLOP per sequence at S=6 (21.24 at S=4) causal-exact, counting `convert` as written
+    (2*T*S*512*256).  bench.py counts the split-weight form actually executed (2*T*256*256), i.e. is conservative."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    for S, survey in ((6, 28.33e9), (4, 21.24e9)):
+        as_written = 2.0 * 500 * S * 512 * 256
+        executed = 2.0 * 500 * 256 * 256
+        assert abs(b.total_flops(1, 500, S) + as_written - executed - survey) < 0.01e9
+    # attention core only: 4*hd*T(T+1)/2 per (head, sequence): 32.1 MFLOP
+    assert abs(b.algorithmic_flops("enc.attn_causal", 1, 500, 6) / 4 - 32.064e6) < 1e3
