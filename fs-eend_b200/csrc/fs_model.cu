@@ -331,6 +331,7 @@ CUtensorMap attn_map(const DevBuf& buf, uint64_t cols, int S, int T, int B, uint
 
 void make_plan(fseend_fs_model* m, int B, int T, int S) {
   if (m->pB == B && m->pT == T && m->pS == S) return;
+  m->pB = m->pT = m->pS = 0;   // the key is only valid once every buffer and descriptor below exists (an allocation may throw)
   const fseend_fs_config& c = m->cfg;
   const int D = c.n_units;
   const size_t Me = 1ull * B * T, Md = Me * S;
@@ -356,7 +357,11 @@ void make_plan(fseend_fs_model* m, int B, int T, int S) {
   A(m->len_dev, B * sizeof(int));
   m->x_stage.free();
   m->logits_stage.free();
-  if (m->cu_host) cudaFreeHost(m->cu_host);
+  if (m->cu_host) {
+    CUDA_CHECK(cudaDeviceSynchronize());   // pending copies out of the old staging buffer
+    cudaFreeHost(m->cu_host);
+    m->cu_host = nullptr;
+  }
   CUDA_CHECK(cudaMallocHost(&m->cu_host, fseend_fs_model::kHostSlots * (2 * B + 1) * sizeof(int)));
   m->ws_bytes = total;
 
@@ -699,6 +704,7 @@ void stream_alloc(fseend_fs_stream* s, int cap) {
   for (auto& b : s->dec_k) grow(*b, 1ull * B * S);
   for (auto& b : s->dec_v) grow(*b, 1ull * B * S);
   grow(s->hist, B);
+  CUDA_CHECK(cudaDeviceSynchronize());   // memset / copies ran on the legacy stream: order them before ANY caller stream
   s->cap = cap;
   s->tm_hist = make_tmap_rows3d(s->hist.p, D, D, cap, B, 128);
 }
@@ -1003,6 +1009,12 @@ int fseend_fs_create(const fseend_fs_config* cfg, int n_tensors, const char* con
   if (cfg->enc_dim_feedforward % 256 || cfg->dec_dim_feedforward % 256 || cfg->in_size < 1 || cfg->conv_kernel < 1 ||
       cfg->enc_n_layers < 1 || cfg->dec_n_layers < 0) {
     set_last_error("unsupported configuration (feed-forward widths must be multiples of 256)");
+    return FSEEND_ERR_INVALID;
+  }
+  if (cfg->conv_kernel != 2 * cfg->conv_padding + 1) {
+    // the forward assumes a 'same' convolution (T frames in, T frames out); the reference hard-codes padding = 9 with
+    // kernel = 2 * conv_delay + 1 (FS:model:30), so any other pairing changes the output length there
+    set_last_error("conv_kernel must equal 2 * conv_padding + 1 ('same' look-ahead convolution)");
     return FSEEND_ERR_INVALID;
   }
   if (!fseend_device_ok()) {

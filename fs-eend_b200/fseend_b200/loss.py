@@ -28,8 +28,9 @@ def standard_loss(ys, ts, label_delay=0):
     lens = torch.tensor([v.shape[0] for v in ts], device=dev, dtype=torch.int32)
     ncls = torch.tensor([v.shape[1] for v in ts], device=dev, dtype=torch.int32)
     for yy, tt in zip(ys, ts):
-        if yy.shape[0] != tt.shape[0] or yy.shape[1] < tt.shape[1]:
-            raise ValueError("each prediction must have its label's length and at least its classes")
+        if tuple(yy.shape) != tuple(tt.shape):
+            # the reference's binary_cross_entropy_with_logits raises on any shape mismatch (loss.py:121-123)
+            raise ValueError("each prediction must have exactly its label's shape (frames, classes)")
     return op_bce_loss(y.contiguous(), t.contiguous(), lens, ncls, label_delay)
 
 

@@ -175,6 +175,39 @@ def _require_cuda(*ts: torch.Tensor):
             raise FseendError("fseend_b200 kernels take contiguous CUDA tensors (no CPU fallback)")
 
 
+class NativeCacheMixin:
+    """Lazy native model of an nn.Module that owns reference-named parameters.
+
+    The cache key is (data_ptr, _version) of every parameter/buffer plus the device they live on.  In-place edits through
+    ``.data`` (``p.data.copy_(...)``, the style of the reference's own copy_params) do NOT bump ``_version``: after such an
+    edit call ``invalidate_native()``.  ``load_state_dict``, optimizer steps and ``.to()`` are picked up automatically.
+    The native model is created on the device the parameters live on, not on ``torch.cuda.current_device()``."""
+
+    _native = None
+    _native_key = None
+
+    def invalidate_native(self):
+        """Drop the cached native model (and any streaming state built on it); the next call rebuilds it."""
+        self._native = None
+        self._native_key = None
+        if hasattr(self, "_stream"):
+            self._stream = None
+
+    def _native_cached(self, build):
+        tensors = list(self.parameters()) + list(self.buffers())
+        dev = tensors[0].device
+        if dev.type != "cuda":
+            raise FseendError("fseend_b200 runs on a CUDA sm_100 device only (move the model with .cuda())")
+        key = (tuple((t.data_ptr(), t._version) for t in tensors), dev.index)
+        if self._native is None or key != self._native_key:
+            with torch.cuda.device(dev):
+                self._native = build()
+            self._native_key = key
+            if hasattr(self, "_stream"):
+                self._stream = None
+        return self._native
+
+
 class FsModel:
     """Owns a native fseend_fs_model built from a reference-named state_dict."""
 
@@ -348,6 +381,8 @@ class LsStream:
         """Fused frame step.  x_t: CUDA fp32 [B, in_size] or None (flush).  Returns logits [B, S] or None."""
         if x_t is not None:
             _require_cuda(x_t)
+            if x_t.dtype != torch.float32 or tuple(x_t.shape) != (self.B, self.model.cfg["in_size"]):
+                raise FseendError("x_t must be float32 [B, in_size]")
         out = torch.empty(self.B, self.S, device="cuda", dtype=torch.float32)
         produced = C.c_int(0)
         _check(self._L.fseend_ls_stream_step(self._h, _ptr(x_t), _ptr(out), C.byref(produced), _stream()))
@@ -355,12 +390,16 @@ class LsStream:
 
     def enc_step(self, x_t: torch.Tensor, t: int) -> torch.Tensor:
         _require_cuda(x_t)
+        if x_t.dtype != torch.float32 or tuple(x_t.shape) != (self.B, self.model.cfg["in_size"]):
+            raise FseendError("x_t must be float32 [B, in_size]")
         emb = torch.empty(self.B, self.model.cfg["n_units"], device="cuda", dtype=torch.float32)
         _check(self._L.fseend_ls_stream_enc_step(self._h, _ptr(x_t), int(t), _ptr(emb), _stream()))
         return emb
 
     def dec_step(self, emb: torch.Tensor, t: int) -> torch.Tensor:
         _require_cuda(emb)
+        if emb.dtype != torch.float32 or tuple(emb.shape) != (self.B, self.model.cfg["n_units"]):
+            raise FseendError("emb must be float32 [B, n_units]")
         att = torch.empty(self.B, self.S, self.model.cfg["n_units"], device="cuda", dtype=torch.float32)
         _check(self._L.fseend_ls_stream_dec_step(self._h, _ptr(emb), int(t), _ptr(att), _stream()))
         return att

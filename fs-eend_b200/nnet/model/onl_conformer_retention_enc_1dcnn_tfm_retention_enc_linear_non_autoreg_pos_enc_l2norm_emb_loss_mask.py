@@ -8,6 +8,8 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
+from fseend_b200.native import NativeCacheMixin
+
 from ..conformer.encoder import ConformerEncoder
 from ..modules.merge_retnet_layer import TransformerEncoderFusionLayer
 
@@ -131,7 +133,7 @@ class MaskedTransformerDecoderModel(nn.Module):
         return att.unsqueeze(1)
 
 
-class OnlineConformerRetentionDADiarization(nn.Module):
+class OnlineConformerRetentionDADiarization(NativeCacheMixin, nn.Module):
     def __init__(self, n_speakers, in_size, n_units, n_heads, enc_n_layers, dec_n_layers, dropout, max_seqlen,
                  recurrent_chunk_size: int = 500, feed_forward_expansion_factor: int = 8,
                  dec_dim_feedforward: int = 2048, conv_expansion_factor: int = 2, conv_kernel_size: int = 16,
@@ -173,12 +175,7 @@ class OnlineConformerRetentionDADiarization(nn.Module):
 
     def native(self):
         from fseend_b200.native import LsModel
-        tensors = list(self.parameters()) + list(self.buffers())
-        key = (tuple((t.data_ptr(), t._version) for t in tensors), torch.cuda.current_device())
-        if self._native is None or key != self._native_key:
-            self._native = LsModel(self._native_cfg(), self.state_dict())
-            self._native_key = key
-        return self._native
+        return self._native_cached(lambda: LsModel(self._native_cfg(), self.state_dict()))
 
     def _pack(self, src, ilens):
         dev = self.cnn.weight.device

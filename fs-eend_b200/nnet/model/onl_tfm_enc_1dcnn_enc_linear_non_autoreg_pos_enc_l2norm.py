@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
-from fseend_b200.native import op_embloss
+from fseend_b200.native import NativeCacheMixin, op_embloss
 from ..modules.merge_tfm_encoder import TransformerEncoder, TransformerEncoderFusionLayer
 
 
@@ -84,7 +84,7 @@ class MaskedTransformerDecoderModel(nn.Module):
         self.attractor_decoder = TransformerEncoder(decoder_layers, n_layers)
 
 
-class OnlineTransformerDADiarization(nn.Module):
+class OnlineTransformerDADiarization(NativeCacheMixin, nn.Module):
     def __init__(self, n_speakers, in_size, n_units, n_heads, enc_n_layers, dec_n_layers, dropout, has_mask,
                  max_seqlen, dec_dim_feedforward, conv_delay=9, mask_delay=0, decom_kernel_size=64):
         super().__init__()
@@ -112,12 +112,7 @@ class OnlineTransformerDADiarization(nn.Module):
     def native(self):
         """The native model for the current parameter values (rebuilt when any parameter/buffer changed)."""
         from fseend_b200.native import FsModel
-        tensors = list(self.parameters()) + list(self.buffers())
-        key = (tuple((t.data_ptr(), t._version) for t in tensors), torch.cuda.current_device())
-        if self._native is None or key != self._native_key:
-            self._native = FsModel(self._native_cfg(), self.state_dict())
-            self._native_key = key
-        return self._native
+        return self._native_cached(lambda: FsModel(self._native_cfg(), self.state_dict()))
 
     def _pack(self, src: Sequence[Tensor], ilens: Sequence[int]):
         dev = self.cnn.weight.device

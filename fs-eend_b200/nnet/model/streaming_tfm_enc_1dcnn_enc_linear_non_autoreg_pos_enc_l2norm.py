@@ -9,6 +9,8 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
+from fseend_b200.native import NativeCacheMixin
+
 from ..modules.streaming_tfm import StreamingAttractorDecoder, StreamingConv1d, StreamingEmbeddingEncoder
 
 
@@ -25,7 +27,7 @@ def streaming_to_masked_key(k: str) -> str:
     return k
 
 
-class StreamingTransformerEDADiarization(nn.Module):
+class StreamingTransformerEDADiarization(NativeCacheMixin, nn.Module):
     def __init__(self, in_size, n_units, n_heads, enc_n_layers, dec_n_layers, dropout, has_mask, max_seqlen,
                  dec_dim_feedforward, conv_delay=9, mask_delay=0, decom_kernel_size=64):
         super().__init__()
@@ -50,14 +52,8 @@ class StreamingTransformerEDADiarization(nn.Module):
 
     def native(self):
         from fseend_b200.native import FsModel
-        tensors = list(self.parameters()) + list(self.buffers())
-        key = (tuple((t.data_ptr(), t._version) for t in tensors), torch.cuda.current_device())
-        if self._native is None or key != self._native_key:
-            sd = {streaming_to_masked_key(k): v for k, v in self.state_dict().items()}
-            self._native = FsModel(self._native_cfg(), sd)
-            self._native_key = key
-            self._stream = None
-        return self._native
+        return self._native_cached(
+            lambda: FsModel(self._native_cfg(), {streaming_to_masked_key(k): v for k, v in self.state_dict().items()}))
 
     def reset(self):
         """Forget the streaming state (start a new recording)."""

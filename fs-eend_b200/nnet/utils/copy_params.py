@@ -12,5 +12,7 @@ def copy_params_from_masked_to_streaming(masked_fs_eend, streaming_fs_eend):
     dst = streaming_fs_eend.state_dict()
     for k, v in dst.items():
         v.copy_(src[streaming_to_masked_key(k)])
+    if hasattr(streaming_fs_eend, "invalidate_native"):
+        streaming_fs_eend.invalidate_native()      # weights changed: the cached native model is stale by definition
     if hasattr(streaming_fs_eend, "reset"):
         streaming_fs_eend.reset()

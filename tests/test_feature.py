@@ -1,6 +1,5 @@
 """Feature front-end tail (started): splice + subsample on the device against the REAL reference functions
 (goldens from tests/golden/make_golden_feature.py).  Pure data movement: compared for exact equality."""
-import importlib.util
 import os
 
 import numpy as np
@@ -14,13 +13,10 @@ CASES = {"feat_T1003_F23": (1003, 23, 7, 10, 0), "feat_T40_F5_c2_s3": (40, 5, 2,
 
 
 def dropin():
-    """fs-eend_b200/datasets/feature.py, loaded by path (an installed `datasets` package may shadow the directory name,
-    exactly as it would for the reference's own datasets/ folder)."""
-    spec = importlib.util.spec_from_file_location("fseend_dropin_feature",
-                                                  os.path.join(ROOT, "fs-eend_b200", "datasets", "feature.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
+    """The device helper lives in the fseend_b200 package (NOT under a `datasets` package: that name belongs to the
+    reference's namespace directory and must keep resolving there, see tests/test_dropin_boundary.py)."""
+    from fseend_b200 import feature
+    return feature
 
 
 def restate(y, ctx, sub):

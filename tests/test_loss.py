@@ -28,7 +28,7 @@ def test_oracle_labels_and_loss_match_reference(name):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(CASES))
 def test_gpu_labels_and_loss_match_reference(name):
-    from train.utils.loss import prepare_labels, standard_loss
+    from fseend_b200.loss import prepare_labels, standard_loss
     seed, lens, n_spks, delay = CASES[name]
     labels, logits = L.synthetic_batch(seed, lens, n_spks)
     tgt = prepare_labels([l.cuda() for l in labels])
@@ -44,7 +44,7 @@ def test_gpu_labels_and_loss_match_reference(name):
 @pytest.mark.gpu
 def test_gpu_loss_at_training_batch_shape():
     """BASELINE configs[1] shape: B=64, T=500, 4 speakers (+2) — kernel vs the fp64 oracle."""
-    from train.utils.loss import prepare_labels, standard_loss
+    from fseend_b200.loss import prepare_labels, standard_loss
     labels, logits = L.synthetic_batch(7, [500] * 64, [4] * 64)
     tgt_ref = L.prepare_labels(labels)
     tgt = prepare_labels([l.cuda() for l in labels])

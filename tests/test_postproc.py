@@ -35,7 +35,7 @@ def test_oracle_median_is_majority_vote_on_binary_input():
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(GOLD))
 def test_make_rttm_dropin_is_byte_identical_to_reference(name):
-    from train.utils.make_rttm import make_rttm
+    from fseend_b200.rttm import make_rttm
     g = GOLD[name]
     pred = P.synthetic_posteriors(g["T"], g["C"], g["seed"])
     rttm = make_rttm("rec_" + name, pred.cuda(), frame_shift=80, threshold=g["threshold"], median=g["median"],

@@ -4,7 +4,6 @@ by frame through the streaming model.  Mirrors the flow of the reference's strea
 
     python tools/demo_pipeline.py [n_mel_frames]
 """
-import importlib.util
 import os
 import sys
 
@@ -15,11 +14,9 @@ import torch  # noqa: E402
 from nnet.model.onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import OnlineTransformerDADiarization  # noqa: E402
 from nnet.model.streaming_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import StreamingTransformerEDADiarization  # noqa: E402
 from nnet.utils.copy_params import copy_params_from_masked_to_streaming  # noqa: E402
-from train.utils.make_rttm import make_rttm  # noqa: E402
+from fseend_b200.rttm import make_rttm  # noqa: E402
+from fseend_b200 import feature  # noqa: E402
 
-spec = importlib.util.spec_from_file_location("dropin_feature", os.path.join(ROOT, "fs-eend_b200", "datasets", "feature.py"))
-feature = importlib.util.module_from_spec(spec)
-spec.loader.exec_module(feature)
 
 
 def main():
