@@ -1,0 +1,843 @@
+// Parity-precision kernels (see p32.cuh): split-precision tcgen05 GEMM on fp32 activations, fp32 retention core,
+// fp32 normalisation / activation kernels.  Reference arithmetic restated per kernel below (paths relative to
+// /root/reference/LS-EEND/nnet).
+#include "p32.cuh"
+
+#include <math.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace fseend {
+
+namespace {
+
+// =====================================================================================================================
+// Split-precision GEMM.  One CTA (256 threads) = one 128 x 128 output tile.
+//   all 8 warps : A producer — fp32 rows from global (coalesced float4), split x = hi + lo (fp16), both halves written
+//                 into 128B-swizzled K-major smem tiles (the layout TMA would have produced)
+//   thread 0    : TMA for the two weight tiles (W_hi, W_lo: split once at model creation)
+//   warp 1      : MMA issue — per 64-wide k block twelve tcgen05.mma into a FRESH TMEM accumulator: the eight small
+//                 products first (A_lo W_hi, A_hi W_lo), then A_hi W_hi (lo.lo dropped: 2^-22 relative)
+//   all 8 warps : fold the finished k-block accumulator into fp32 REGISTERS (tcgen05.ld + add), epilogue from registers
+// Why registers: the tensor core truncates (round-toward-zero) when it adds into the fp32 TMEM accumulator — measured
+// on B200, the error of a plain TMEM-resident accumulation grows linearly with the number of MMA steps (3e-5 absolute at
+// K = 1024, 6.5e-5 at K = 4864 on O(1) outputs: ~17 bits).  With one fresh accumulator per k-block only the four
+// A_hi W_hi steps truncate at full magnitude, and the sum across k-blocks is round-to-nearest on the CUDA cores.
+// Two stages of (A_hi, A_lo, W_hi, W_lo) = 128 KB and two 128-column accumulators: the split of k-block i+1 and the
+// fold of k-block i-1 overlap the MMAs of k-block i.
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int kStages = 2;
+constexpr int kTileBytes = 128 * BK * 2;          // 16 KB
+constexpr int kStageBytes = 4 * kTileBytes;       // A_hi | A_lo | W_hi | W_lo
+constexpr int kGemmSmem = kStages * kStageBytes + 1024;
+constexpr uint32_t kTmemCols = 256;            // two ping-pong 128-column accumulators
+
+__device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  __half h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __float2half_rn(x[i]);
+    l[i] = __float2half_rn(x[i] - __half2float(h[i]));
+  }
+  hi.x = static_cast<uint32_t>(__half_as_ushort(h[0])) | (static_cast<uint32_t>(__half_as_ushort(h[1])) << 16);
+  hi.y = static_cast<uint32_t>(__half_as_ushort(h[2])) | (static_cast<uint32_t>(__half_as_ushort(h[3])) << 16);
+  hi.z = static_cast<uint32_t>(__half_as_ushort(h[4])) | (static_cast<uint32_t>(__half_as_ushort(h[5])) << 16);
+  hi.w = static_cast<uint32_t>(__half_as_ushort(h[6])) | (static_cast<uint32_t>(__half_as_ushort(h[7])) << 16);
+  lo.x = static_cast<uint32_t>(__half_as_ushort(l[0])) | (static_cast<uint32_t>(__half_as_ushort(l[1])) << 16);
+  lo.y = static_cast<uint32_t>(__half_as_ushort(l[2])) | (static_cast<uint32_t>(__half_as_ushort(l[3])) << 16);
+  lo.z = static_cast<uint32_t>(__half_as_ushort(l[4])) | (static_cast<uint32_t>(__half_as_ushort(l[5])) << 16);
+  lo.w = static_cast<uint32_t>(__half_as_ushort(l[6])) | (static_cast<uint32_t>(__half_as_ushort(l[7])) << 16);
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == P32_RELU) return fmaxf(v, 0.f);
+  if (act == P32_SWISH) return v / (1.f + expf(-v));
+  return v;
+}
+
+__global__ void __launch_bounds__(256, 1)
+p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
+                const P32GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t done_bar[kStages];   // MMAs of a k-block complete: smem stage free + accumulator ready
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = p.N / BN;
+  const int n_tile = blockIdx.x % n_tiles;
+  const int m_tile = blockIdx.x / n_tiles;
+  const int tiles_per_seq = (p.rows_per_seq + BM - 1) / BM;
+  const int seq = m_tile / tiles_per_seq;
+  const int t0 = (m_tile % tiles_per_seq) * BM;
+  const int n0 = n_tile * BN;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&done_bar[s], 1);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmWhi);
+    tma_prefetch_desc(&tmWlo);
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int total_it = p.taps * p.k_blocks;
+  const int a_off = p.a_row_offset + (p.a_row_offset_dev ? *p.a_row_offset_dev : 0);
+  const float* a_seq = p.A + static_cast<size_t>(seq) * p.a_seq_rows * p.lda;
+  constexpr uint32_t idesc = make_idesc_f16(BM, BN, false);
+
+  // this thread's slice of the output tile: row (warp & 3) * 32 + lane, columns (warp >> 2) * 64 .. + 64
+  const int cbase = (warp >> 2) * 64;
+  const uint32_t lane_addr = (static_cast<uint32_t>((warp & 3) * 32) << 16) + cbase;
+  float acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  auto fold = [&](int buf) {      // acc += finished k-block accumulator `buf`
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + buf * 128 + lane_addr + half * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[half * 32 + j] += __uint_as_float(raw[j]);
+    }
+  };
+
+  for (int it = 0; it < total_it; ++it) {
+    const int s = it & 1;
+    const uint32_t ph = (it >> 1) & 1;
+    if (it >= kStages) {
+      mbar_wait(&done_bar[s], ph ^ 1, 71);   // the MMAs of iteration it-2 are complete: fold their accumulator,
+      tc_fence_after();                      // then stage s and accumulator s are free
+      fold(s);
+      tc_fence_before();
+    }
+    const int tap = it / p.k_blocks;
+    const int kb = it - tap * p.k_blocks;
+    uint8_t* sAhi = smem + s * kStageBytes;
+    uint8_t* sAlo = sAhi + kTileBytes;
+    uint8_t* sWhi = sAlo + kTileBytes;
+    uint8_t* sWlo = sWhi + kTileBytes;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&full_bar[s], 2 * kTileBytes);
+      tma_load_2d(sWhi, &tmWhi, &full_bar[s], kb * BK, tap * p.N + n0);
+      tma_load_2d(sWlo, &tmWlo, &full_bar[s], kb * BK, tap * p.N + n0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = tid + 256 * i;
+      const int r = q >> 3, c = q & 7;                 // tile row, 16-byte chunk (8 halfs) inside the 64-wide k block
+      const int t = t0 + r;
+      const int arow = t + tap + p.tap_shift + a_off;
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (t < p.rows_per_seq && arow >= 0 && arow < p.a_seq_rows) {
+        const float4* src = reinterpret_cast<const float4*>(a_seq + static_cast<size_t>(arow) * p.lda + kb * BK + c * 8);
+        v0 = __ldg(src);
+        v1 = __ldg(src + 1);
+      }
+      uint4 hi, lo;
+      split8(v0, v1, hi, lo);
+      const uint32_t off = sw128_offset(r, c);
+      *reinterpret_cast<uint4*>(sAhi + off) = hi;
+      *reinterpret_cast<uint4*>(sAlo + off) = lo;
+    }
+    fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    __syncthreads();               // (also orders every thread's fold of accumulator s before its re-use below)
+    if (warp == 1) {
+      mbar_wait(&full_bar[s], ph, 72);
+      tc_fence_after();
+      const uint64_t dAhi = smem_desc_sw128(smem_u32(sAhi)), dAlo = smem_desc_sw128(smem_u32(sAlo));
+      const uint64_t dWhi = smem_desc_sw128(smem_u32(sWhi)), dWlo = smem_desc_sw128(smem_u32(sWlo));
+      const uint32_t d = tmem_base + s * 128;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          umma_f16(d, dAlo + 2 * kk, dWhi + 2 * kk, idesc, kk > 0 ? 1u : 0u);
+          umma_f16(d, dAhi + 2 * kk, dWlo + 2 * kk, idesc, 1u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) umma_f16(d, dAhi + 2 * kk, dWhi + 2 * kk, idesc, 1u);
+        umma_commit(&done_bar[s]);
+      }
+      __syncwarp();
+    }
+  }
+  // drain the last (up to) two k-blocks in issue order
+  for (int j = (total_it >= 2 ? total_it - 2 : 0); j < total_it; ++j) {
+    mbar_wait(&done_bar[j & 1], (j >> 1) & 1, 73);
+    tc_fence_after();
+    fold(j & 1);
+  }
+
+  // ---------------- epilogue from registers
+  {
+    const int r = (warp & 3) * 32 + lane;
+    const int t = t0 + r;
+    if (t < p.rows_per_seq) {
+      const size_t orow = static_cast<size_t>(seq) * p.rows_per_seq + t;
+      const int col0 = n0 + cbase;
+      float* op = p.out + orow * p.ldo + col0;
+      const float* rp = p.residual ? p.residual + orow * p.ldr + col0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float x = acc[j + k] * p.w_inv_scale;
+          if (p.bias) x += __ldg(p.bias + col0 + j + k);
+          v[k] = p.alpha * act_apply(x, p.act);
+        }
+        if (rp) {
+          const float4 rr = *reinterpret_cast<const float4*>(rp + j);
+          v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+        }
+        *reinterpret_cast<float4*>(op + j) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =====================================================================================================================
+// LayerNorm over rows of 256 fp32 (biased variance, two-pass in registers): one warp per row, lane owns columns
+// [4 lane, 4 lane + 4) and [128 + 4 lane, ...).  y1 = g1 ? LN(x) : x -> out1;  out2 = LN(y1; g2, b2).
+__device__ __forceinline__ void warp_ln8(float (&v)[8], const float* g, const float* b, int lane, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  const float mean = s * (1.f / 256.f);
+  float m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float d = v[i] - mean;
+    m2 = fmaf(d, d, m2);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);
+  const float rstd = 1.f / sqrtf(m2 * (1.f / 256.f) + eps);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + lane), g1 = __ldg(reinterpret_cast<const float4*>(g + 128) + lane);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + lane), b1 = __ldg(reinterpret_cast<const float4*>(b + 128) + lane);
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
+}
+
+__global__ void __launch_bounds__(256)
+p32_layernorm_kernel(const float* __restrict__ x, int rows, const float* __restrict__ g1, const float* __restrict__ b1,
+                     float* __restrict__ out1, const float* __restrict__ g2, const float* __restrict__ b2,
+                     float* __restrict__ out2, float eps, const int* __restrict__ seq_len, int rows_per_seq) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * 256);
+  const float4 a = xp[lane], b = xp[32 + lane];
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  bool zero = false;
+  if (seq_len) {
+    const int sq = row / rows_per_seq;
+    zero = (row - sq * rows_per_seq) >= seq_len[sq];
+  }
+  if (g1) warp_ln8(v, g1, b1, lane, eps);
+  if (zero) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+  if (out1) {
+    float4* op = reinterpret_cast<float4*>(out1 + static_cast<size_t>(row) * 256);
+    op[lane] = make_float4(v[0], v[1], v[2], v[3]);
+    op[32 + lane] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (out2) {
+    warp_ln8(v, g2, b2, lane, eps);
+    if (zero) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+    float4* op = reinterpret_cast<float4*>(out2 + static_cast<size_t>(row) * 256);
+    op[lane] = make_float4(v[0], v[1], v[2], v[3]);
+    op[32 + lane] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+__global__ void p32_pad_input_kernel(const float* __restrict__ x, const int* __restrict__ cu, int Tmax, int Din,
+                                     int Kpad, float* __restrict__ out) {
+  const int row = blockIdx.x;
+  const int b = row / Tmax, t = row - b * Tmax;
+  const int start = cu[b], len = cu[b + 1] - start;
+  const float* src = (t < len) ? x + static_cast<size_t>(start + t) * Din : nullptr;
+  float* dst = out + static_cast<size_t>(row) * Kpad;
+  for (int i = threadIdx.x; i < Kpad; i += blockDim.x) dst[i] = (src && i < Din) ? __ldg(src + i) : 0.f;
+}
+
+// GLU over channel halves (conformer/activation.py:40-42): out = a * sigmoid(b)
+__global__ void __launch_bounds__(256)
+p32_glu_kernel(const float* __restrict__ h, size_t n4, float* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // float4 index into [rows][64 float4]
+  if (i >= n4) return;
+  const size_t row = i >> 6, c = i & 63;
+  const float4 a = reinterpret_cast<const float4*>(h)[row * 128 + c];
+  const float4 g = reinterpret_cast<const float4*>(h)[row * 128 + 64 + c];
+  float4 o;
+  o.x = a.x / (1.f + expf(-g.x));
+  o.y = a.y / (1.f + expf(-g.y));
+  o.z = a.z / (1.f + expf(-g.z));
+  o.w = a.w / (1.f + expf(-g.w));
+  reinterpret_cast<float4*>(out)[i] = o;
+}
+
+// Causal depthwise Conv1d (left zero padding K-1, conformer/convolution.py:144,65-68) -> BatchNorm1d (eval, folded)
+// -> swish.  Thread = (channel, 8 output frames); one-step form reads and slides the (K-1)-frame cache.
+__global__ void __launch_bounds__(256)
+p32_dwconv_bn_swish_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ sc,
+                           const float* __restrict__ sh, int T, int K, float* __restrict__ hist,
+                           float* __restrict__ out) {
+  const int n = blockIdx.y, c = threadIdx.x;
+  const int t0 = blockIdx.x * 8;
+  float wk[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) wk[k] = k < K ? w[c * K + k] : 0.f;
+  const float* up = u + static_cast<size_t>(n) * T * 256 + c;
+  float* hp = hist ? hist + static_cast<size_t>(n) * (K - 1) * 256 + c : nullptr;
+  const float s0 = sc[c], h0 = sh[c];
+  for (int t = t0; t < min(t0 + 8, T); ++t) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k < K) {
+        const int tt = t - (K - 1) + k;
+        float v = 0.f;
+        if (tt >= 0) v = up[static_cast<size_t>(tt) * 256];
+        else if (hp) v = hp[static_cast<size_t>(tt + K - 1) * 256];
+        acc = fmaf(wk[k], v, acc);
+      }
+    }
+    acc = fmaf(acc, s0, h0);
+    out[(static_cast<size_t>(n) * T + t) * 256 + c] = acc / (1.f + expf(-acc));
+  }
+  if (hp && T == 1) {   // slide the cache: drop the oldest frame, append u[0]
+    float prev[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) prev[k] = (k < K - 1) ? hp[static_cast<size_t>(k) * 256] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k < K - 2) hp[static_cast<size_t>(k) * 256] = prev[k + 1];
+    }
+    if (K >= 2) hp[static_cast<size_t>(K - 2) * 256] = up[0];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+p32_l2norm_kernel(float* __restrict__ x, int rows) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float4* xp = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * 256);
+  float4 a = xp[lane], b = xp[32 + lane];
+  float ss = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  const float inv = 1.f / sqrtf(ss);      // no eps, as the reference (x / norm): a zero row gives NaN there too
+  a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+  b.x *= inv; b.y *= inv; b.z *= inv; b.w *= inv;
+  xp[lane] = a;
+  xp[32 + lane] = b;
+}
+
+__global__ void __launch_bounds__(256)
+p32_convert_kernel(const float* __restrict__ y, const float* __restrict__ pe_proj, size_t n4, int S,
+                   float* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // float4 index into [rows][S][64]
+  if (i >= n4) return;
+  const size_t c = i & 63, rs = i >> 6;
+  const size_t row = rs / S, s = rs - row * S;
+  const float4 a = reinterpret_cast<const float4*>(y)[row * 64 + c];
+  const float4 b = __ldg(reinterpret_cast<const float4*>(pe_proj) + s * 64 + c);
+  reinterpret_cast<float4*>(out)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+// Speaker-axis attention (merge_retnet_layer.py:244-249 -> nn.MultiheadAttention, no mask): thread = (frame, slot, head).
+constexpr int kMaxS = 16;
+__global__ void __launch_bounds__(128)
+p32_spk_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n_frames, int S, float scale) {
+  const long long gi = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gi >= static_cast<long long>(n_frames) * S * 4) return;
+  const int h = static_cast<int>(gi & 3);
+  const long long row = gi >> 2;               // frame * S + slot
+  const long long f = row / S;
+  float q[64];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(qkv + row * 768 + h * 64);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 t = __ldg(qp + i);
+      q[4 * i] = t.x * scale; q[4 * i + 1] = t.y * scale; q[4 * i + 2] = t.z * scale; q[4 * i + 3] = t.w * scale;
+    }
+  }
+  float sc[kMaxS];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int b = 0; b < kMaxS; ++b) {
+    sc[b] = -INFINITY;
+    if (b < S) {
+      const float4* kp = reinterpret_cast<const float4*>(qkv + (f * S + b) * 768 + 256 + h * 64);
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 t = __ldg(kp + i);
+        d = fmaf(q[4 * i], t.x, d); d = fmaf(q[4 * i + 1], t.y, d);
+        d = fmaf(q[4 * i + 2], t.z, d); d = fmaf(q[4 * i + 3], t.w, d);
+      }
+      sc[b] = d;
+      mx = fmaxf(mx, d);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int b = 0; b < kMaxS; ++b) {
+    if (b < S) {
+      sc[b] = expf(sc[b] - mx);
+      sum += sc[b];
+    }
+  }
+  const float inv = 1.f / sum;
+  float o[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int b = 0; b < kMaxS; ++b) {
+    if (b < S) {
+      const float pw = sc[b] * inv;
+      const float4* vp = reinterpret_cast<const float4*>(qkv + (f * S + b) * 768 + 512 + h * 64);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 t = __ldg(vp + i);
+        o[4 * i] = fmaf(pw, t.x, o[4 * i]); o[4 * i + 1] = fmaf(pw, t.y, o[4 * i + 1]);
+        o[4 * i + 2] = fmaf(pw, t.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(pw, t.w, o[4 * i + 3]);
+      }
+    }
+  }
+  float4* op = reinterpret_cast<float4*>(out + row * 256 + h * 64);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) op[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+}
+
+// Logits head (LS:model:136-143): att_n = att / ||att||, y = emb . att_n.  One warp per frame.
+__global__ void __launch_bounds__(256)
+p32_head_kernel(const float* __restrict__ emb, const float* __restrict__ att, int n_frames, int S,
+                float* __restrict__ logits, float* __restrict__ emb_out, float* __restrict__ att_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_frames) return;
+  const float4* ep = reinterpret_cast<const float4*>(emb + static_cast<size_t>(warp) * 256);
+  const float4 e0 = ep[lane], e1 = ep[32 + lane];
+  if (emb_out) {
+    float4* eo = reinterpret_cast<float4*>(emb_out + static_cast<size_t>(warp) * 256);
+    eo[lane] = e0;
+    eo[32 + lane] = e1;
+  }
+  for (int s = 0; s < S; ++s) {
+    const size_t row = static_cast<size_t>(warp) * S + s;
+    const float4* ap = reinterpret_cast<const float4*>(att + row * 256);
+    const float4 a0 = ap[lane], a1 = ap[32 + lane];
+    float ss = a0.x * a0.x + a0.y * a0.y + a0.z * a0.z + a0.w * a0.w + a1.x * a1.x + a1.y * a1.y + a1.z * a1.z + a1.w * a1.w;
+    float dot = a0.x * e0.x + a0.y * e0.y + a0.z * e0.z + a0.w * e0.w + a1.x * e1.x + a1.y * e1.y + a1.z * e1.z + a1.w * e1.w;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, off);
+      dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    }
+    const float inv = 1.f / sqrtf(ss);
+    if (lane == 0) logits[row] = dot * inv;
+    if (att_out) {
+      float4* ao = reinterpret_cast<float4*>(att_out + row * 256);
+      ao[lane] = make_float4(a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv);
+      ao[32 + lane] = make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv);
+    }
+  }
+}
+
+// =====================================================================================================================
+// Retention, pass 1: per (sequence n = (b, s), head h) the exclusive prefix KV_c = sum_{t in chunks < c} k_t^T v_t
+// (modules/retention.py:167-180 without the 1/sqrt(C) weights, re-applied where used) and
+// cross_scale_c = max(1, max_d sum_e |KV_c[e][d]| / sqrt(C)).  256 threads = 16 x 16, each owns a 4 x 4 block of KV.
+__global__ void __launch_bounds__(256)
+p32_ret_chunk_state_kernel(const float* __restrict__ qkvg, int S, int T, int chunk, int n_chunks,
+                           float* __restrict__ state, float* __restrict__ cross_scale) {
+  const int n = blockIdx.x >> 2, h = blockIdx.x & 3;
+  const int b = n / S, s = n - b * S;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  __shared__ __align__(16) float ks[32][64];
+  __shared__ __align__(16) float vs[32][64];
+  __shared__ float colpart[16][64];     // per-ty partial column |.|-sums (fixed-order reduction: bit-reproducible)
+  __shared__ float colsum[64];
+  float kv[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) kv[i][j] = 0.f;
+  const size_t row_stride = static_cast<size_t>(S) * 1024;
+  const float* base = qkvg + (static_cast<size_t>(b) * T * S + s) * 1024 + h * 64;
+  const float inv_sqrt_c = 1.f / sqrtf(static_cast<float>(chunk));
+  for (int c = 0; c < n_chunks; ++c) {
+    // state entering chunk c
+    float* sp = state + ((static_cast<size_t>(n) * 4 + h) * n_chunks + c) * 4096;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(sp + (4 * ty + i) * 64 + 4 * tx) = make_float4(kv[i][0], kv[i][1], kv[i][2], kv[i][3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      colpart[ty][4 * tx + j] = fabsf(kv[0][j]) + fabsf(kv[1][j]) + fabsf(kv[2][j]) + fabsf(kv[3][j]);
+    __syncthreads();
+    if (tid < 64) {
+      float a = 0.f;
+#pragma unroll
+      for (int y = 0; y < 16; ++y) a += colpart[y][tid];
+      colsum[tid] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float mx = 0.f;
+      for (int d = 0; d < 64; ++d) mx = fmaxf(mx, colsum[d]);
+      cross_scale[(static_cast<size_t>(n) * 4 + h) * n_chunks + c] = fmaxf(1.f, mx * inv_sqrt_c);
+    }
+    if (c == n_chunks - 1) break;
+    for (int r0 = 0; r0 < chunk; r0 += 32) {
+      __syncthreads();
+      // 32 rows x (64 k + 64 v) floats = 1024 float4: 4 per thread
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = tid + 256 * i;
+        const int rr = q >> 5, part = (q >> 4) & 1, c4 = q & 15;
+        const int t = c * chunk + r0 + rr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + rr < chunk) v = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(t) * row_stride + 256 + part * 256) + c4);
+        *reinterpret_cast<float4*>(part ? &vs[rr][4 * c4] : &ks[rr][4 * c4]) = v;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) {
+        const float4 kk = *reinterpret_cast<const float4*>(&ks[rr][4 * ty]);
+        const float4 vv = *reinterpret_cast<const float4*>(&vs[rr][4 * tx]);
+        const float ke[4] = {kk.x, kk.y, kk.z, kk.w};
+        const float vd[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) kv[i][j] = fmaf(ke[i], vd[j], kv[i][j]);
+      }
+    }
+  }
+}
+
+// Retention, pass 2 (modules/retention.py:146-194,222-224 restated in retention.cu's header):
+//   O_j = sum_{i<=j, same chunk} (q_j.k_i) v_i + q_j KV_c;   inner_j = max(1, sum_{i<=j} |q_j.k_i| / sqrt(j+1))
+//   ret_j = O_j / (sqrt(j+1) max(inner_j, cross_c));   out_j = swish(g_j) * LayerNorm_64(ret_j; eps 1e-6)
+// CTA = 64 query rows of one (sequence, head, chunk); 256 threads = 16 (ty: rows 4ty..) x 16 (tx); S tile columns are
+// owned strided (tx + 16 jj) so that the row-major K tile is read without bank conflicts, O columns contiguous (4 tx..).
+constexpr int kLD = 68;
+constexpr int kRetSmem = 4 * 64 * kLD * 4;
+
+__global__ void __launch_bounds__(256, 2)
+p32_retention_kernel(const float* __restrict__ qkvg, const float* __restrict__ state,
+                     const float* __restrict__ cross_scale, int S, int T, int chunk, int n_chunks,
+                     float* __restrict__ out) {
+  extern __shared__ __align__(16) float rsm[];
+  float* Qs = rsm;
+  float* Ks = Qs + 64 * kLD;
+  float* Vs = Ks + 64 * kLD;
+  float* Ss = Vs + 64 * kLD;
+  const int n_qt = (chunk + 63) / 64;
+  const int qt = n_qt - 1 - static_cast<int>(blockIdx.x);     // heaviest tiles first
+  const int h = blockIdx.y;
+  const int c = blockIdx.z % n_chunks, n = blockIdx.z / n_chunks;
+  const int b = n / S, s = n - b * S;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const size_t row_stride = static_cast<size_t>(S) * 1024;
+  const float* base = qkvg + ((static_cast<size_t>(b) * T + static_cast<size_t>(c) * chunk) * S + s) * 1024 + h * 64;
+  const int q0 = qt * 64;
+
+  auto load_tile = [&](float* dst, int col_off, int r0) {      // rows r0.. of the chunk, 64 floats at col_off
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = tid + 256 * i;
+      const int rr = q >> 4, c4 = q & 15;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + rr < chunk) v = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(r0 + rr) * row_stride + col_off) + c4);
+      *reinterpret_cast<float4*>(dst + rr * kLD + 4 * c4) = v;
+    }
+  };
+  // O[4ty+i][4tx+j] += sum_k L[4ty+i][k] * R[k][4tx+j]   (L, R: 64 x 64 tiles with leading dimension kLD)
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  auto mac_lr = [&](const float* L, const float* R) {
+#pragma unroll 4
+    for (int k4 = 0; k4 < 64; k4 += 4) {
+      float l[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(L + (4 * ty + i) * kLD + k4);
+        l[i][0] = t.x; l[i][1] = t.y; l[i][2] = t.z; l[i][3] = t.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 t = *reinterpret_cast<const float4*>(R + (k4 + k) * kLD + 4 * tx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          o[i][0] = fmaf(l[i][k], t.x, o[i][0]);
+          o[i][1] = fmaf(l[i][k], t.y, o[i][1]);
+          o[i][2] = fmaf(l[i][k], t.z, o[i][2]);
+          o[i][3] = fmaf(l[i][k], t.w, o[i][3]);
+        }
+      }
+    }
+  };
+
+  load_tile(Qs, 0, q0);
+  float asum[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c > 0) {   // cross-chunk term: O += Q KV_c
+    const float* sp = state + ((static_cast<size_t>(n) * 4 + h) * n_chunks + c) * 4096;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = tid + 256 * i;
+      const int rr = q >> 4, c4 = q & 15;
+      *reinterpret_cast<float4*>(Vs + rr * kLD + 4 * c4) = __ldg(reinterpret_cast<const float4*>(sp + rr * 64) + c4);
+    }
+    __syncthreads();
+    mac_lr(Qs, Vs);
+  }
+  for (int kt = 0; kt <= qt; ++kt) {
+    __syncthreads();                       // previous tile's readers of Ks / Vs / Ss are done (and Qs is loaded)
+    load_tile(Ks, 256, kt * 64);
+    load_tile(Vs, 512, kt * 64);
+    __syncthreads();
+    // S[4ty+i][tx+16jj] = q_row . k_col
+    float sacc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sacc[i][j] = 0.f;
+#pragma unroll 4
+    for (int d4 = 0; d4 < 64; d4 += 4) {
+      float4 qv[4], kv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(Qs + (4 * ty + i) * kLD + d4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kv[j] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * kLD + d4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sacc[i][j] = fmaf(qv[i].x, kv[j].x, sacc[i][j]);
+          sacc[i][j] = fmaf(qv[i].y, kv[j].y, sacc[i][j]);
+          sacc[i][j] = fmaf(qv[i].z, kv[j].z, sacc[i][j]);
+          sacc[i][j] = fmaf(qv[i].w, kv[j].w, sacc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int jr = q0 + 4 * ty + i;                 // query index inside the chunk
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ic = kt * 64 + tx + 16 * j;         // key index inside the chunk
+        const float v = (ic <= jr) ? sacc[i][j] : 0.f;
+        asum[i] += fabsf(v);
+        Ss[(4 * ty + i) * kLD + tx + 16 * j] = v;
+      }
+    }
+    __syncthreads();
+    mac_lr(Ss, Vs);
+  }
+  // row-wise |.| sums across the 16 tx lanes of a row
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) asum[i] += __shfl_xor_sync(0xffffffffu, asum[i], off);
+  }
+  const float cross = (c > 0) ? cross_scale[(static_cast<size_t>(n) * 4 + h) * n_chunks + c] : 1.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int jr = q0 + 4 * ty + i;
+    const float sq = sqrtf(static_cast<float>(jr + 1));
+    const float inner = fmaxf(1.f, asum[i] / sq);
+    const float den = sq * fmaxf(inner, cross);
+    float r[4] = {o[i][0] / den, o[i][1] / den, o[i][2] / den, o[i][3] / den};
+    float sm = r[0] + r[1] + r[2] + r[3];
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, off);
+    const float mean = sm * (1.f / 64.f);
+    float m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m2 = fmaf(r[j] - mean, r[j] - mean, m2);
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);
+    const float rstd = 1.f / sqrtf(m2 * (1.f / 64.f) + 1e-6f);
+    if (jr < chunk) {
+      const size_t grow = (static_cast<size_t>(b) * T + static_cast<size_t>(c) * chunk + jr) * S + s;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(qkvg + grow * 1024 + 768 + h * 64) + tx);
+      const float gg[4] = {g.x, g.y, g.z, g.w};
+      float4 ov;
+      ov.x = (r[0] - mean) * rstd * (gg[0] / (1.f + expf(-gg[0])));
+      ov.y = (r[1] - mean) * rstd * (gg[1] / (1.f + expf(-gg[1])));
+      ov.z = (r[2] - mean) * rstd * (gg[2] / (1.f + expf(-gg[2])));
+      ov.w = (r[3] - mean) * rstd * (gg[3] / (1.f + expf(-gg[3])));
+      *reinterpret_cast<float4*>(out + grow * 256 + h * 64 + 4 * tx) = ov;
+    }
+  }
+}
+
+// Recurrent retention step (modules/retention.py:126-144), fp32 in / fp32 state / fp32 out; see elementwise.cu.
+__global__ void __launch_bounds__(64)
+p32_ret_step_kernel(const float* __restrict__ qkvg, float* __restrict__ state, int t_arg, const int* __restrict__ t_dev,
+                    float* __restrict__ out) {
+  const int n = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
+  const int t = t_dev ? *t_dev : t_arg;
+  __shared__ float q_s[64], k_s[64], red[2];
+  const float* row = qkvg + static_cast<size_t>(n) * 1024 + h * 64;
+  q_s[d] = row[d];
+  k_s[d] = row[256 + d];
+  const float v = row[512 + d];
+  const float g = row[768 + d];
+  __syncthreads();
+  float* st = state + (static_cast<size_t>(n) * 4 + h) * 4096;
+  const float a = sqrtf(static_cast<float>(t)) / sqrtf(static_cast<float>(t + 1));
+  const float bsc = 1.f / sqrtf(static_cast<float>(t + 1));
+  float o = 0.f;
+#pragma unroll 8
+  for (int e = 0; e < 64; ++e) {
+    float kv = st[e * 64 + d];
+    kv = (t > 0 ? kv * a : 0.f) + k_s[e] * v * bsc;
+    st[e * 64 + d] = kv;
+    o = fmaf(q_s[e], kv, o);
+  }
+  float sm = o;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, off);
+  if ((d & 31) == 0) red[d >> 5] = sm;
+  __syncthreads();
+  const float mean = (red[0] + red[1]) * (1.f / 64.f);
+  __syncthreads();
+  float dv = (o - mean) * (o - mean);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) dv += __shfl_xor_sync(0xffffffffu, dv, off);
+  if ((d & 31) == 0) red[d >> 5] = dv;
+  __syncthreads();
+  const float rstd = 1.f / sqrtf((red[0] + red[1]) * (1.f / 64.f) + 1e-6f);
+  out[static_cast<size_t>(n) * 256 + h * 64 + d] = (o - mean) * rstd * (g / (1.f + expf(-g)));
+}
+
+__global__ void p32_hist_append_kernel(const float* __restrict__ src, float* __restrict__ hist, int cap, int pos_arg,
+                                       const int* __restrict__ pos_dev) {
+  const int n = blockIdx.x;
+  const int pos = pos_dev ? *pos_dev : pos_arg;
+  hist[(static_cast<size_t>(n) * cap + pos) * 256 + threadIdx.x] = src ? src[static_cast<size_t>(n) * 256 + threadIdx.x] : 0.f;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P32GemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(p32_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    attr_set = true;
+  }
+  const int tiles_per_seq = (p.rows_per_seq + BM - 1) / BM;
+  const int grid = p.n_seq * tiles_per_seq * (p.N / BN);
+  p32_gemm_kernel<<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
+}
+
+void launch_p32_layernorm(const float* x, int rows, const float* g1, const float* b1, float* out1, const float* g2,
+                          const float* b2, float* out2, float eps, const int* seq_len, int rows_per_seq,
+                          cudaStream_t st) {
+  if (rows <= 0) return;
+  p32_layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, g1, b1, out1, g2, b2, out2, eps, seq_len,
+                                                      rows_per_seq > 0 ? rows_per_seq : rows);
+}
+
+void launch_p32_pad_input(const float* x, const int* cu, int B, int Tmax, int Din, int Kpad, float* out, cudaStream_t st) {
+  p32_pad_input_kernel<<<B * Tmax, 128, 0, st>>>(x, cu, Tmax, Din, Kpad, out);
+}
+
+void launch_p32_glu(const float* h, int rows, float* out, cudaStream_t st) {
+  const size_t n4 = static_cast<size_t>(rows) * 64;
+  if (n4 == 0) return;
+  p32_glu_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(h, n4, out);
+}
+
+int launch_p32_dwconv_bn_swish(const float* u, const float* w, const float* sc, const float* sh, int n_seq, int T, int K,
+                               float* hist, float* out, cudaStream_t st) {
+  if (K < 1 || K > 32) return -1;
+  p32_dwconv_bn_swish_kernel<<<dim3((T + 7) / 8, n_seq), 256, 0, st>>>(u, w, sc, sh, T, K, hist, out);
+  return 0;
+}
+
+void launch_p32_l2norm(float* x, int rows, cudaStream_t st) {
+  if (rows <= 0) return;
+  p32_l2norm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows);
+}
+
+void launch_p32_convert(const float* y, const float* pe_proj, int rows, int S, float* out, cudaStream_t st) {
+  const size_t n4 = static_cast<size_t>(rows) * S * 64;
+  if (n4 == 0) return;
+  p32_convert_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(y, pe_proj, n4, S, out);
+}
+
+int launch_p32_spk_attn(const float* qkv, float* out, int n_frames, int S, float scale, cudaStream_t st) {
+  if (S < 1 || S > kMaxS) return -1;
+  const long long n = static_cast<long long>(n_frames) * S * 4;
+  if (n == 0) return 0;
+  p32_spk_attn_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(qkv, out, n_frames, S, scale);
+  return 0;
+}
+
+void launch_p32_head(const float* emb, const float* att, int n_frames, int S, float* logits, float* emb_out,
+                     float* att_out, cudaStream_t st) {
+  if (n_frames <= 0) return;
+  p32_head_kernel<<<(n_frames + 7) / 8, 256, 0, st>>>(emb, att, n_frames, S, logits, emb_out, att_out);
+}
+
+void launch_p32_ret_chunk_state(const float* qkvg, int B, int S, int T, int chunk, float* state, float* cross_scale,
+                                cudaStream_t st) {
+  p32_ret_chunk_state_kernel<<<B * S * 4, 256, 0, st>>>(qkvg, S, T, chunk, T / chunk, state, cross_scale);
+}
+
+void launch_p32_retention(const float* qkvg, const float* state, const float* cross_scale, int B, int S, int T,
+                          int chunk, float* out, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(p32_retention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRetSmem);
+    attr_set = true;
+  }
+  const int nc = T / chunk;
+  dim3 grid((chunk + 63) / 64, 4, B * S * nc);
+  p32_retention_kernel<<<grid, 256, kRetSmem, st>>>(qkvg, state, cross_scale, S, T, chunk, nc, out);
+}
+
+void launch_p32_ret_step(const float* qkvg, float* state, int n_seq, int t, float* out, cudaStream_t st,
+                         const int* t_dev) {
+  p32_ret_step_kernel<<<dim3(n_seq, 4), 64, 0, st>>>(qkvg, state, t, t_dev, out);
+}
+
+void launch_p32_hist_append(const float* src, float* hist, int n_seq, int cap, int pos, cudaStream_t st,
+                            const int* pos_dev) {
+  p32_hist_append_kernel<<<n_seq, 256, 0, st>>>(src, hist, cap, pos, pos_dev);
+}
+
+}  // namespace fseend

@@ -48,6 +48,8 @@ EXPORTS = [
     "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
     "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes", "fseend_op_spk_qkv_attn", "fseend_op_decide_median", "fseend_op_label_prepare", "fseend_op_splice_subsample",
     "fseend_op_bce_loss", "fseend_op_bce_loss_workspace_bytes",
+    "fseend_ls_forward_host", "fseend_ls_set_option", "fseend_ls_get_option", "fseend_p32_linear_create",
+    "fseend_p32_linear_destroy", "fseend_p32_linear_apply", "fseend_op_p32_retention",
 ]
 
 
@@ -104,6 +106,20 @@ def lib() -> C.CDLL:
     L.fseend_ls_forward.argtypes = [vp, vp, C.POINTER(ip), ip, ip, vp, vp, vp, vp]
     L.fseend_ls_launches_per_forward.restype = ip
     L.fseend_ls_launches_per_forward.argtypes = [vp]
+    L.fseend_ls_forward_host.restype = ip
+    L.fseend_ls_forward_host.argtypes = [vp, vp, C.POINTER(ip), ip, ip, vp, vp, vp]
+    L.fseend_ls_set_option.restype = ip
+    L.fseend_ls_set_option.argtypes = [vp, C.c_char_p, ip]
+    L.fseend_ls_get_option.restype = ip
+    L.fseend_ls_get_option.argtypes = [vp, C.c_char_p]
+    L.fseend_p32_linear_create.restype = ip
+    L.fseend_p32_linear_create.argtypes = [vp, ip, ip, C.POINTER(vp)]
+    L.fseend_p32_linear_destroy.restype = None
+    L.fseend_p32_linear_destroy.argtypes = [vp]
+    L.fseend_p32_linear_apply.restype = ip
+    L.fseend_p32_linear_apply.argtypes = [vp, vp, ip, vp, ip, fp, vp, vp, vp]
+    L.fseend_op_p32_retention.restype = ip
+    L.fseend_op_p32_retention.argtypes = [vp, ip, ip, ip, ip, vp, vp]
     L.fseend_ls_stream_create.restype = ip
     L.fseend_ls_stream_create.argtypes = [vp, ip, ip, C.POINTER(vp)]
     L.fseend_ls_stream_destroy.restype = None
@@ -354,6 +370,32 @@ class LsModel:
                                          _stream()))
         return logits, emb, att
 
+    def forward_host(self, x_packed: torch.Tensor, ilens: Sequence[int], max_nspks: int,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host-buffer entry point (H2D + forward + D2H inside the call).  x_packed: CPU fp32; returns CPU logits
+        [B, Tp, S]."""
+        if x_packed.is_cuda or x_packed.dtype != torch.float32 or not x_packed.is_contiguous():
+            raise FseendError("forward_host takes a contiguous CPU float32 tensor")
+        B = len(ilens)
+        if x_packed.shape[0] != int(sum(ilens)) or x_packed.shape[1] != self.cfg["in_size"]:
+            raise FseendError("x_packed shape does not match ilens / in_size")
+        Tp = int(self._L.fseend_ls_padded_len(self._h, int(max(ilens))))
+        logits = out if out is not None else torch.empty(B, Tp, max_nspks, dtype=torch.float32)
+        il = (C.c_int * B)(*[int(i) for i in ilens])
+        _check(self._L.fseend_ls_forward_host(self._h, _ptr(x_packed), il, B, max_nspks, _ptr(logits), None, None))
+        return logits
+
+    PRECISIONS = {"fp16": 0, "fp32": 1, "parity": 1}
+
+    def set_precision(self, mode: str):
+        """"fp32" / "parity" (default): fp32 activations + split-precision tcgen05 GEMMs, logits within 1e-3 of the
+        reference everywhere; "fp16": fp16-operand throughput mode.  Streams created afterwards inherit it."""
+        _check(self._L.fseend_ls_set_option(self._h, b"precision", self.PRECISIONS[mode]))
+
+    @property
+    def precision(self) -> str:
+        return "fp32" if int(self._L.fseend_ls_get_option(self._h, b"precision")) == 1 else "fp16"
+
     @property
     def launches_per_forward(self) -> int:
         return int(self._L.fseend_ls_launches_per_forward(self._h))
@@ -542,6 +584,54 @@ def op_retention(qkvg: torch.Tensor, chunk: int) -> torch.Tensor:
     cs = torch.ones(B * S * 4 * nc, device=qkvg.device, dtype=torch.float32)
     out = torch.empty(B, T, S, 256, device=qkvg.device, dtype=torch.float16)
     _check(lib().fseend_op_retention(_ptr(qkvg), B, S, T, chunk, _ptr(state), _ptr(cs), _ptr(out), _stream()))
+    return out
+
+
+class P32Linear:
+    """Linear layer of the parity path: fp32 weights split once into fp16 hi + lo, applied with three tcgen05 MMAs per
+    product on fp32 activations.  w: fp32 [N, K] (any device; staged through the host once)."""
+
+    def __init__(self, w: torch.Tensor):
+        self._L = lib()
+        wh = w.detach().to(device="cpu", dtype=torch.float32).contiguous()
+        self.N, self.K = int(wh.shape[0]), int(wh.shape[1])
+        if not torch.cuda.is_available():
+            raise FseendError("fseend_b200 requires a CUDA (sm_100) device; there is no CPU fallback")
+        h = C.c_void_p()
+        _check(self._L.fseend_p32_linear_create(_ptr(wh), self.N, self.K, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.fseend_p32_linear_destroy(h)
+
+    def __call__(self, a: torch.Tensor, *, bias=None, act: int = 0, alpha: float = 1.0, residual=None) -> torch.Tensor:
+        _require_cuda(a, bias, residual)
+        if a.dtype != torch.float32 or a.dim() != 2 or a.shape[1] != self.K:
+            raise FseendError("a must be float32 [rows, K]")
+        out = torch.empty(a.shape[0], self.N, device=a.device, dtype=torch.float32)
+        _check(self._L.fseend_p32_linear_apply(self._h, _ptr(a), a.shape[0], _ptr(bias), int(act), float(alpha),
+                                               _ptr(residual), _ptr(out), _stream()))
+        return out
+
+
+def op_p32_gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = 0, alpha: float = 1.0, residual=None):
+    """One-shot form of P32Linear: CUDA fp32 [rows, K] x fp32 [N, K]^T -> CUDA fp32 [rows, N]."""
+    lin = P32Linear(w)
+    out = lin(a, bias=bias, act=act, alpha=alpha, residual=residual)
+    torch.cuda.current_stream().synchronize()      # the weights are released with `lin`
+    return out
+
+
+def op_p32_retention(qkvg: torch.Tensor, chunk: int) -> torch.Tensor:
+    """qkvg: CUDA fp32 [B, T, S, 1024] -> fp32 [B, T, S, 256]."""
+    _require_cuda(qkvg)
+    if qkvg.dtype != torch.float32:
+        raise FseendError("qkvg must be float32")
+    B, T, S, _ = qkvg.shape
+    out = torch.empty(B, T, S, 256, device=qkvg.device, dtype=torch.float32)
+    _check(lib().fseend_op_p32_retention(_ptr(qkvg), B, S, T, chunk, _ptr(out), _stream()))
     return out
 
 

@@ -137,6 +137,19 @@ int fseend_ls_padded_len(const fseend_ls_model* m, int max_ilen);
 int fseend_ls_forward(fseend_ls_model* m, const float* x_packed_dev, const int* ilens_host, int B, int max_nspks,
                       float* logits_dev, float* emb_dev, float* att_dev, void* stream);
 int fseend_ls_launches_per_forward(const fseend_ls_model* m);
+/* Host-buffer form of fseend_ls_forward (packed features and outputs in host memory; H2D + forward + D2H inside the
+ * call, synchronous on return): what bench.py's end-to-end leg times for LS-EEND.  Outputs are padded to
+ * Tp = fseend_ls_padded_len(max ilen). */
+int fseend_ls_forward_host(fseend_ls_model* m, const float* x_packed_host, const int* ilens_host, int B, int max_nspks,
+                           float* logits_host, float* emb_host, float* att_host);
+/* Options.  "precision": 1 (default) = parity mode — fp32 activations, split-precision (hi + lo fp16, three
+ * tcgen05.mma per product) GEMMs, fp32 retention core: logits within 1e-3 max-abs of the reference on every frame
+ * (LS-EEND/nnet/modules/retention.py:222-226: the eps = 1e-6 per-head group norm amplifies operand rounding);
+ * 0 = throughput mode — fp16 operands / fp16 activations (median error 2-3e-4, isolated frames up to 7e-2).
+ * The environment variable FSEEND_LS_PRECISION=fp16|fp32 sets the default at creation.  Streams inherit the model's
+ * precision when they are created. */
+int fseend_ls_set_option(fseend_ls_model* m, const char* key, int value);
+int fseend_ls_get_option(const fseend_ls_model* m, const char* key);
 
 /* One-step (recurrent) LS-EEND.  State per stream: retention states + conv caches (O(1) per frame) and the encoder
  * history of the look-ahead conv.  fseend_ls_stream_step is the fused loop body of streaming_predict
@@ -234,6 +247,21 @@ int fseend_op_dwconv_bn_swish(const void* u_f16, const float* w, const float* sc
                               int T, int K, void* hist_f16, void* out_f16, void* stream);
 /* Recurrent retention step for 0-based frame index t: state fp32 [n_seq][4][64][64] updated in place. */
 int fseend_op_ret_step(const void* qkvg_f16, float* state, int n_seq, int t, void* out_f16, void* stream);
+
+/* Parity-precision kernels (csrc/p32.cu).
+ * fseend_p32_linear_*: a linear layer with split-precision weights (w fp32 [N][K] in HOST memory, split into fp16
+ *   hi + lo once at creation; K % 64 == 0, N % 128 == 0).  apply: out[rows][N] = residual + alpha * act(a[rows][K] w^T
+ *   + bias), fp32 device buffers, asynchronous on `stream`; act: 0 none, 1 ReLU, 2 swish.  Replaces nn.Linear /
+ *   nn.Conv1d-as-GEMM call sites where the fp16 pipeline is not accurate enough (StreamingConv1d of the LS-EEND model
+ *   file :151-186 in parity mode).
+ * fseend_op_p32_retention: qkvg fp32 [B][T][S][1024] -> out fp32 [B][T][S][256] = swish(g) * GroupNorm(retention),
+ *   LS-EEND/nnet/modules/retention.py:146-194,222-224 in fp32. */
+typedef struct fseend_p32_linear fseend_p32_linear;
+int fseend_p32_linear_create(const float* w_host, int N, int K, fseend_p32_linear** out);
+void fseend_p32_linear_destroy(fseend_p32_linear* h);
+int fseend_p32_linear_apply(const fseend_p32_linear* h, const float* a_dev, int rows, const float* bias_dev, int act,
+                            float alpha, const float* residual_dev, float* out_dev, void* stream);
+int fseend_op_p32_retention(const float* qkvg_dev, int B, int S, int T, int chunk, float* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -416,6 +416,38 @@ def random_state_dict(seed: int = 0, in_size: int = 345, n_units: int = 256, n_h
     return sd
 
 
+def wide_state_dict(seed: int = 0, alpha: float = 1.5, S: int = 6) -> SD:
+    """Synthetic weights whose logits use most of the cosine range: default random weights give logits with std ~0.02
+    (range -0.2..0.1), so a 1e-3 absolute bound is ~5 % of the signal.  Here the attractor init passes the embedding
+    through (convert = alpha * I + noise on the embedding half; the positional half maps slot s onto a designed offset
+    of growing size) and the decoder layers are near-identity, so logits span alpha > 0: +0.15..+0.97 over the slots,
+    alpha < 0: -0.97..-0.2."""
+    sd = random_state_dict(seed=seed, trained_like=True)
+    D = sd["dec.convert.weight"].shape[0]
+    g = torch.Generator().manual_seed(1000 + seed)
+    pe = sd["dec.pos_enc.pe"][0, :S]
+    targets = torch.randn(S, D, generator=g)
+    targets = targets / targets.norm(dim=1, keepdim=True)
+    beta = torch.tensor([0.0, 0.15, 0.4, 0.8, 1.6, 4.0, 6.0, 8.0, 10.0, 12.0, 14.0, 16.0, 18.0, 20.0, 22.0, 24.0])[:S]
+    targets = targets * (beta * abs(alpha))[:, None]
+    M = targets.T @ torch.linalg.pinv(pe.T)                    # M pe_s = target_s
+    W = sd["dec.convert.weight"].clone()
+    W[:, :D] = alpha * torch.eye(D) + 0.1 * W[:, :D]
+    W[:, D:] = M
+    sd["dec.convert.weight"] = W
+    sd["dec.convert.bias"] = sd["dec.convert.bias"] * 0.05
+    n_dec = len({k.split(".")[3] for k in sd if k.startswith("dec.attractor_decoder.layers.")})
+    for l in range(n_dec):
+        p = f"dec.attractor_decoder.layers.{l}."
+        for k in ("self_attn1.out_proj", "self_attn2.out_proj", "linear2"):
+            sd[p + k + ".weight"] = sd[p + k + ".weight"] * 0.1
+            sd[p + k + ".bias"] = sd[p + k + ".bias"] * 0.1
+        for nm in ("norm11", "norm21", "norm22"):
+            sd[p + nm + ".weight"] = torch.ones(D) + 0.05 * (sd[p + nm + ".weight"] - 1)
+            sd[p + nm + ".bias"] = sd[p + nm + ".bias"] * 0.05
+    return sd
+
+
 def synthetic_features(B: int, T: int, in_size: int = 345, seed: int = 777, lens: Optional[Sequence[int]] = None):
     """x ~ N(0,1) float32 (T_i, 345) per item, seed 777."""
     g = torch.Generator().manual_seed(seed)

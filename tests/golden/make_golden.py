@@ -48,9 +48,54 @@ CASES = {
 }
 
 
+WIDE_CASES = {
+    # name: (weight seed, alpha, lens, max_nspks): logits spanning most of the cosine range (oracle.wide_state_dict)
+    "wide_pos_S6": (0, 1.5, [300, 211], 6),
+    "wide_neg_S6": (1, -1.5, [300, 211], 6),
+}
+
+
+def wide_goldens():
+    """Wide-dynamic-range weight sets: masked-model logits, plus (for the first) the streaming model's frame loop and the
+    reference's own sigmoid-space self-check (streaming_infer_dia.py:97: allclose(stream, masked, atol=rtol=1e-4))."""
+    for name, (wseed, alpha, lens, S) in WIDE_CASES.items():
+        sd = O.wide_state_dict(seed=wseed, alpha=alpha, S=S)
+        ref = build_ref(sd)
+        src, lens = O.synthetic_features(len(lens), max(lens), lens=lens)
+        with torch.no_grad():
+            out, _, _ = ref.test(src, lens, max_nspks=S)
+        rec = {f"logits_{i}": o.numpy() for i, o in enumerate(out)}
+        if alpha > 0:
+            stream = StreamingTransformerEDADiarization(
+                in_size=345, n_units=256, n_heads=4, enc_n_layers=4, dec_n_layers=2, dropout=0.1, has_mask=True,
+                max_seqlen=500, dec_dim_feedforward=2048).eval()
+            copy_params_from_masked_to_streaming(ref, stream)
+            T = 120
+            with torch.no_grad():
+                ys = []
+                for t in range(T):
+                    y = stream.test(src[0][None, t:t + 1], max_nspks=S)
+                    if y is not None:
+                        ys.append(y)
+                for _ in range(9):
+                    ys.append(stream.test(torch.zeros(1, 1, 345), max_nspks=S, dummy_conv_input=True))
+                ys = torch.cat(ys, dim=1)[0]
+                masked = ref.test([src[0][:T]], [T], max_nspks=S)[0][0]
+            ok = torch.allclose(torch.sigmoid(ys[:, 1:]), torch.sigmoid(masked[:, 1:]), atol=1e-4, rtol=1e-4)
+            print(name, "reference self-check (sigmoid space, 1e-4):", ok, (ys - masked).abs().max().item())
+            rec["stream"] = ys.numpy()
+            rec["stream_masked"] = masked.numpy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+        y = torch.cat([o.flatten() for o in out])
+        print(name, "logit range", y.min().item(), y.max().item(), "std", y.std().item())
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "wide":
+        wide_goldens()
+        return
     for name, (wseed, trained, lens, S, md) in CASES.items():
         sd = O.random_state_dict(seed=wseed, trained_like=trained)
         ref = build_ref(sd, mask_delay=md)

@@ -92,10 +92,40 @@ def forward_loss_golden():
     print("ls_forward_loss_S6: loss", loss.item(), [tuple(o.shape) for o in out], tuple(att[1].shape))
 
 
+BIG_CASES = {
+    # BASELINE.json configs[2] shape: B=16 recordings x T=2000 frames, 8 speakers (+2 slots); one recording shorter
+    "ls_B16_T2000_S10": (4, True, [2000] * 15 + [1711], 10),
+}
+
+
+def big_goldens():
+    """BASELINE-shape batch golden (logits only, 1.3 MB) and a long one-step golden (T = 2000 frames through the real
+    streaming_predict loop: 4 retention chunks' worth of recurrent state, S = 10)."""
+    for name, (wseed, trained, lens, S) in BIG_CASES.items():
+        sd = O.random_state_dict(seed=wseed, trained_like=trained)
+        ref = build_ref(sd)
+        src, lens = FO.synthetic_features(len(lens), max(lens), lens=lens)
+        with torch.no_grad():
+            out, _, _ = ref.test(src, lens, max_nspks=S)
+        rec = {f"logits_{i}": o.numpy() for i, o in enumerate(out)}
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+        print(name, [tuple(o.shape) for o in out][:2], "max|logit|", max(o.abs().max().item() for o in out))
+    sd = O.random_state_dict(seed=5, trained_like=True)
+    ref = build_ref(sd)
+    src, lens = FO.synthetic_features(1, 2000)
+    with torch.no_grad():
+        ys = streaming_predict(ref, src[0], 10)
+    np.savez_compressed(os.path.join(HERE, "ls_stream_T2000_S10.npz"), stream=ys.numpy())
+    print("ls_stream_T2000_S10", tuple(ys.shape), "max|logit|", ys.abs().max().item())
+
+
 def main():
     torch.set_num_threads(8)
     if len(sys.argv) > 1 and sys.argv[1] == "forward_loss":
         forward_loss_golden()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        big_goldens()
         return
     forward_loss_golden()
     for name, (wseed, trained, lens, S) in CASES.items():

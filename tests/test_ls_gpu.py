@@ -1,11 +1,12 @@
-"""LS-EEND on B200: per-kernel parity of the LS-specific kernels against torch fp32 on the same fp16 operands, and
-the end-to-end forward against golden logits of the real reference.
+"""LS-EEND on B200: per-kernel parity of the LS-specific kernels, and the end-to-end forward / one-step paths against
+golden logits of the real reference, in BOTH precision modes.
 
-End-to-end tolerance.  The LS-EEND network amplifies operand rounding at isolated frames (per-head LayerNorm, eps 1e-6,
-over near-constant retention outputs): emulating fp16 operands in the CPU oracle gives median 1.6e-4 / p99 2.6e-3 /
-max 2.3e-2 on these synthetic weights, and only a split-precision (hi+lo fp16, 3 MMAs) path reaches 1e-4 everywhere
-(DESIGN.md §1).  The tests therefore assert median < 1e-3, p95 < 1e-2 and max < 0.15, and print the distribution;
-the north-star max-abs 1e-3 bound is NOT met on the tail for LS-EEND in this round."""
+PARITY mode ("fp32", the default: fp32 activations, split-precision tcgen05 GEMMs, fp32 retention core — csrc/p32.cu):
+every end-to-end test asserts max-abs logit error < 1e-3, the north-star tolerance, on every frame.
+THROUGHPUT mode ("fp16": fp16 operands and activations): the LS-EEND network amplifies operand rounding at isolated
+frames (per-head LayerNorm, eps 1e-6, over near-constant retention outputs), so this mode is checked on
+the error DISTRIBUTION (median < 1e-3, p95 < 1e-2) and its maximum is printed, not bounded at 1e-3."""
+TOL = 1e-3          # north-star: logits within 1e-3 max-abs of the reference
 import math
 import os
 
@@ -145,7 +146,7 @@ def test_retention_step_matches_chunkwise_first_chunk(N):
     assert (outs.float() - ref).abs().max().item() < 5e-3
 
 
-def make_ls_model(sd):
+def make_ls_model(sd, precision="fp32"):
     from nnet.model.onl_conformer_retention_enc_1dcnn_tfm_retention_enc_linear_non_autoreg_pos_enc_l2norm_emb_loss_mask import (
         OnlineConformerRetentionDADiarization)
     m = OnlineConformerRetentionDADiarization(
@@ -153,72 +154,166 @@ def make_ls_model(sd):
         max_seqlen=1000, recurrent_chunk_size=500, feed_forward_expansion_factor=4, dec_dim_feedforward=2048,
         conv_kernel_size=16)
     m.load_state_dict(sd, strict=True)
-    return m.cuda().eval()
+    m = m.cuda().eval()
+    m.set_precision(precision)
+    assert m.native().precision == precision
+    return m
 
 
+def check_errs(label, errs, precision):
+    med, p95, p99, mx = np.median(errs), np.percentile(errs, 95), np.percentile(errs, 99), errs.max()
+    print(f"{label} [{precision}]: logit error vs reference  median {med:.2e}  p95 {p95:.2e}  p99 {p99:.2e}  max {mx:.2e}")
+    if precision == "fp32":
+        assert mx < TOL, f"parity mode must meet {TOL} on every frame, got {mx:.3e}"
+    else:
+        assert med < 1e-3 and p95 < 1e-2      # throughput mode: distribution only (module docstring)
+
+
+# ------------------------------------------------------------------------------------------- parity-mode kernels
+def test_p32_split_gemm_matches_fp64(N):
+    """Three-MMA split-precision GEMM vs an fp64 product of the same fp32 operands: ~1e-6 relative (fp16 operands: 1e-3)."""
+    a = rnd(389, 1024, seed=41) * 3.0
+    w = rnd(256, 1024, scale=1 / 32, seed=42)
+    bias = rnd(256, seed=43) * 0.3
+    res = rnd(389, 256, seed=44)
+    out = N.op_p32_gemm(a, w, bias=bias, alpha=0.5, residual=res)
+    ref = (res.double() + 0.5 * (a.double() @ w.double().T + bias.double()))
+    err = (out.double() - ref).abs().max().item()
+    print(f"p32 gemm K=1024: max abs err {err:.2e} (|ref| max {ref.abs().max().item():.1f})")
+    assert err < 2e-5
+    # swish epilogue, N = 1024, a weight matrix with large entries (power-of-two pre-scale must not overflow fp16)
+    w2 = rnd(1024, 256, scale=4.0, seed=45)
+    out2 = N.op_p32_gemm(a[:, :256].contiguous(), w2, bias=None, act=2)
+    h = a[:, :256].double() @ w2.double().T
+    ref2 = h * torch.sigmoid(h)
+    rel = (out2.double() - ref2).abs().max().item() / ref2.abs().max().item()      # error relative to the output scale
+    print(f"p32 gemm swish, |w| up to {w2.abs().max().item():.0f}: max err / max|ref| = {rel:.2e}")
+    assert torch.isfinite(out2).all() and rel < 3e-6
+
+
+def test_p32_linear_handle_reuse_and_small_rows(N):
+    lin = N.P32Linear(rnd(128, 4864, scale=0.02, seed=46))
+    for rows in (1, 5, 130):
+        a = rnd(rows, 4864, seed=47 + rows)
+        out = lin(a)
+        ref = a.double() @ rnd(128, 4864, scale=0.02, seed=46).double().T
+        assert (out.double() - ref).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("B,T,S,chunk", [(2, 500, 1, 500), (1, 1000, 3, 500), (1, 384, 2, 128), (1, 1500, 2, 500)])
+def test_p32_retention_chunkwise(N, B, T, S, chunk):
+    """fp32 retention core (chunk state + intra-chunk + group norm + gate) vs the fp64 evaluation of the same algebra."""
+    qkvg = rnd(B, T, S, 1024, scale=0.7, seed=60 + T)
+    out = N.op_p32_retention(qkvg, chunk)
+    ref = retention_ref(qkvg.double(), chunk)
+    err = (out.double() - ref).abs()
+    print(f"p32 retention B={B} T={T} S={S}: max {err.max().item():.2e} mean {err.mean().item():.2e}")
+    assert err.max().item() < 2e-3 and err.mean().item() < 2e-6     # group norm (eps 1e-6) amplifies fp32 rounding
+
+
+# ------------------------------------------------------------------------------------------- end to end
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
 @pytest.mark.parametrize("name", list(LS_CASES))
-def test_ls_logits_vs_reference_golden(name):
+def test_ls_logits_vs_reference_golden(name, precision):
     sd, src, lens, S, g = load_ls_case(name)
-    m = make_ls_model(sd)
+    m = make_ls_model(sd, precision)
     out, emb, att = m.test([s.cuda() for s in src], lens, max_nspks=S)
     errs = np.concatenate([np.abs(o.cpu().numpy() - g[f"logits_{i}"]).ravel() for i, o in enumerate(out)])
-    med, p95, p99, mx = np.median(errs), np.percentile(errs, 95), np.percentile(errs, 99), errs.max()
-    print(f"{name}: logit error vs reference  median {med:.2e}  p95 {p95:.2e}  p99 {p99:.2e}  max {mx:.2e}")
     assert all(tuple(o.shape) == g[f"logits_{i}"].shape for i, o in enumerate(out))
     assert att[0].shape == (lens[0], S, 256) and emb[0].shape == (lens[0], 256)
-    assert med < 1e-3 and p95 < 1e-2 and mx < 0.15
+    check_errs(name, errs, precision)
+    if precision == "fp32":
+        stride = int(g["emb_stride"][0])
+        assert np.abs(emb[0].cpu().numpy()[::stride] - g["emb_0"]).max() < TOL
 
 
-def test_ls_forward_api_and_masked_emb_consistency_loss():
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_ls_baseline_shape_B16_T2000_S10(precision):
+    """BASELINE.json configs[2]: 16 recordings x 2000 frames, 10 attractor slots, vs the real reference's logits."""
+    from test_oracle_ls import load_ls_big_case
+    sd, src, lens, S, g = load_ls_big_case()
+    m = make_ls_model(sd, precision)
+    out = m.test_logits([s.cuda() for s in src], lens, max_nspks=S)
+    errs = np.concatenate([np.abs(o.cpu().numpy() - g[f"logits_{i}"]).ravel() for i, o in enumerate(out)])
+    assert all(tuple(o.shape) == g[f"logits_{i}"].shape for i, o in enumerate(out))
+    check_errs("ls_B16_T2000_S10", errs, precision)
+    # host-buffer entry point returns the same logits
+    x = torch.cat([s[:l] for s, l in zip(src, lens)]).contiguous()
+    yh = m.native().forward_host(x, lens, S)
+    for i, l in enumerate(lens):
+        assert torch.equal(yh[i, :l], out[i].cpu()), (yh[i, :l] - out[i].cpu()).abs().max().item()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_ls_forward_api_and_masked_emb_consistency_loss(precision):
     """forward(src, tgt, ilens) vs the real reference's forward (golden): logits sliced [:ilen, :n_spk], attractors
     [:ilen, 1:n_spk], length-masked loss (LS:model:92-113) from the tcgen05 loss kernel."""
     from test_oracle_ls import ls_forward_loss_case
     sd, src, tgt, lens, g = ls_forward_loss_case()
-    m = make_ls_model(sd)
+    m = make_ls_model(sd, precision)
     out, loss, emb, att = m([s.cuda() for s in src], tgt, lens)
     print(f"LS masked emb-consistency loss: {loss.item():.6f} vs reference {float(g['emb_consis_loss']):.6f}")
     assert abs(loss.item() - float(g["emb_consis_loss"])) < 1e-3
     for i in range(2):
-        err = np.abs(out[i].cpu().numpy() - g[f"fwd_logits_{i}"])
-        assert out[i].shape == g[f"fwd_logits_{i}"].shape and np.median(err) < 1e-3 and err.max() < 0.15
+        assert out[i].shape == g[f"fwd_logits_{i}"].shape
+    check_errs("ls_forward", np.concatenate([np.abs(out[i].cpu().numpy() - g[f"fwd_logits_{i}"]).ravel()
+                                             for i in range(2)]), precision)
     assert tuple(att[1].shape) == tuple(g["att_shape_1"]) and emb[1].shape == (lens[1], 256)
 
 
-def test_ls_one_step_fused_stream_vs_reference_golden():
-    """Fused native frame loop vs the reference's streaming_predict output (golden, one-step/recurrent path)."""
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ls_stream_T48_S4.npz"))
-    sd = O.random_state_dict(seed=3)
-    m = make_ls_model(sd)
-    src, _ = FO.synthetic_features(1, 48)
-    x = src[0].cuda()
-    st = m.new_stream(batch_size=1, max_nspks=4)
+def run_fused_stream(m, x, S):
+    T = x.shape[0]
+    st = m.new_stream(batch_size=1, max_nspks=S)
     ys = []
-    for t in range(48):
+    for t in range(T):
         y = st.step(x[t:t + 1].contiguous())
         assert (y is None) == (t < 9)
         if y is not None:
             ys.append(y)
     for _ in range(9):
         ys.append(st.step(None))
-    ys = torch.cat(ys).cpu().numpy()
-    err = np.abs(ys - g["stream"])
-    print(f"LS one-step T=48: error vs reference  median {np.median(err):.2e}  p95 {np.percentile(err, 95):.2e}  max {err.max():.2e}")
+    return torch.cat(ys).cpu().numpy()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_ls_one_step_fused_stream_vs_reference_golden(precision):
+    """Fused native frame loop vs the reference's streaming_predict output (golden, one-step/recurrent path)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ls_stream_T48_S4.npz"))
+    sd = O.random_state_dict(seed=3)
+    m = make_ls_model(sd, precision)
+    src, _ = FO.synthetic_features(1, 48)
+    ys = run_fused_stream(m, src[0].cuda(), 4)
     assert ys.shape == g["stream"].shape
-    assert np.median(err) < 1e-3 and err.max() < 0.15
+    check_errs("LS one-step T=48", np.abs(ys - g["stream"]).ravel(), precision)
 
 
-def test_ls_one_step_reference_api_loop():
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_ls_one_step_long_stream_T2000_S10(precision):
+    """2000 frames (4 retention chunks' worth of recurrent state, history re-allocation at 1024 frames, CUDA-graph
+    replay) through the fused frame loop vs the real reference's streaming_predict (golden)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ls_stream_T2000_S10.npz"))
+    sd = O.random_state_dict(seed=5)
+    m = make_ls_model(sd, precision)
+    src, _ = FO.synthetic_features(1, 2000)
+    ys = run_fused_stream(m, src[0].cuda(), 10)
+    assert ys.shape == g["stream"].shape
+    check_errs("LS one-step T=2000 S=10", np.abs(ys - g["stream"]).ravel(), precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_ls_one_step_reference_api_loop(precision):
     """The reference's own streaming_predict loop (LS-EEND/streaming_infer_dia.py:52-97) run against the drop-in
     API: enc.forward_one_step / StreamingConv1d / dec.forward_one_step with caller-owned state lists."""
     from nnet.model.onl_conformer_retention_enc_1dcnn_tfm_retention_enc_linear_non_autoreg_pos_enc_l2norm_emb_loss_mask import (
         StreamingConv1d)
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ls_stream_T48_S4.npz"))
     sd = O.random_state_dict(seed=3)
-    model = make_ls_model(sd)
+    model = make_ls_model(sd, precision)
     device = "cuda"
     feat = FO.synthetic_features(1, 48)[0][0].to(device)
     max_nspks = 4
     streaming_cnn = StreamingConv1d(model.n_units, model.n_units, kernel_size=2 * model.delay + 1).to(device)
+    streaming_cnn.precision = precision
     streaming_cnn.conv.load_state_dict(model.cnn.state_dict())
     n_enc, n_dec = len(model.enc.encoder.layers), len(model.dec.layers)
     enc_states = {"ret_states": [dict() for _ in range(n_enc)],
@@ -249,6 +344,5 @@ def test_ls_one_step_reference_api_loop():
         if y is not None:
             preds.append(y)
     ys = torch.cat(preds, dim=1).squeeze(0).cpu().numpy()
-    err = np.abs(ys - g["stream"])
-    print(f"LS reference-API loop T=48: median {np.median(err):.2e} max {err.max():.2e}")
-    assert ys.shape == g["stream"].shape and np.median(err) < 1e-3 and err.max() < 0.15
+    assert ys.shape == g["stream"].shape
+    check_errs("LS reference-API loop T=48", np.abs(ys - g["stream"]).ravel(), precision)

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import fs_eend_oracle as O
-from test_oracle import CASES, load_case
+from test_oracle import CASES, WIDE_CASES, load_case, load_wide_case
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -37,6 +37,25 @@ def test_logits_match_reference_golden(name):
         assert np.abs(emb[i].cpu().numpy()[::stride] - g[f"emb_{i}"]).max() < TOL
         assert att[i].shape == (lens[i], S, 256)
     print(f"{name}: max-abs logit error vs reference = {worst:.2e}")
+    assert worst < TOL
+
+
+@pytest.mark.parametrize("name", list(WIDE_CASES))
+def test_wide_dynamic_range_logits_and_sigmoid_space_check(name):
+    """Weights whose logits span most of the cosine range (std 0.26 instead of 0.02): the 1e-3 absolute bound is then
+    0.4 % of the signal.  Also the reference's own acceptance check, in sigmoid space with atol = rtol = 1e-4
+    (FS-EEND/streaming_infer_dia.py:97), against the real reference's logits."""
+    sd, src, lens, S, g = load_wide_case(name)
+    m = make_model(sd)
+    out, _, _ = m.test([s.cuda() for s in src], lens, max_nspks=S)
+    worst = 0.0
+    for i, o in enumerate(out):
+        ref = torch.from_numpy(g[f"logits_{i}"])
+        worst = max(worst, float((o.cpu() - ref).abs().max()))
+        assert torch.allclose(torch.sigmoid(o.cpu()[:, 1:]), torch.sigmoid(ref[:, 1:]), atol=1e-4, rtol=1e-4)
+    print(f"{name}: max-abs logit error vs reference = {worst:.2e} on logits in "
+          f"[{min(float(g[f'logits_{i}'].min()) for i in range(len(lens))):.2f}, "
+          f"{max(float(g[f'logits_{i}'].max()) for i in range(len(lens))):.2f}]")
     assert worst < TOL
 
 
@@ -172,6 +191,54 @@ def test_streaming_matches_reference_stream_golden():
     err = np.abs(ys - g["stream"]).max()
     print(f"streaming T=60: max-abs logit error vs reference frame loop = {err:.2e}")
     assert err < TOL
+
+
+def test_streaming_infer_dia_body_on_wide_logits():
+    """The body of FS-EEND/streaming_infer_dia.py:42-97 on synthetic features: masked model -> load_state_dict with the
+    Lightning 'model.' prefix stripped -> masked test -> copy_params -> frame loop -> flush -> the script's own
+    acceptance check torch.allclose(sigmoid(stream), sigmoid(masked), atol=1e-4, rtol=1e-4); both also against the
+    real reference's outputs for the same weights (golden)."""
+    from nnet.model.onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import OnlineTransformerDADiarization
+    from nnet.model.streaming_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import StreamingTransformerEDADiarization
+    from nnet.utils.copy_params import copy_params_from_masked_to_streaming
+    sd, src, lens, S, g = load_wide_case("wide_pos_S6")
+    device = torch.device("cuda:0")
+    params = dict(n_units=256, n_heads=4, enc_n_layers=4, dec_n_layers=2, dropout=0.1, has_mask=True, max_seqlen=500,
+                  dec_dim_feedforward=2048, conv_delay=9, mask_delay=0)
+    feat = src[0][:120].to(device)
+    masked_model = OnlineTransformerDADiarization(n_speakers=4, in_size=345, **params).to(device)
+    streaming_model = StreamingTransformerEDADiarization(in_size=345, **params).to(device)
+    state_dict = {"model." + k: v for k, v in sd.items()}                     # a Lightning checkpoint's key layout
+    new_state_dict = {(k[len("model."):] if k.startswith("model.") else k): v for k, v in state_dict.items()}
+    masked_model.load_state_dict(new_state_dict)
+    masked_model.eval()
+    with torch.no_grad():
+        masked_pred, _, _ = masked_model.test([feat], [len(feat)], max_nspks=S)
+        masked_logits = masked_pred[0].detach().cpu().float()
+        masked_pred = torch.sigmoid(masked_pred[0][:, 1:]).detach().cpu().float()
+    copy_params_from_masked_to_streaming(masked_model, streaming_model)
+    preds = []
+    streaming_model.eval()
+    with torch.no_grad():
+        for t in range(len(feat)):
+            pred_t = streaming_model.test(feat[t:t + 1].unsqueeze(0), max_nspks=S)
+            if pred_t is not None:
+                preds.append(pred_t)
+        for _ in range(params["conv_delay"]):
+            dummy_feat = torch.zeros(1, 1, feat.shape[-1], device=feat.device)
+            pred_t = streaming_model.test(dummy_feat, max_nspks=S, dummy_conv_input=True)
+            if pred_t is not None:
+                preds.append(pred_t)
+    preds = torch.cat(preds, dim=1)
+    stream_logits = preds[0].detach().cpu().float()
+    pred = torch.sigmoid(preds[0][:, 1:]).detach().cpu().float()
+    print(f"stream vs masked (sigmoid space) max diff {float((pred - masked_pred).abs().max()):.2e}; vs reference: "
+          f"stream {float((stream_logits - torch.from_numpy(g['stream'])).abs().max()):.2e}, "
+          f"masked {float((masked_logits - torch.from_numpy(g['stream_masked'])).abs().max()):.2e} (logits)")
+    assert torch.allclose(pred, masked_pred, atol=1e-4, rtol=1e-4)            # streaming_infer_dia.py:97
+    assert (stream_logits - torch.from_numpy(g["stream"])).abs().max().item() < TOL
+    assert (masked_logits - torch.from_numpy(g["stream_masked"])).abs().max().item() < TOL
+    assert torch.allclose(pred, torch.sigmoid(torch.from_numpy(g["stream"])[:, 1:]), atol=1e-4, rtol=1e-4)
 
 
 def test_streaming_equals_batch_path_two_recordings_and_cache_growth():

@@ -20,6 +20,31 @@ CASES = {
 }
 
 
+# must mirror tests/golden/make_golden.py::WIDE_CASES (logits spanning most of the cosine range)
+WIDE_CASES = {
+    "wide_pos_S6": (0, 1.5, [300, 211], 6),
+    "wide_neg_S6": (1, -1.5, [300, 211], 6),
+}
+
+
+def load_wide_case(name):
+    wseed, alpha, lens, S = WIDE_CASES[name]
+    sd = O.wide_state_dict(seed=wseed, alpha=alpha, S=S)
+    src, lens = O.synthetic_features(len(lens), max(lens), lens=lens)
+    return sd, src, lens, S, np.load(os.path.join(GOLD, name + ".npz"))
+
+
+@pytest.mark.parametrize("name", list(WIDE_CASES))
+def test_oracle_matches_reference_on_wide_logits(name):
+    sd, src, lens, S, g = load_wide_case(name)
+    with torch.no_grad():
+        out, _, _ = O.test(sd, src, lens, S, O.Cfg())
+    allv = np.concatenate([g[f"logits_{i}"].ravel() for i in range(len(lens))])
+    assert allv.max() - allv.min() > 0.7 and allv.std() > 0.2           # the case really is wide
+    for i, o in enumerate(out):
+        assert np.abs(o.numpy() - g[f"logits_{i}"]).max() < 2e-5
+
+
 def load_case(name):
     wseed, trained, lens, S, md = CASES[name]
     sd = O.random_state_dict(seed=wseed, trained_like=trained)

@@ -29,6 +29,23 @@ def load_ls_case(name):
     return sd, src, lens, S, np.load(os.path.join(GOLD, name + ".npz"))
 
 
+def load_ls_big_case():
+    """BASELINE.json configs[2] shape (tests/golden/make_golden_ls.py::big_goldens)."""
+    lens = [2000] * 15 + [1711]
+    sd = O.random_state_dict(seed=4, trained_like=True)
+    src, lens = FO.synthetic_features(len(lens), max(lens), lens=lens)
+    return sd, src, lens, 10, np.load(os.path.join(GOLD, "ls_B16_T2000_S10.npz"))
+
+
+def test_ls_oracle_matches_reference_at_baseline_shape_sample():
+    """One recording of the B=16 x T=2000 x S=10 golden through the oracle (the whole batch takes minutes on CPU)."""
+    sd, src, lens, S, g = load_ls_big_case()
+    with torch.no_grad():
+        out, _, _ = O.test(sd, src[15:16], lens[15:16], S, O.Cfg())
+    assert out[0].shape == g["logits_15"].shape
+    assert np.abs(out[0].numpy() - g["logits_15"]).max() < 3e-4
+
+
 @pytest.mark.parametrize("name", list(LS_CASES))
 def test_ls_oracle_matches_reference(name):
     sd, src, lens, S, g = load_ls_case(name)
