@@ -245,6 +245,132 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ secondary workloads
+def secondary_measurements(dev):
+    """The other BASELINE.json configurations, measured in the same run (rank 0, N = 1) with their own CPU figure beside
+    them: LS-EEND batch inference at B=16 x T=2000 x S=10 (configs[2]) in both precision modes (device-resident, end to
+    end through fseend_ls_forward_host, logit error against the CPU oracle on one recording), frame-by-frame latency
+    of FS-EEND and LS-EEND (configs[4]: the one-hour recording is per-frame latency x 36000, the LS step is O(1))."""
+    import torch
+    from oracle import fs_eend_oracle as FO
+    from oracle import ls_eend_oracle as LO
+    from nnet.model.onl_conformer_retention_enc_1dcnn_tfm_retention_enc_linear_non_autoreg_pos_enc_l2norm_emb_loss_mask import (
+        OnlineConformerRetentionDADiarization)
+    from nnet.model.onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import OnlineTransformerDADiarization
+    from nnet.model.streaming_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import StreamingTransformerEDADiarization
+    from nnet.utils.copy_params import copy_params_from_masked_to_streaming
+
+    def ev_time(fn, warm, iters):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    out = {}
+    ncpu = os.cpu_count() or 1
+    cpu_threads = min(ncpu, 16)
+    torch.set_num_threads(cpu_threads)
+    # ---------------- LS-EEND batch, BASELINE configs[2]
+    LB, LT, LS_ = 16, 2000, 10
+    sd = LO.random_state_dict(seed=4, trained_like=True)
+    ls = OnlineConformerRetentionDADiarization(
+        n_speakers=8, in_size=DIN, n_units=D, n_heads=H, enc_n_layers=4, dec_n_layers=2, dropout=0.1, max_seqlen=1000,
+        recurrent_chunk_size=500, feed_forward_expansion_factor=4, dec_dim_feedforward=FF, conv_kernel_size=16)
+    ls.load_state_dict(sd, strict=True)
+    ls = ls.to(dev).eval()
+    src, lens = FO.synthetic_features(LB, LT)
+    x_host = torch.cat(src).contiguous().pin_memory()
+    x_dev = x_host.to(dev)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        ref0 = LO.test(sd, src[:1], lens[:1], LS_, LO.Cfg())[0][0]
+        cpu_s = time.perf_counter() - t0
+    rec = {"workload": f"LS-EEND fwd B={LB} T={LT} S={LS_} (8-spk), retention chunk 500",
+           "cpu_baseline": {"value": LT / cpu_s, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                            "sample": f"1 recording x {LT} frames, oracle port, torch CPU fp32, {cpu_threads} threads"}}
+    nat = ls.native()
+    out_host = torch.empty(LB, LT, LS_).pin_memory()
+    for mode in ("fp32", "fp16"):
+        nat.set_precision(mode)
+        y = nat.forward(x_dev, lens, LS_)[0]
+        err = (y[0].cpu() - ref0).abs()
+        ms = ev_time(lambda: nat.forward(x_dev, lens, LS_), 2, 5)
+        nat.forward_host(x_host, lens, LS_, out=out_host)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            nat.forward_host(x_host, lens, LS_, out=out_host)
+        e2e_s = (time.perf_counter() - t0) / 3
+        rec[mode] = {"dtype": "fp32 activations, split fp16 hi+lo tensor-core operands (3 MMAs)" if mode == "fp32"
+                     else "fp16 operands and activations, fp32 accumulate",
+                     "ms_per_forward": ms, "frames_per_s": LB * LT / ms * 1e3,
+                     "e2e_frames_per_s": LB * LT / e2e_s, "e2e_api": "fseend_ls_forward_host",
+                     "h2d_bytes": LB * LT * DIN * 4, "d2h_bytes": LB * LT * LS_ * 4,
+                     "launches": nat.launches_per_forward,
+                     "logit_err_vs_oracle": {"max": float(err.max()), "median": float(err.median()),
+                                             "p99": float(err.flatten().kthvalue(int(0.99 * err.numel())).values)}}
+    out["ls_batch_B16_T2000_S10"] = rec
+    # ---------------- LS-EEND frame by frame, B = 1, S = 10 (BASELINE configs[4]: T = 36000 = this latency x 36000)
+    n_cpu_frames = 40
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        LO.stream_all(sd, src[0][None, :n_cpu_frames], LS_, LO.Cfg())
+        cpu_frame = (time.perf_counter() - t0) / (n_cpu_frames + 9)
+    rec = {"workload": "LS-EEND one-step (recurrent) inference, B=1, S=10; 1 hour = 36000 frames of 100 ms",
+           "cpu_baseline": {"ms_per_frame": cpu_frame * 1e3, "real_time_factor": cpu_frame / 0.1, "cores": cpu_threads,
+                            "kind": "port", "sample": f"{n_cpu_frames} frames + flush, oracle port"}}
+    xt = torch.randn(1, DIN, device=dev)
+    for mode in ("fp32", "fp16"):
+        nat.set_precision(mode)
+        st = ls.new_stream(1, LS_)
+        for _ in range(40):
+            st.step(xt)
+        torch.cuda.synchronize()
+        n = 400
+        t0 = time.perf_counter()
+        for _ in range(n):
+            st.step(xt)
+        torch.cuda.synchronize()
+        lat = (time.perf_counter() - t0) / n
+        rec[mode] = {"ms_per_frame": lat * 1e3, "real_time_factor": lat / 0.1, "one_hour_T36000_seconds": lat * 36009,
+                     "frames_timed": n}
+        del st
+    out["ls_stream_B1_S10"] = rec
+    nat.set_precision("fp32")
+    # ---------------- FS-EEND frame by frame, B = 1, S = 6
+    fsd = FO.random_state_dict(seed=0, trained_like=False)
+    kw = dict(in_size=DIN, n_units=D, n_heads=H, enc_n_layers=ENC_L, dec_n_layers=DEC_L, dropout=0.1, has_mask=True,
+              max_seqlen=T, dec_dim_feedforward=FF)
+    fs = OnlineTransformerDADiarization(n_speakers=4, **kw)
+    fs.load_state_dict(fsd, strict=True)
+    fs = fs.to(dev).eval()
+    sfs = StreamingTransformerEDADiarization(**kw).to(dev).eval()
+    copy_params_from_masked_to_streaming(fs, sfs)
+    xt3 = torch.randn(1, 1, DIN, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(500):
+        sfs.test(xt3, S)
+    torch.cuda.synchronize()
+    fs_lat = (time.perf_counter() - t0) / 500
+    fsrc, _ = FO.synthetic_features(1, 60)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        FO.stream_all(fsd, fsrc[0][None], S, FO.Cfg())
+        fs_cpu = (time.perf_counter() - t0) / 69
+    out["fs_stream_B1_S6"] = {"workload": "FS-EEND frame-by-frame, B=1, S=6, first 500 frames (attention over the growing cache)",
+                              "ms_per_frame": fs_lat * 1e3, "real_time_factor": fs_lat / 0.1,
+                              "cpu_baseline": {"ms_per_frame": fs_cpu * 1e3, "cores": cpu_threads, "kind": "port",
+                                               "sample": "60 frames + flush, oracle port (first 60 frames: shorter cache "
+                                                         "than the GPU figure's 500)"}}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -297,6 +423,23 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = native.launches_per_forward * args.steps
 
+    # ---- sustained figure: the same loop for >= 200 steps (a 20-step region is ~45 ms: boost clocks, no power cap yet)
+    sustained = None
+    if rank == 0 and world == 1 and args.steps < 200 and not args.no_secondary:
+        n_sus = 300
+        s_sampler = ClockSampler(local)
+        s_sampler.start()
+        sv0, sv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        sv0.record()
+        for i in range(n_sus):
+            native.forward(xs[i % n_buf], lens, S)
+        sv1.record()
+        torch.cuda.synchronize()
+        s_ms = sv0.elapsed_time(sv1)
+        sustained = {"steps": n_sus, "value": B * T * n_sus / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms / n_sus,
+                     "clocks": s_sampler.stop()}
+
     # ---- end-to-end through the host-buffer C-ABI entry point (H2D + forward + D2H every step)
     e2e_steps = max(3, min(args.steps, 20))
     for i in range(2):
@@ -335,15 +478,21 @@ def run_ours(args):
         d_ms = prof[dom][0] / prof[dom][1]
         fl = algorithmic_flops(dom, B, T, S)
         ach = fl / (d_ms * 1e-3) / 1e12
-        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["tflops"], "traffic": traffic.get(dom), "peak_source": pk["source"],
+        # The kernel is timed alone (events around single launches in a 3-forward pass: boost clocks, no power cap), so
+        # the BURST cuBLAS figure is the denominator that applies; the fraction of the sustained figure is given beside it.
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                "frac": ach / pk["tflops_burst"], "peak_kind": "burst (kernel timed in isolation)",
+                "frac_of_sustained_peak": ach / pk["tflops"], "peak_sustained": pk["tflops"],
+                "traffic": traffic.get(dom), "peak_source": pk["source"],
                 "avg_launch_ms": d_ms, "algorithmic_flops_per_launch": fl}
         for k in ("dec.attn_causal",):
             if k in prof:
                 a_ms = prof[k][0] / prof[k][1]
                 a = algorithmic_flops(k, B, T, S) / (a_ms * 1e-3) / 1e12
-                roof_attn = {"kernel": k, "bound": "tensor", "achieved": a, "peak": pk["tflops"], "unit": "TFLOP/s",
-                             "frac": a / pk["tflops"], "avg_launch_ms": a_ms, "flops": "causal-exact"}
+                roof_attn = {"kernel": k, "bound": "tensor", "achieved": a, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                             "frac": a / pk["tflops_burst"], "peak_kind": "burst (kernel timed in isolation)",
+                             "frac_of_sustained_peak": a / pk["tflops"], "avg_launch_ms": a_ms, "flops": "causal-exact",
+                             "traffic": traffic.get(k)}
 
     if world > 1:
         dist.barrier()
@@ -358,6 +507,13 @@ def run_ours(args):
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
                "sample": f"{reps} x 4 sequences x {T} frames in {el:.1f} s (oracle port, torch CPU fp32, "
                          f"best of 8/16/32/64/all threads)"}
+
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        try:
+            secondary = secondary_measurements(dev)
+        except Exception as e:      # the headline line must not be lost to a secondary workload
+            secondary = {"error": f"{type(e).__name__}: {e}"}
 
     frames = world * B * T
     value = frames * args.steps / (ms * 1e-3)
@@ -379,6 +535,8 @@ def run_ours(args):
         "roofline": roof,
         "roofline_attention": roof_attn,
         "cpu_baseline": cpu,
+        "sustained": sustained,
+        "secondary": secondary,
         "kernels": prof_table,
         "options": os.environ.get("FSEEND_OPTS", "default"),
     }
@@ -394,6 +552,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the LS-EEND / streaming secondary workloads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -33,30 +33,31 @@ constexpr int kStageBytes = 4 * kTileBytes;       // A_hi | A_lo | W_hi | W_lo
 constexpr int kGemmSmem = kStages * kStageBytes + 1024;
 constexpr uint32_t kTmemCols = 256;            // two ping-pong 128-column accumulators
 
+// x = hi + lo with both halves fp16.  Packed conversions only: cvt.rn.f16x2.f32 (F2FP, full rate) and HADD2.F32 —
+// the scalar F2F.F16.F32 form runs on the quarter-rate conversion pipe and was 30 % of the first version's stall samples.
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
-  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  __half h[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h[i] = __float2half_rn(x[i]);
-    l[i] = __float2half_rn(x[i] - __half2float(h[i]));
-  }
-  hi.x = static_cast<uint32_t>(__half_as_ushort(h[0])) | (static_cast<uint32_t>(__half_as_ushort(h[1])) << 16);
-  hi.y = static_cast<uint32_t>(__half_as_ushort(h[2])) | (static_cast<uint32_t>(__half_as_ushort(h[3])) << 16);
-  hi.z = static_cast<uint32_t>(__half_as_ushort(h[4])) | (static_cast<uint32_t>(__half_as_ushort(h[5])) << 16);
-  hi.w = static_cast<uint32_t>(__half_as_ushort(h[6])) | (static_cast<uint32_t>(__half_as_ushort(h[7])) << 16);
-  lo.x = static_cast<uint32_t>(__half_as_ushort(l[0])) | (static_cast<uint32_t>(__half_as_ushort(l[1])) << 16);
-  lo.y = static_cast<uint32_t>(__half_as_ushort(l[2])) | (static_cast<uint32_t>(__half_as_ushort(l[3])) << 16);
-  lo.z = static_cast<uint32_t>(__half_as_ushort(l[4])) | (static_cast<uint32_t>(__half_as_ushort(l[5])) << 16);
-  lo.w = static_cast<uint32_t>(__half_as_ushort(l[6])) | (static_cast<uint32_t>(__half_as_ushort(l[7])) << 16);
+  split2(a.x, a.y, hi.x, lo.x);
+  split2(a.z, a.w, hi.y, lo.y);
+  split2(b.x, b.y, hi.z, lo.z);
+  split2(b.z, b.w, hi.w, lo.w);
 }
 
-__device__ __forceinline__ float act_apply(float v, int act) {
-  if (act == P32_RELU) return fmaxf(v, 0.f);
-  if (act == P32_SWISH) return v / (1.f + expf(-v));
+template <int kAct>
+__device__ __forceinline__ float act_apply(float v) {
+  if (kAct == P32_RELU) return fmaxf(v, 0.f);
+  // swish: v * 1 / (1 + e^-v) with a correctly rounded reciprocal (no IEEE-division slow path)
+  if (kAct == P32_SWISH) return v * __frcp_rn(1.f + expf(-v));
   return v;
 }
 
+template <int kAct>
 __global__ void __launch_bounds__(256, 1)
 p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                 const P32GemmParams p) {
@@ -64,6 +65,7 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t done_bar[kStages];   // MMAs of a k-block complete: smem stage free + accumulator ready
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[BN];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -85,6 +87,7 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
     tma_prefetch_desc(&tmWlo);
   }
   if (warp == 2) tmem_alloc(&tmem_base_slot, kTmemCols);
+  if (tid < BN) bias_s[tid] = p.bias ? __ldg(p.bias + n0 + tid) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -187,15 +190,15 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
       const int col0 = n0 + cbase;
       float* op = p.out + orow * p.ldo + col0;
       const float* rp = p.residual ? p.residual + orow * p.ldr + col0 : nullptr;
+      const float wsc = p.w_inv_scale, alpha = p.alpha;
 #pragma unroll
       for (int j = 0; j < 64; j += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(&bias_s[cbase + j]);     // same address in every lane: broadcast
         float v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float x = acc[j + k] * p.w_inv_scale;
-          if (p.bias) x += __ldg(p.bias + col0 + j + k);
-          v[k] = p.alpha * act_apply(x, p.act);
-        }
+        v[0] = alpha * act_apply<kAct>(fmaf(acc[j + 0], wsc, bb.x));
+        v[1] = alpha * act_apply<kAct>(fmaf(acc[j + 1], wsc, bb.y));
+        v[2] = alpha * act_apply<kAct>(fmaf(acc[j + 2], wsc, bb.z));
+        v[3] = alpha * act_apply<kAct>(fmaf(acc[j + 3], wsc, bb.w));
         if (rp) {
           const float4 rr = *reinterpret_cast<const float4*>(rp + j);
           v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
@@ -755,12 +758,16 @@ __global__ void p32_hist_append_kernel(const float* __restrict__ src, float* __r
 void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P32GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(p32_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    cudaFuncSetAttribute(p32_gemm_kernel<P32_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    cudaFuncSetAttribute(p32_gemm_kernel<P32_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    cudaFuncSetAttribute(p32_gemm_kernel<P32_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
     attr_set = true;
   }
   const int tiles_per_seq = (p.rows_per_seq + BM - 1) / BM;
   const int grid = p.n_seq * tiles_per_seq * (p.N / BN);
-  p32_gemm_kernel<<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
+  if (p.act == P32_RELU) p32_gemm_kernel<P32_RELU><<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
+  else if (p.act == P32_SWISH) p32_gemm_kernel<P32_SWISH><<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
+  else p32_gemm_kernel<P32_NONE><<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
 }
 
 void launch_p32_layernorm(const float* x, int rows, const float* g1, const float* b1, float* out1, const float* g2,
