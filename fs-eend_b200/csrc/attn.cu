@@ -458,12 +458,28 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 // attn2.cu: two query tiles per CTA, 128-key KV tiles (causal mode)
 void launch_attn2(const CUtensorMap& tmQ, const CUtensorMap& tmKV, __half* out, const AttnParams& p,
                   cudaStream_t stream);
+void launch_attn3(const CUtensorMap& tmQ, __half* out, const AttnParams& p, int step_keys, cudaStream_t stream);
 
 void launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmKV, __half* out, const AttnParams& p,
                  cudaStream_t stream) {
   if (p.mode == ATTN_CAUSAL) {
-    const char* e = getenv("FSEEND_ATTN");     // 1 = one query tile per CTA (this file), default = attn2.cu
-    if (!(e && e[0] == '1')) {
+    // FSEEND_ATTN: 1 = one query tile per CTA with role warps (this file), 2 = query-tile pairs with role warps
+    // (attn2.cu), 3 = self-contained warpgroup per query tile with whole-step softmax (attn3.cu;
+    // FSEEND_ATTN_STEP = 128 (default, 4 CTAs / SM) or 256 (2 CTAs / SM) keys per step).
+    // Default (measured, profiles/r02_attention_study.md): attn3 where there are enough (sequence, head, tile) items to
+    // balance 4 persistent CTAs per SM dynamically (the decoder: 6144 items), attn2 for small launches (the encoder).
+    const char* e = getenv("FSEEND_ATTN");
+    int variant = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 0;
+    if (variant == 0) {
+      const long long items = 1ll * ((p.T + 127) / 128) * p.H * p.B * p.S;
+      variant = items >= 4096 ? 3 : 2;
+    }
+    if (variant == 3) {
+      const char* s = getenv("FSEEND_ATTN_STEP");
+      launch_attn3(tmQ, out, p, (s && atoi(s) == 256) ? 256 : 128, stream);
+      return;
+    }
+    if (variant == 2) {
       launch_attn2(tmQ, tmKV, out, p, stream);
       return;
     }

@@ -199,7 +199,9 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             }
             release_slot(s0);
             release_slot(s0 + 1);
-            if (ks2 == 1) umma_commit(&p_empty[pb]);
+            if (!kTS && ks2 == 1) umma_commit(&p_empty[pb]);   // TS: nobody waits on p_empty (the P columns are
+                                                                 // protected by the in-order tensor pipe) - an arrive
+                                                                 // that is never waited on is a synccheck finding
           }
           __syncwarp();
           use += 2;

@@ -144,13 +144,27 @@ ATTN_SHAPES = [(2, 300, 1, 0), (1, 500, 3, 0), (2, 130, 2, 2), (1, 64, 1, 0), (1
                (3, 1000, 1, 5), (1, 129, 1, 0)]
 
 
+@pytest.mark.parametrize("step", ["128", "256"])
 @pytest.mark.parametrize("B,T,S,md", ATTN_SHAPES)
-def test_causal_attention(N, B, T, S, md):
-    """Default kernel (attn2.cu: pairs of query tiles; odd and even tile counts, look-ahead, no-mask)."""
+def test_causal_attention(N, monkeypatch, B, T, S, md, step):
+    """attn3.cu (the decoder's kernel: one self-contained warpgroup per query tile, whole-step softmax, dynamic item
+    queue; 128- and 256-key steps; odd and even tile counts, partial last tiles, look-ahead, no-mask, multi-step rows
+    at T = 700 / 1000)."""
+    monkeypatch.setenv("FSEEND_ATTN", "3")
+    monkeypatch.setenv("FSEEND_ATTN_STEP", step)
     qkv = rnd(B, T, S, 768, seed=25 + T).half()
     out = N.op_causal_attn(qkv, mask_delay=md)
     ref = attn_ref(qkv, md)
     assert (out.float() - ref).abs().max().item() < 4e-3
+
+
+@pytest.mark.parametrize("B,T,S,md", ATTN_SHAPES)
+def test_causal_attention_tile_pair_kernel(N, monkeypatch, B, T, S, md):
+    """FSEEND_ATTN=2: the round-1 default (attn2.cu: pairs of query tiles, role warps)."""
+    monkeypatch.setenv("FSEEND_ATTN", "2")
+    qkv = rnd(B, T, S, 768, seed=25 + T).half()
+    out = N.op_causal_attn(qkv, mask_delay=md)
+    assert (out.float() - attn_ref(qkv, md)).abs().max().item() < 4e-3
 
 
 @pytest.mark.parametrize("B,T,S,md", ATTN_SHAPES)
@@ -162,7 +176,7 @@ def test_causal_attention_one_tile_kernel(N, monkeypatch, B, T, S, md):
     assert (out.float() - attn_ref(qkv, md)).abs().max().item() < 4e-3
 
 
-@pytest.mark.parametrize("variant", ["", "1"])
+@pytest.mark.parametrize("variant", ["", "1", "2", "3"])
 def test_causal_attention_large_scores_exercise_lazy_rescale(N, monkeypatch, variant):
     """Scores with a spread of ~±60 in log2 units: the running maximum outgrows the lazy reference by more than 2^8
     many times per row, so the rare path (rescale O in TMEM, the row sum and the P chunks already written) runs."""

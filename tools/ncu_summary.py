@@ -1,31 +1,27 @@
-"""Summarise an .ncu-rep (read here, no GPU needed) into the handful of metrics the roofline uses."""
+"""Summarise an .ncu-rep (read on the CPU box): per captured launch the metrics the review asks for.
+    python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.txt"""
 import csv
 import subprocess
 import sys
 
-KEYS = [
-    "gpu__time_duration.sum", "sm__cycles_elapsed.avg", "launch__grid_size", "launch__block_size",
-    "launch__registers_per_thread", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
-    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
-    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
-    "smsp__inst_executed.sum",
-]
-
-
-def main(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.avg",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem"]
+for rep in sys.argv[1:]:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    rows = [r for r in rows if len(r) > 10]
     hdr, units = rows[0], rows[1]
-    name_col = hdr.index("Kernel Name")
     for r in rows[2:]:
-        print(f"## {r[name_col][:60]}  (launch id {r[0]})")
-        for h, u, v in zip(hdr, units, r):
-            if h in KEYS:
-                print(f"  {h} [{u}] = {v}")
-
-
-if __name__ == "__main__":
-    main(sys.argv[1])
+        name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        print(f"## {name[:110]}  (launch id {r[hdr.index('ID')]})")
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                print(f"  {w} [{units[i]}] = {r[i]}")
