@@ -24,6 +24,7 @@
 #include "ffn.cuh"
 #include "gemm.cuh"
 #include "loss.cuh"
+#include "p32.cuh"
 #include "spkfuse.cuh"
 #include "tmap.h"
 
@@ -139,6 +140,13 @@ struct fseend_fs_model {
   int host_chunks = 0;     // 0 = automatic
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
   cudaEvent_t chunk_ev[kMaxHostChunks] = {};
+  // pipelined host-buffer forward (fseend_fs_forward_host_async): kHostDepth calls in flight, each with its own device
+  // staging of the features / logits; the H2D copy of call i+1 overlaps the kernels of call i
+  static constexpr int kHostDepth = 2;
+  DevBuf hx[kHostDepth], hl[kHostDepth];
+  cudaEvent_t h2d_ev[kHostDepth] = {}, done_ev[kHostDepth] = {};
+  long long host_calls = 0;            // tickets handed out so far
+
   // descriptors
   CUtensorMap tm_x16, tm_hA, tm_hB, tm_qkv_e_out, tm_qkv_e_attn, tm_ao_e_attn, tm_ao_e, tm_f_e_out, tm_f_e_in;
   CUtensorMap tm_hconv_in, tm_hB_seq, tm_emb_out, tm_emb_in, tm_cvt_out;
@@ -158,6 +166,10 @@ struct fseend_fs_model {
     for (auto& e : cu_ev)
       if (e) cudaEventDestroy(e);
     for (auto& e : chunk_ev)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : h2d_ev)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : done_ev)
       if (e) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (compute_stream) cudaStreamDestroy(compute_stream);
@@ -188,6 +200,12 @@ struct fseend_fs_stream {
   int eager_decodes = 0;                   // decoder steps run eagerly so far (first ones: lazy kernel attributes)
   bool use_graph = true;
   cudaStream_t cap_stream = nullptr;       // private capture stream
+  // Small-row path (B * S <= 16 rows per step, the usual B = 1 recording): every product is a weight-streaming
+  // matrix-vector job, so the step runs on the CUDA-core row-vector kernel of p32.cu with the model's fp16 weights and
+  // fp32 activations / caches instead of 128-row tcgen05 tiles (FSEEND_STREAM_RV=0 keeps the tile kernels).
+  bool rv = false;
+  std::vector<std::unique_ptr<DevBuf>> enc_k32, enc_v32, dec_k32, dec_v32;
+  DevBuf hist32, rX, rh0, rh1, rqkv, rao, rf, ra0, ra1, ra2, rT1, remb, rY;
   ~fseend_fs_stream() {
     if (graph_step) cudaGraphExecDestroy(graph_step);
     if (graph_flush) cudaGraphExecDestroy(graph_flush);
@@ -688,25 +706,33 @@ void forward_impl(fseend_fs_model* m, const float* x_packed, const int* ilens, i
 void stream_alloc(fseend_fs_stream* s, int cap) {
   const fseend_fs_config& c = s->m->cfg;
   const int D = c.n_units, B = s->B, S = s->S;
-  auto grow = [&](DevBuf& buf, size_t n_seq) {
+  auto grow = [&](DevBuf& buf, size_t n_seq, size_t es = 2) {
     DevBuf nb;
-    nb.alloc(n_seq * cap * D * 2);
+    nb.alloc(n_seq * cap * D * es);
     CUDA_CHECK(cudaMemset(nb.p, 0, nb.bytes));
     if (buf.p && s->cap > 0)
-      CUDA_CHECK(cudaMemcpy2D(nb.p, 1ull * cap * D * 2, buf.p, 1ull * s->cap * D * 2, 1ull * s->cap * D * 2, n_seq,
+      CUDA_CHECK(cudaMemcpy2D(nb.p, 1ull * cap * D * es, buf.p, 1ull * s->cap * D * es, 1ull * s->cap * D * es, n_seq,
                               cudaMemcpyDeviceToDevice));
     std::swap(buf.p, nb.p);
     std::swap(buf.bytes, nb.bytes);
   };
   CUDA_CHECK(cudaDeviceSynchronize());
-  for (auto& b : s->enc_k) grow(*b, B);
-  for (auto& b : s->enc_v) grow(*b, B);
-  for (auto& b : s->dec_k) grow(*b, 1ull * B * S);
-  for (auto& b : s->dec_v) grow(*b, 1ull * B * S);
-  grow(s->hist, B);
+  if (s->rv) {
+    for (auto& b : s->enc_k32) grow(*b, B, 4);
+    for (auto& b : s->enc_v32) grow(*b, B, 4);
+    for (auto& b : s->dec_k32) grow(*b, 1ull * B * S, 4);
+    for (auto& b : s->dec_v32) grow(*b, 1ull * B * S, 4);
+    grow(s->hist32, B, 4);
+  } else {
+    for (auto& b : s->enc_k) grow(*b, B);
+    for (auto& b : s->enc_v) grow(*b, B);
+    for (auto& b : s->dec_k) grow(*b, 1ull * B * S);
+    for (auto& b : s->dec_v) grow(*b, 1ull * B * S);
+    grow(s->hist, B);
+  }
   CUDA_CHECK(cudaDeviceSynchronize());   // memset / copies ran on the legacy stream: order them before ANY caller stream
   s->cap = cap;
-  s->tm_hist = make_tmap_rows3d(s->hist.p, D, D, cap, B, 128);
+  if (!s->rv) s->tm_hist = make_tmap_rows3d(s->hist.p, D, D, cap, B, 128);
 }
 
 void stream_init(fseend_fs_stream* s, fseend_fs_model* m, int B, int S) {
@@ -718,12 +744,34 @@ void stream_init(fseend_fs_stream* s, fseend_fs_model* m, int B, int S) {
   for (int l = 0; l < c.enc_n_layers; ++l) {
     s->enc_k.push_back(std::make_unique<DevBuf>());
     s->enc_v.push_back(std::make_unique<DevBuf>());
+    s->enc_k32.push_back(std::make_unique<DevBuf>());
+    s->enc_v32.push_back(std::make_unique<DevBuf>());
   }
   for (int l = 0; l < c.dec_n_layers; ++l) {
     s->dec_k.push_back(std::make_unique<DevBuf>());
     s->dec_v.push_back(std::make_unique<DevBuf>());
+    s->dec_k32.push_back(std::make_unique<DevBuf>());
+    s->dec_v32.push_back(std::make_unique<DevBuf>());
   }
   const size_t Rd = 1ull * B * S;
+  s->rv = B * S <= 16;
+  if (const char* e = getenv("FSEEND_STREAM_RV")) s->rv = s->rv && e[0] != '0';
+  if (s->rv) {
+    const size_t f = sizeof(float);
+    const size_t Fmax = static_cast<size_t>(std::max(c.enc_dim_feedforward, c.dec_dim_feedforward));
+    s->rX.alloc(1ull * B * m->Kin * f);
+    s->rh0.alloc(1ull * B * D * f);
+    s->rh1.alloc(1ull * B * D * f);
+    s->rqkv.alloc(Rd * 3 * D * f);
+    s->rao.alloc(Rd * D * f);
+    s->rf.alloc(Rd * Fmax * f);
+    s->ra0.alloc(Rd * D * f);
+    s->ra1.alloc(Rd * D * f);
+    s->ra2.alloc(Rd * D * f);
+    s->rT1.alloc(Rd * D * f);
+    s->remb.alloc(1ull * B * D * f);
+    s->rY.alloc(1ull * B * D * f);
+  }
   s->x16.alloc(1ull * B * m->Kin * 2);
   s->h0.alloc(1ull * B * D * 2);
   s->h1.alloc(1ull * B * D * 2);
@@ -774,10 +822,114 @@ void stream_init(fseend_fs_stream* s, fseend_fs_model* m, int B, int S) {
   stream_alloc(s, 1024);
 }
 
+// Small-row frame step (see fseend_fs_stream::rv): same arithmetic as stream_launch below with fp32 activations and
+// caches; every product goes through the row-vector kernel (fp16 weights read once from L2, no tensor-core tiles).
+void stream_launch_rv(fseend_fs_stream* s, const float* x_in, bool decode, float* y_out, cudaStream_t st) {
+  fseend_fs_model* m = s->m;
+  const fseend_fs_config& c = m->cfg;
+  const int D = c.n_units, B = s->B, S = s->S;
+  const int Rd = B * S;
+  const float scale = 1.f / sqrtf(64.f);
+  const int* enc_pos = static_cast<const int*>(s->ctr.p);
+  const int* dec_pos = enc_pos + 1;
+  auto F = [](DevBuf& b) { return static_cast<float*>(b.p); };
+  auto lin = [&](const float* A, int rows, const WMat& w, const float* bias, int act, const float* res, float* out) {
+    P32GemmParams p{};
+    p.A = A;
+    p.lda = w.K;
+    p.a_seq_rows = rows;
+    p.rows_per_seq = rows;
+    p.n_seq = 1;
+    p.k_blocks = w.K / 64;
+    p.taps = 1;
+    p.N = w.rows;
+    p.bias = bias;
+    p.act = act;
+    p.alpha = 1.f;
+    p.w_inv_scale = 1.f;
+    p.residual = res;
+    p.ldr = w.rows;
+    p.out = out;
+    p.ldo = w.rows;
+    if (!launch_p32_rowvec(static_cast<const __half*>(w.buf.p), nullptr, p, st))
+      throw std::runtime_error("row-vector kernel rejected the shape");
+  };
+  auto ln = [&](const float* x, int rows, const FVec& g, const FVec& b, float* out) {
+    launch_p32_layernorm(x, rows, g.f(), b.f(), out, nullptr, nullptr, nullptr, c.ln_eps, nullptr, 0, st);
+  };
+  if (x_in) {
+    launch_p32_pad_input(x_in, static_cast<const int*>(s->cu.p), B, 1, c.in_size, m->Kin, F(s->rX), st, m->bn_scale.f(),
+                         m->bn_shift.f(), -1.f);
+    lin(F(s->rX), B, m->w_in, m->b_in.f(), P32_NONE, nullptr, F(s->rT1));
+    ln(F(s->rT1), B, m->g_in, m->be_in, F(s->rh0));
+    for (int l = 0; l < c.enc_n_layers; ++l) {
+      EncLayer& E = *m->enc[l];
+      lin(F(s->rh0), B, E.wqkv, E.bqkv.f(), P32_NONE, nullptr, F(s->rqkv));
+      launch_p32_step_attn(F(s->rqkv), F(*s->enc_k32[l]), F(*s->enc_v32[l]), B, s->cap, 0, scale, F(s->rao), st, enc_pos);
+      lin(F(s->rao), B, E.wo, E.bo.f(), P32_NONE, F(s->rh0), F(s->rT1));
+      ln(F(s->rT1), B, E.g1, E.be1, F(s->rh1));
+      lin(F(s->rh1), B, E.w1, E.b1.f(), P32_RELU, nullptr, F(s->rf));
+      lin(F(s->rf), B, E.w2, E.b2.f(), P32_NONE, F(s->rh1), F(s->rT1));
+      ln(F(s->rT1), B, E.g2, E.be2, F(s->rh0));
+    }
+    launch_p32_hist_append(F(s->rh0), F(s->hist32), B, s->cap, 0, st, enc_pos);
+  } else {
+    launch_p32_hist_append(nullptr, F(s->hist32), B, s->cap, 0, st, enc_pos);
+  }
+  if (!decode) {
+    launch_advance_counters(static_cast<int*>(s->ctr.p), 1, 0, 0, 0, st);
+    return;
+  }
+  {
+    const int K = c.conv_kernel, center = K / 2;
+    P32GemmParams p{};
+    p.A = F(s->hist32);
+    p.lda = D;
+    p.a_seq_rows = s->cap;
+    p.rows_per_seq = 1;
+    p.n_seq = B;
+    p.k_blocks = D / 64;
+    p.taps = K;
+    p.tap_shift = -center;
+    p.a_row_offset_dev = dec_pos;
+    p.N = D;
+    p.bias = m->b_conv.f();
+    p.alpha = 1.f;
+    p.w_inv_scale = 1.f;
+    p.out = F(s->remb);
+    p.ldo = D;
+    if (!launch_p32_rowvec(static_cast<const __half*>(m->w_conv.buf.p), nullptr, p, st))
+      throw std::runtime_error("row-vector kernel rejected the conv shape");
+    launch_p32_l2norm(F(s->remb), B, st);
+  }
+  lin(F(s->remb), B, m->w_cvt, nullptr, P32_NONE, nullptr, F(s->rY));
+  launch_p32_convert(F(s->rY), m->pe_proj.f(), B, S, F(s->ra0), st);
+  for (int l = 0; l < c.dec_n_layers; ++l) {
+    DecLayer& Dl = *m->dec[l];
+    lin(F(s->ra0), Rd, Dl.wqkv1, Dl.bqkv1.f(), P32_NONE, nullptr, F(s->rqkv));
+    launch_p32_step_attn(F(s->rqkv), F(*s->dec_k32[l]), F(*s->dec_v32[l]), Rd, s->cap, 0, scale, F(s->rao), st, dec_pos);
+    lin(F(s->rao), Rd, Dl.wo1, Dl.bo1.f(), P32_NONE, F(s->ra0), F(s->rT1));
+    ln(F(s->rT1), Rd, Dl.g11, Dl.be11, F(s->ra1));
+    lin(F(s->ra1), Rd, Dl.wqkv2, Dl.bqkv2.f(), P32_NONE, nullptr, F(s->rqkv));
+    launch_p32_spk_attn(F(s->rqkv), F(s->rao), B, S, scale, st);
+    lin(F(s->rao), Rd, Dl.wo2, Dl.bo2.f(), P32_NONE, F(s->ra1), F(s->rT1));
+    ln(F(s->rT1), Rd, Dl.g21, Dl.be21, F(s->ra2));
+    lin(F(s->ra2), Rd, Dl.w1, Dl.b1.f(), P32_RELU, nullptr, F(s->rf));
+    lin(F(s->rf), Rd, Dl.w2, Dl.b2.f(), P32_NONE, F(s->ra2), F(s->rT1));
+    ln(F(s->rT1), Rd, Dl.g22, Dl.be22, F(s->ra0));
+  }
+  launch_p32_head(F(s->remb), F(s->ra0), B, S, y_out, nullptr, nullptr, st);
+  launch_advance_counters(static_cast<int*>(s->ctr.p), 1, 1, 0, 0, st);
+}
+
 // The kernels of one frame.  Every per-frame index is read from the device counters (ctr[0] = encoder frame index,
 // ctr[1] = decoder frame index), so the same launch sequence is valid for every frame and can be replayed from a CUDA
 // graph.  x_in: staged frame (nullptr: flush step, zero conv input); decode: the look-ahead window is full.
 void stream_launch(fseend_fs_stream* s, const float* x_in, bool decode, float* y_out, cudaStream_t st) {
+  if (s->rv) {
+    stream_launch_rv(s, x_in, decode, y_out, st);
+    return;
+  }
   fseend_fs_model* m = s->m;
   const fseend_fs_config& c = m->cfg;
   const int D = c.n_units, B = s->B, S = s->S;
@@ -1121,6 +1273,66 @@ int fseend_fs_forward_host(fseend_fs_model* m, const float* x_packed_host, const
     if (emb_host) CUDA_CHECK(cudaMemcpyAsync(emb_host, de, n_emb * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (att_host) CUDA_CHECK(cudaMemcpyAsync(att_host, da, n_att * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+// Pipelined host-buffer forward: enqueue and return a ticket; fseend_fs_host_wait(ticket) blocks until that call's logits
+// are in logits_host.  Two calls may be in flight: while call i runs its kernels on the compute stream, the copy stream
+// already moves call i+1's features into the other staging buffer, so in steady state a step costs max(copy, compute)
+// instead of copy + compute.  x_packed_host / logits_host must stay valid (and should be pinned) until the wait.
+int fseend_fs_forward_host_async(fseend_fs_model* m, const float* x_packed_host, const int* ilens_host, int B,
+                                 int max_nspks, float* logits_host, long long* ticket) {
+  if (!m || !x_packed_host || !ilens_host || !logits_host || !ticket) {
+    set_last_error("null argument");
+    return FSEEND_ERR_INVALID;
+  }
+  return guarded([&] {
+    if (B < 1) throw std::invalid_argument("B must be >= 1");
+    long long total = 0;
+    int T = 0;
+    for (int b = 0; b < B; ++b) {
+      if (ilens_host[b] < 1) throw std::invalid_argument("ilens must be >= 1");
+      total += ilens_host[b];
+      T = ilens_host[b] > T ? ilens_host[b] : T;
+    }
+    const size_t xin = static_cast<size_t>(total) * m->cfg.in_size * sizeof(float);
+    const size_t n_log = 1ull * B * T * max_nspks;
+    if (!m->compute_stream) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&m->compute_stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    }
+    const long long tk = m->host_calls;
+    const int slot = static_cast<int>(tk % fseend_fs_model::kHostDepth);
+    if (!m->h2d_ev[slot]) {
+      CUDA_CHECK(cudaEventCreateWithFlags(&m->h2d_ev[slot], cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&m->done_ev[slot], cudaEventDisableTiming));
+    } else {
+      // the call that used this slot last (ticket tk - kHostDepth) must have finished before its staging is reused
+      CUDA_CHECK(cudaEventSynchronize(m->done_ev[slot]));
+    }
+    if (m->hx[slot].bytes < xin) m->hx[slot].alloc(xin);
+    if (m->hl[slot].bytes < n_log * sizeof(float)) m->hl[slot].alloc(n_log * sizeof(float));
+    CUDA_CHECK(cudaMemcpyAsync(m->hx[slot].p, x_packed_host, xin, cudaMemcpyHostToDevice, m->copy_stream));
+    CUDA_CHECK(cudaEventRecord(m->h2d_ev[slot], m->copy_stream));
+    cudaStream_t st = m->compute_stream;
+    CUDA_CHECK(cudaStreamWaitEvent(st, m->h2d_ev[slot], 0));
+    forward_impl(m, static_cast<const float*>(m->hx[slot].p), ilens_host, B, max_nspks, static_cast<float*>(m->hl[slot].p),
+                 nullptr, nullptr, st);
+    CUDA_CHECK(cudaMemcpyAsync(logits_host, m->hl[slot].p, n_log * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaEventRecord(m->done_ev[slot], st));
+    m->host_calls = tk + 1;
+    *ticket = tk;
+  });
+}
+
+int fseend_fs_host_wait(fseend_fs_model* m, long long ticket) {
+  if (!m) return FSEEND_ERR_INVALID;
+  return guarded([&] {
+    if (ticket < 0 || ticket >= m->host_calls) throw std::invalid_argument("unknown ticket");
+    if (ticket < m->host_calls - fseend_fs_model::kHostDepth)
+      return;   // older than the calls in flight: its slot was synchronised when it was reused
+    const int slot = static_cast<int>(ticket % fseend_fs_model::kHostDepth);
+    CUDA_CHECK(cudaEventSynchronize(m->done_ev[slot]));
   });
 }
 

@@ -115,6 +115,31 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
     }
   };
 
+  // A tile of k-block `it`: 4 chunks of 8 floats per thread, fetched one iteration AHEAD into registers so that the
+  // global-load latency hides behind the MMAs of the current k-block (the first version loaded and consumed in the same
+  // iteration: ~1000 clk of exposed L2 latency per k-block)
+  float4 pre[8];
+  auto fetch = [&](int it) {
+    const int tap = it / p.k_blocks;
+    const int kb = it - tap * p.k_blocks;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = tid + 256 * i;
+      const int r = q >> 3, c = q & 7;                 // tile row, 16-byte chunk (8 halfs) inside the 64-wide k block
+      const int t = t0 + r;
+      const int arow = t + tap + p.tap_shift + a_off;
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (t < p.rows_per_seq && arow >= 0 && arow < p.a_seq_rows) {
+        const float4* src = reinterpret_cast<const float4*>(a_seq + static_cast<size_t>(arow) * p.lda + kb * BK + c * 8);
+        v0 = __ldg(src);
+        v1 = __ldg(src + 1);
+      }
+      pre[2 * i] = v0;
+      pre[2 * i + 1] = v1;
+    }
+  };
+  fetch(0);
+
   for (int it = 0; it < total_it; ++it) {
     const int s = it & 1;
     const uint32_t ph = (it >> 1) & 1;
@@ -138,21 +163,14 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int q = tid + 256 * i;
-      const int r = q >> 3, c = q & 7;                 // tile row, 16-byte chunk (8 halfs) inside the 64-wide k block
-      const int t = t0 + r;
-      const int arow = t + tap + p.tap_shift + a_off;
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-      if (t < p.rows_per_seq && arow >= 0 && arow < p.a_seq_rows) {
-        const float4* src = reinterpret_cast<const float4*>(a_seq + static_cast<size_t>(arow) * p.lda + kb * BK + c * 8);
-        v0 = __ldg(src);
-        v1 = __ldg(src + 1);
-      }
+      const int r = q >> 3, c = q & 7;
       uint4 hi, lo;
-      split8(v0, v1, hi, lo);
+      split8(pre[2 * i], pre[2 * i + 1], hi, lo);
       const uint32_t off = sw128_offset(r, c);
       *reinterpret_cast<uint4*>(sAhi + off) = hi;
       *reinterpret_cast<uint4*>(sAlo + off) = lo;
     }
+    if (it + 1 < total_it) fetch(it + 1);
     fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     __syncthreads();               // (also orders every thread's fold of accumulator s before its re-use below)
     if (warp == 1) {
@@ -181,35 +199,217 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
     fold(j & 1);
   }
 
-  // ---------------- epilogue from registers
+  // ---------------- epilogue: registers -> padded fp32 tile in shared memory (the pipeline stages are idle now) ->
+  // whole rows per warp, so that the residual loads and the output stores are 512-byte coalesced (the first version
+  // stored 64 floats per THREAD: every store instruction touched 32 different rows with half-filled sectors)
   {
-    const int r = (warp & 3) * 32 + lane;
-    const int t = t0 + r;
-    if (t < p.rows_per_seq) {
-      const size_t orow = static_cast<size_t>(seq) * p.rows_per_seq + t;
-      const int col0 = n0 + cbase;
-      float* op = p.out + orow * p.ldo + col0;
-      const float* rp = p.residual ? p.residual + orow * p.ldr + col0 : nullptr;
-      const float wsc = p.w_inv_scale, alpha = p.alpha;
+    constexpr int kLdT = BN + 4;                       // 132 floats: conflict-free float4 row writes and reads
+    float* tile = reinterpret_cast<float*>(smem);
+    __syncthreads();                                   // every warp has folded the last accumulators: stages are free
+    {
+      const int r = (warp & 3) * 32 + lane;
+      float* trow = tile + r * kLdT + cbase;
 #pragma unroll
-      for (int j = 0; j < 64; j += 4) {
-        const float4 bb = *reinterpret_cast<const float4*>(&bias_s[cbase + j]);     // same address in every lane: broadcast
-        float v[4];
-        v[0] = alpha * act_apply<kAct>(fmaf(acc[j + 0], wsc, bb.x));
-        v[1] = alpha * act_apply<kAct>(fmaf(acc[j + 1], wsc, bb.y));
-        v[2] = alpha * act_apply<kAct>(fmaf(acc[j + 2], wsc, bb.z));
-        v[3] = alpha * act_apply<kAct>(fmaf(acc[j + 3], wsc, bb.w));
-        if (rp) {
-          const float4 rr = *reinterpret_cast<const float4*>(rp + j);
-          v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-        }
-        *reinterpret_cast<float4*>(op + j) = make_float4(v[0], v[1], v[2], v[3]);
+      for (int j = 0; j < 64; j += 4) *reinterpret_cast<float4*>(trow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    }
+    __syncthreads();
+    const float4 bb = *reinterpret_cast<const float4*>(&bias_s[4 * lane]);
+    const float wsc = p.w_inv_scale, alpha = p.alpha;
+    const int col = n0 + 4 * lane;
+    for (int r = warp; r < BM; r += 8) {
+      const int t = t0 + r;
+      if (t >= p.rows_per_seq) break;                  // rows are handed out in increasing order per warp
+      const size_t orow = static_cast<size_t>(seq) * p.rows_per_seq + t;
+      const float4 a = *reinterpret_cast<const float4*>(tile + r * kLdT + 4 * lane);
+      float4 v;
+      v.x = alpha * act_apply<kAct>(fmaf(a.x, wsc, bb.x));
+      v.y = alpha * act_apply<kAct>(fmaf(a.y, wsc, bb.y));
+      v.z = alpha * act_apply<kAct>(fmaf(a.z, wsc, bb.z));
+      v.w = alpha * act_apply<kAct>(fmaf(a.w, wsc, bb.w));
+      if (p.residual) {
+        const float4 rr = *reinterpret_cast<const float4*>(p.residual + orow * p.ldr + col);
+        v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
       }
+      *reinterpret_cast<float4*>(p.out + orow * p.ldo + col) = v;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =====================================================================================================================
+// Small-row form of the same product (see p32.cuh): at most 16 output rows.  CTA = 8 warps x 2 output columns; K is
+// walked in blocks of 512 whose activations (R x 512 fp32) are staged in shared memory once per CTA.
+constexpr int kRvMaxRows = 16, kRvKB = 512, kRvCols = 2, kRvWarps = 8;
+
+template <int kAct>
+__global__ void __launch_bounds__(kRvWarps * 32)
+p32_rowvec_kernel(const __half* __restrict__ whi, const __half* __restrict__ wlo, const P32GemmParams p) {
+  __shared__ __align__(16) float a_s[kRvMaxRows][kRvKB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = p.n_seq * p.rows_per_seq;
+  const int K = p.k_blocks * 64, Ktot = p.taps * K;
+  const int n0 = (blockIdx.x * kRvWarps + warp) * kRvCols;
+  const int a_off = p.a_row_offset + (p.a_row_offset_dev ? *p.a_row_offset_dev : 0);
+  float acc[kRvCols][kRvMaxRows];
+#pragma unroll
+  for (int c = 0; c < kRvCols; ++c)
+#pragma unroll
+    for (int r = 0; r < kRvMaxRows; ++r) acc[c][r] = 0.f;
+
+  for (int kb0 = 0; kb0 < Ktot; kb0 += kRvKB) {
+    __syncthreads();
+    // stage A[r][kb0 .. kb0 + 512) (taps: output row t of a sequence reads A row t + tap + tap_shift + a_off, zero outside)
+    for (int i = tid; i < R * (kRvKB / 4); i += kRvWarps * 32) {
+      const int r = i / (kRvKB / 4), k = kb0 + (i - r * (kRvKB / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < Ktot) {
+        const int tap = k / K, c = k - tap * K;
+        const int seq = r / p.rows_per_seq, t = r - seq * p.rows_per_seq;
+        const int arow = t + tap + p.tap_shift + a_off;
+        if (arow >= 0 && arow < p.a_seq_rows)
+          v = __ldg(reinterpret_cast<const float4*>(p.A + (static_cast<size_t>(seq) * p.a_seq_rows + arow) * p.lda + c));
+      }
+      *reinterpret_cast<float4*>(&a_s[r][k - kb0]) = v;
+    }
+    __syncthreads();
+    if (n0 < p.N) {
+#pragma unroll
+      for (int j = 0; j < kRvKB / 256; ++j) {
+        const int kl = (lane + 32 * j) * 8, k = kb0 + kl;
+        if (k < Ktot) {
+          const int tap = k / K, c = k - tap * K;
+          float w[kRvCols][8];
+#pragma unroll
+          for (int cc = 0; cc < kRvCols; ++cc) {
+            const size_t off = (static_cast<size_t>(tap) * p.N + n0 + cc) * K + c;
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(whi + off));
+            const __half2* hh = reinterpret_cast<const __half2*>(&h);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(hh[q]);
+              w[cc][2 * q] = f.x;
+              w[cc][2 * q + 1] = f.y;
+            }
+            if (wlo) {
+              const uint4 l = __ldg(reinterpret_cast<const uint4*>(wlo + off));
+              const __half2* ll = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(ll[q]);
+                w[cc][2 * q] += f.x;          // hi + lo: exact in fp32 (two non-overlapping 11-bit mantissas)
+                w[cc][2 * q + 1] += f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < kRvMaxRows; ++r) {
+            if (r < R) {
+              const float4 a0 = *reinterpret_cast<const float4*>(&a_s[r][kl]);
+              const float4 a1 = *reinterpret_cast<const float4*>(&a_s[r][kl + 4]);
+#pragma unroll
+              for (int cc = 0; cc < kRvCols; ++cc) {
+                float s = acc[cc][r];
+                s = fmaf(w[cc][0], a0.x, s); s = fmaf(w[cc][1], a0.y, s); s = fmaf(w[cc][2], a0.z, s); s = fmaf(w[cc][3], a0.w, s);
+                s = fmaf(w[cc][4], a1.x, s); s = fmaf(w[cc][5], a1.y, s); s = fmaf(w[cc][6], a1.z, s); s = fmaf(w[cc][7], a1.w, s);
+                acc[cc][r] = s;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (n0 >= p.N) return;
+#pragma unroll
+  for (int cc = 0; cc < kRvCols; ++cc)
+#pragma unroll
+    for (int r = 0; r < kRvMaxRows; ++r) {
+      if (r < R) {
+        float v = acc[cc][r];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        acc[cc][r] = v;
+      }
+    }
+  // lane l < R * kRvCols finishes output (row l / kRvCols, column n0 + l % kRvCols)
+#pragma unroll
+  for (int cc = 0; cc < kRvCols; ++cc)
+#pragma unroll
+    for (int r = 0; r < kRvMaxRows; ++r) {
+      if (r < R && lane == ((r * kRvCols + cc) & 31)) {
+        const int n = n0 + cc;
+        float x = fmaf(acc[cc][r], p.w_inv_scale, p.bias ? __ldg(p.bias + n) : 0.f);
+        x = p.alpha * act_apply<kAct>(x);
+        if (p.residual) x += p.residual[static_cast<size_t>(r) * p.ldr + n];
+        p.out[static_cast<size_t>(r) * p.ldo + n] = x;
+      }
+    }
+}
+
+// Streaming attention step in fp32 (see elementwise.cu: step_attn_kernel for the fp16-cache form).
+__global__ void __launch_bounds__(128)
+p32_step_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kcache, float* __restrict__ vcache, int cap,
+                     int pos_arg, const int* __restrict__ pos_dev, float scale, float* __restrict__ out) {
+  const int n = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int pos = pos_dev ? *pos_dev : pos_arg;
+  __shared__ float q_s[64];
+  __shared__ float red_m[128], red_l[128];
+  __shared__ float red_o[4][64];
+  const float* row = qkv + static_cast<size_t>(n) * 768;
+  float* kc = kcache + (static_cast<size_t>(n) * cap) * 256 + h * 64;
+  float* vc = vcache + (static_cast<size_t>(n) * cap) * 256 + h * 64;
+  if (tid < 64) {
+    q_s[tid] = row[h * 64 + tid] * scale * 1.4426950408889634f;
+    kc[static_cast<size_t>(pos) * 256 + tid] = row[256 + h * 64 + tid];
+    vc[static_cast<size_t>(pos) * 256 + tid] = row[512 + h * 64 + tid];
+  }
+  __syncthreads();
+  float m = -INFINITY, l = 0.f, o[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) o[i] = 0.f;
+  for (int j = tid; j <= pos; j += 128) {
+    const float4* kp = reinterpret_cast<const float4*>(kc + static_cast<size_t>(j) * 256);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 f = kp[i];
+      s = fmaf(q_s[4 * i], f.x, s); s = fmaf(q_s[4 * i + 1], f.y, s);
+      s = fmaf(q_s[4 * i + 2], f.z, s); s = fmaf(q_s[4 * i + 3], f.w, s);
+    }
+    const float m_new = fmaxf(m, s);
+    const float a = exp2f(m - m_new), pj = exp2f(s - m_new);
+    l = l * a + pj;
+    const float4* vp = reinterpret_cast<const float4*>(vc + static_cast<size_t>(j) * 256);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 f = vp[i];
+      o[4 * i] = fmaf(pj, f.x, o[4 * i] * a); o[4 * i + 1] = fmaf(pj, f.y, o[4 * i + 1] * a);
+      o[4 * i + 2] = fmaf(pj, f.z, o[4 * i + 2] * a); o[4 * i + 3] = fmaf(pj, f.w, o[4 * i + 3] * a);
+    }
+    m = m_new;
+  }
+  red_m[tid] = m;
+  __syncthreads();
+  float gm = -INFINITY;
+  for (int i = 0; i < 128; ++i) gm = fmaxf(gm, red_m[i]);
+  const float w = (m == -INFINITY) ? 0.f : exp2f(m - gm);
+  red_l[tid] = l * w;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    float v = o[i] * w;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((tid & 31) == 0) red_o[tid >> 5][i] = v;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float lt = 0.f;
+    for (int i = 0; i < 128; ++i) lt += red_l[i];
+    const float v = red_o[0][tid] + red_o[1][tid] + red_o[2][tid] + red_o[3][tid];
+    out[static_cast<size_t>(n) * 256 + h * 64 + tid] = v / lt;
+  }
 }
 
 // =====================================================================================================================
@@ -276,14 +476,23 @@ p32_layernorm_kernel(const float* __restrict__ x, int rows, const float* __restr
   }
 }
 
+// optional per-channel affine (BatchNorm folded, FS:model:165-166: rows t >= len take pad_value BEFORE the affine)
 __global__ void p32_pad_input_kernel(const float* __restrict__ x, const int* __restrict__ cu, int Tmax, int Din,
-                                     int Kpad, float* __restrict__ out) {
+                                     int Kpad, float* __restrict__ out, const float* __restrict__ sc,
+                                     const float* __restrict__ sh, float pad_value) {
   const int row = blockIdx.x;
   const int b = row / Tmax, t = row - b * Tmax;
   const int start = cu[b], len = cu[b + 1] - start;
   const float* src = (t < len) ? x + static_cast<size_t>(start + t) * Din : nullptr;
   float* dst = out + static_cast<size_t>(row) * Kpad;
-  for (int i = threadIdx.x; i < Kpad; i += blockDim.x) dst[i] = (src && i < Din) ? __ldg(src + i) : 0.f;
+  for (int i = threadIdx.x; i < Kpad; i += blockDim.x) {
+    float v = 0.f;
+    if (i < Din) {
+      v = src ? __ldg(src + i) : pad_value;
+      if (sc) v = fmaf(v, sc[i], sh[i]);
+    }
+    dst[i] = v;
+  }
 }
 
 // GLU over channel halves (conformer/activation.py:40-42): out = a * sigmoid(b)
@@ -770,6 +979,21 @@ void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P
   else p32_gemm_kernel<P32_NONE><<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
 }
 
+bool launch_p32_rowvec(const __half* whi, const __half* wlo, const P32GemmParams& p, cudaStream_t st) {
+  const int R = p.n_seq * p.rows_per_seq;
+  if (R < 1 || R > kRvMaxRows || (p.k_blocks * 64) % 8 || p.lda % 4) return false;
+  const int grid = (p.N + kRvWarps * kRvCols - 1) / (kRvWarps * kRvCols);
+  if (p.act == P32_RELU) p32_rowvec_kernel<P32_RELU><<<grid, kRvWarps * 32, 0, st>>>(whi, wlo, p);
+  else if (p.act == P32_SWISH) p32_rowvec_kernel<P32_SWISH><<<grid, kRvWarps * 32, 0, st>>>(whi, wlo, p);
+  else p32_rowvec_kernel<P32_NONE><<<grid, kRvWarps * 32, 0, st>>>(whi, wlo, p);
+  return true;
+}
+
+void launch_p32_step_attn(const float* qkv, float* kcache, float* vcache, int n_seq, int cap, int pos, float scale,
+                          float* out, cudaStream_t st, const int* pos_dev) {
+  p32_step_attn_kernel<<<dim3(n_seq, 4), 128, 0, st>>>(qkv, kcache, vcache, cap, pos, pos_dev, scale, out);
+}
+
 void launch_p32_layernorm(const float* x, int rows, const float* g1, const float* b1, float* out1, const float* g2,
                           const float* b2, float* out2, float eps, const int* seq_len, int rows_per_seq,
                           cudaStream_t st) {
@@ -778,8 +1002,9 @@ void launch_p32_layernorm(const float* x, int rows, const float* g1, const float
                                                       rows_per_seq > 0 ? rows_per_seq : rows);
 }
 
-void launch_p32_pad_input(const float* x, const int* cu, int B, int Tmax, int Din, int Kpad, float* out, cudaStream_t st) {
-  p32_pad_input_kernel<<<B * Tmax, 128, 0, st>>>(x, cu, Tmax, Din, Kpad, out);
+void launch_p32_pad_input(const float* x, const int* cu, int B, int Tmax, int Din, int Kpad, float* out, cudaStream_t st,
+                          const float* sc, const float* sh, float pad_value) {
+  p32_pad_input_kernel<<<B * Tmax, 128, 0, st>>>(x, cu, Tmax, Din, Kpad, out, sc, sh, pad_value);
 }
 
 void launch_p32_glu(const float* h, int rows, float* out, cudaStream_t st) {

@@ -39,13 +39,21 @@ struct P32GemmParams {
 // tmWhi / tmWlo: 2-D (K, taps*N) fp16, box (64, 128), 128B swizzle
 void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P32GemmParams& p, cudaStream_t st);
 
+// The same product for at most 16 output rows (the per-frame streaming steps: 1 .. B * S rows): with so few rows the
+// GEMM is a weight-streaming matrix-vector product — L2-bandwidth bound, tensor cores idle either way — so it runs on
+// CUDA cores: every warp owns two output columns, lanes split K, the weights (fp16 hi [+ lo] planes, [taps*N][K]
+// row-major) are read once with 16-byte loads and reconstructed as fp32 (hi + lo is exact), activations stay fp32.
+// wlo == nullptr: single-plane fp16 weights (the FS-EEND streaming path).  Returns false if rows > 16.
+bool launch_p32_rowvec(const __half* whi, const __half* wlo, const P32GemmParams& p, cudaStream_t st);
+
 // y1 = g1 ? LN(x; g1, b1) : x  -> out1 (optional);  out2 = LN(y1; g2, b2) (optional).  Rows of 256 fp32.
 // seq_len (optional, with rows_per_seq): rows t >= seq_len[b] are written as zeros (both outputs).
 void launch_p32_layernorm(const float* x, int rows, const float* g1, const float* b1, float* out1, const float* g2,
                           const float* b2, float* out2, float eps, const int* seq_len, int rows_per_seq,
                           cudaStream_t st);
 // packed fp32 rows (cu_seqlens) -> [B][Tmax][Kpad] fp32, rows t >= len and columns >= Din are zero
-void launch_p32_pad_input(const float* x, const int* cu, int B, int Tmax, int Din, int Kpad, float* out, cudaStream_t st);
+void launch_p32_pad_input(const float* x, const int* cu, int B, int Tmax, int Din, int Kpad, float* out, cudaStream_t st,
+                          const float* sc = nullptr, const float* sh = nullptr, float pad_value = 0.f);
 // out[r][c] = h[r][c] * sigmoid(h[r][256 + c]),  h: [rows][512]
 void launch_p32_glu(const float* h, int rows, float* out, cudaStream_t st);
 // causal depthwise conv (K <= 32) + folded BatchNorm + swish on fp32 [n_seq][T][256]; hist: optional [n_seq][K-1][256]
@@ -72,6 +80,10 @@ void launch_p32_retention(const float* qkvg, const float* state, const float* cr
 // recurrent step: qkvg fp32 [n_seq][1024], state fp32 [n_seq][4][64][64] (updated), out fp32 [n_seq][256]
 void launch_p32_ret_step(const float* qkvg, float* state, int n_seq, int t, float* out, cudaStream_t st,
                          const int* t_dev);
+// Streaming attention step on fp32 (FS-EEND frame loop, FS:stream_mod:28-35): appends this frame's K / V rows of
+// qkv [n_seq][768] to the fp32 caches [n_seq][cap][256] at `pos`, then attends over keys 0..pos.  out fp32 [n_seq][256].
+void launch_p32_step_attn(const float* qkv, float* kcache, float* vcache, int n_seq, int cap, int pos, float scale,
+                          float* out, cudaStream_t st, const int* pos_dev);
 // rows [n_seq] of 256 fp32 copied (zero-filled when src == nullptr) into hist[n][pos]
 void launch_p32_hist_append(const float* src, float* hist, int n_seq, int cap, int pos, cudaStream_t st,
                             const int* pos_dev);

@@ -48,7 +48,7 @@ EXPORTS = [
     "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
     "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes", "fseend_op_spk_qkv_attn", "fseend_op_decide_median", "fseend_op_label_prepare", "fseend_op_splice_subsample",
     "fseend_op_bce_loss", "fseend_op_bce_loss_workspace_bytes",
-    "fseend_ls_forward_host", "fseend_ls_set_option", "fseend_ls_get_option", "fseend_p32_linear_create",
+    "fseend_fs_forward_host_async", "fseend_fs_host_wait", "fseend_ls_forward_host", "fseend_ls_set_option", "fseend_ls_get_option", "fseend_p32_linear_create",
     "fseend_p32_linear_destroy", "fseend_p32_linear_apply", "fseend_op_p32_retention",
 ]
 
@@ -75,6 +75,10 @@ def lib() -> C.CDLL:
     L.fseend_fs_forward.argtypes = [vp, vp, C.POINTER(ip), ip, ip, vp, vp, vp, vp]
     L.fseend_fs_forward_host.restype = ip
     L.fseend_fs_forward_host.argtypes = [vp, vp, C.POINTER(ip), ip, ip, vp, vp, vp]
+    L.fseend_fs_forward_host_async.restype = ip
+    L.fseend_fs_forward_host_async.argtypes = [vp, vp, C.POINTER(ip), ip, ip, vp, C.POINTER(C.c_longlong)]
+    L.fseend_fs_host_wait.restype = ip
+    L.fseend_fs_host_wait.argtypes = [vp, C.c_longlong]
     L.fseend_fs_set_profiling.restype = ip
     L.fseend_fs_set_profiling.argtypes = [vp, ip]
     L.fseend_fs_get_profile.restype = ip
@@ -293,6 +297,25 @@ class FsModel:
         _check(self._L.fseend_fs_forward_host(self._h, _ptr(x_packed), il, B, max_nspks, _ptr(logits), _ptr(emb),
                                               _ptr(att)))
         return logits, emb, att
+
+    def forward_host_async(self, x_packed: torch.Tensor, ilens: Sequence[int], max_nspks: int, out: torch.Tensor) -> int:
+        """Pipelined host-buffer entry point: enqueues H2D + forward + D2H and returns a ticket; ``host_wait(ticket)``
+        blocks until ``out`` (CPU fp32 [B, T, S], ideally pinned) holds the logits.  Two calls may be in flight, so
+        the copy of the next batch overlaps the kernels of the current one.  ``x_packed`` and ``out`` must stay alive
+        and untouched until the wait."""
+        if x_packed.is_cuda or x_packed.dtype != torch.float32 or not x_packed.is_contiguous():
+            raise FseendError("forward_host_async takes a contiguous CPU float32 tensor")
+        B, T = len(ilens), int(max(ilens))
+        if out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != B * T * max_nspks:
+            raise FseendError("out must be a contiguous CPU float32 tensor of B * T * max_nspks elements")
+        il = (C.c_int * B)(*[int(i) for i in ilens])
+        ticket = C.c_longlong(-1)
+        _check(self._L.fseend_fs_forward_host_async(self._h, _ptr(x_packed), il, B, max_nspks, _ptr(out),
+                                                    C.byref(ticket)))
+        return int(ticket.value)
+
+    def host_wait(self, ticket: int):
+        _check(self._L.fseend_fs_host_wait(self._h, int(ticket)))
 
     def set_option(self, key: str, value: int):
         _check(self._L.fseend_fs_set_option(self._h, key.encode(), int(value)))

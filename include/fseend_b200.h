@@ -75,6 +75,13 @@ int fseend_fs_forward(fseend_fs_model* m, const float* x_packed_dev, const int* 
 /* Same with HOST buffers (pinned or pageable): H2D copy, forward, D2H copy, stream synchronise. */
 int fseend_fs_forward_host(fseend_fs_model* m, const float* x_packed_host, const int* ilens_host, int B,
                            int max_nspks, float* logits_host, float* emb_host, float* att_host);
+/* Pipelined host-buffer form: enqueue one forward (H2D on a copy stream, kernels + D2H on a compute stream) and return a
+ * ticket.  Two calls may be in flight, so the copy of call i+1 overlaps the kernels of call i; fseend_fs_host_wait
+ * blocks until the ticket's logits are in logits_host.  x_packed_host and logits_host must stay valid until then and
+ * should be pinned (cudaHostAlloc) for the copies to be asynchronous.  Logits are [B][max ilen][max_nspks]. */
+int fseend_fs_forward_host_async(fseend_fs_model* m, const float* x_packed_host, const int* ilens_host, int B,
+                                 int max_nspks, float* logits_host, long long* ticket);
+int fseend_fs_host_wait(fseend_fs_model* m, long long ticket);
 
 /* Tuning switches.  "ffn": 0 = two GEMM launches (hidden activations through HBM); fused FFN kernel:
  * 1 = hidden chunk via smem, 2 = 1 + 2-CTA clusters sharing weight tiles by TMA multicast, 3 = hidden chunk kept in

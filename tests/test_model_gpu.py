@@ -79,6 +79,28 @@ def test_host_buffer_entry_point_matches_device_entry_point():
     assert torch.equal(dev_logits.cpu(), host_logits)
 
 
+def test_pipelined_host_entry_point_matches_blocking_call():
+    """fseend_fs_forward_host_async / host_wait: five calls with different inputs, two in flight at any time; every
+    result equals the blocking host call's (bitwise: same kernels, same plan)."""
+    sd, src, lens, S, cfg, g = load_case("ragged_S6")
+    m = make_model(sd)
+    nat = m.native()
+    xs = [(torch.cat(src) * (1.0 + 0.1 * i)).contiguous().pin_memory() for i in range(5)]
+    want = [nat.forward_host(x, lens, S)[0] for x in xs]
+    outs = [torch.empty(len(lens), max(lens), S).pin_memory() for _ in range(5)]
+    tickets = []
+    for i, x in enumerate(xs):
+        tickets.append(nat.forward_host_async(x, lens, S, outs[i]))
+        if i >= 1:
+            nat.host_wait(tickets[i - 1])
+            assert torch.equal(outs[i - 1], want[i - 1])
+    nat.host_wait(tickets[-1])
+    assert torch.equal(outs[-1], want[-1])
+    nat.host_wait(tickets[0])                      # waiting on an old ticket is a no-op
+    with pytest.raises(Exception):
+        nat.host_wait(10 ** 6)
+
+
 @pytest.mark.parametrize("chunks", [1, 2, 4])
 def test_host_entry_point_chunked_copy_compute_overlap(chunks):
     """forward_host splits the batch into chunks of whole sequences (copy of chunk i+1 under the kernels of chunk i);
@@ -181,7 +203,10 @@ def _run_stream(stream, x, S):
     return torch.cat(ys, dim=1)
 
 
-def test_streaming_matches_reference_stream_golden():
+@pytest.mark.parametrize("rv", ["1", "0"])
+def test_streaming_matches_reference_stream_golden(monkeypatch, rv):
+    """rv=1: the small-row CUDA-core step (default for B * S <= 16 rows); rv=0: the 128-row tcgen05 tile kernels."""
+    monkeypatch.setenv("FSEEND_STREAM_RV", rv)
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stream_T60_S6.npz"))
     sd = O.random_state_dict(seed=4, trained_like=True)
     masked, stream = _make_stream(sd)
@@ -241,7 +266,13 @@ def test_streaming_infer_dia_body_on_wide_logits():
     assert torch.allclose(pred, torch.sigmoid(torch.from_numpy(g["stream"])[:, 1:]), atol=1e-4, rtol=1e-4)
 
 
-def test_streaming_equals_batch_path_two_recordings_and_cache_growth():
+@pytest.mark.parametrize("rv", ["1", "0"])
+def test_streaming_equals_batch_path_two_recordings_and_cache_growth(monkeypatch, rv):
+    monkeypatch.setenv("FSEEND_STREAM_RV", rv)
+    _streaming_equals_batch()
+
+
+def _streaming_equals_batch():
     """The reference's own invariant (streaming_infer_dia.py:97): frame-by-frame == batch.  Two recordings in
     parallel, 1100 frames (> the initial 1024-frame cache capacity, so the caches are re-allocated mid-stream)."""
     sd = O.random_state_dict(seed=9, trained_like=True)
