@@ -205,7 +205,7 @@ struct fseend_fs_stream {
   // fp32 activations / caches instead of 128-row tcgen05 tiles (FSEEND_STREAM_RV=0 keeps the tile kernels).
   bool rv = false;
   std::vector<std::unique_ptr<DevBuf>> enc_k32, enc_v32, dec_k32, dec_v32;
-  DevBuf hist32, rX, rh0, rh1, rqkv, rao, rf, ra0, ra1, ra2, rT1, remb, rY;
+  DevBuf hist32, rX, rh0, rh1, rqkv, rao, rf, ra0, ra1, ra2, rT1, remb, rY, epi_ctr;
   ~fseend_fs_stream() {
     if (graph_step) cudaGraphExecDestroy(graph_step);
     if (graph_flush) cudaGraphExecDestroy(graph_flush);
@@ -771,6 +771,8 @@ void stream_init(fseend_fs_stream* s, fseend_fs_model* m, int B, int S) {
     s->rT1.alloc(Rd * D * f);
     s->remb.alloc(1ull * B * D * f);
     s->rY.alloc(1ull * B * D * f);
+    s->epi_ctr.alloc(sizeof(unsigned int));
+    CUDA_CHECK(cudaMemset(s->epi_ctr.p, 0, sizeof(unsigned int)));
   }
   s->x16.alloc(1ull * B * m->Kin * 2);
   s->h0.alloc(1ull * B * D * 2);
@@ -833,7 +835,9 @@ void stream_launch_rv(fseend_fs_stream* s, const float* x_in, bool decode, float
   const int* enc_pos = static_cast<const int*>(s->ctr.p);
   const int* dec_pos = enc_pos + 1;
   auto F = [](DevBuf& b) { return static_cast<float*>(b.p); };
-  auto lin = [&](const float* A, int rows, const WMat& w, const float* bias, int act, const float* res, float* out) {
+  // product (+ optional LayerNorm of the 256-wide result into `ln_out`, fused into the same launch)
+  auto lin = [&](const float* A, int rows, const WMat& w, const float* bias, int act, const float* res, float* out,
+                 const FVec* ln_g = nullptr, const FVec* ln_b = nullptr, float* ln_out = nullptr) {
     P32GemmParams p{};
     p.A = A;
     p.lda = w.K;
@@ -851,26 +855,27 @@ void stream_launch_rv(fseend_fs_stream* s, const float* x_in, bool decode, float
     p.ldr = w.rows;
     p.out = out;
     p.ldo = w.rows;
+    if (ln_out) {
+      p.row_epi_counter = static_cast<unsigned int*>(s->epi_ctr.p);
+      p.ln_g1 = ln_g->f();
+      p.ln_b1 = ln_b->f();
+      p.ln_out1 = ln_out;
+      p.ln_eps = c.ln_eps;
+    }
     if (!launch_p32_rowvec(static_cast<const __half*>(w.buf.p), nullptr, p, st))
       throw std::runtime_error("row-vector kernel rejected the shape");
-  };
-  auto ln = [&](const float* x, int rows, const FVec& g, const FVec& b, float* out) {
-    launch_p32_layernorm(x, rows, g.f(), b.f(), out, nullptr, nullptr, nullptr, c.ln_eps, nullptr, 0, st);
   };
   if (x_in) {
     launch_p32_pad_input(x_in, static_cast<const int*>(s->cu.p), B, 1, c.in_size, m->Kin, F(s->rX), st, m->bn_scale.f(),
                          m->bn_shift.f(), -1.f);
-    lin(F(s->rX), B, m->w_in, m->b_in.f(), P32_NONE, nullptr, F(s->rT1));
-    ln(F(s->rT1), B, m->g_in, m->be_in, F(s->rh0));
+    lin(F(s->rX), B, m->w_in, m->b_in.f(), P32_NONE, nullptr, F(s->rT1), &m->g_in, &m->be_in, F(s->rh0));
     for (int l = 0; l < c.enc_n_layers; ++l) {
       EncLayer& E = *m->enc[l];
       lin(F(s->rh0), B, E.wqkv, E.bqkv.f(), P32_NONE, nullptr, F(s->rqkv));
       launch_p32_step_attn(F(s->rqkv), F(*s->enc_k32[l]), F(*s->enc_v32[l]), B, s->cap, 0, scale, F(s->rao), st, enc_pos);
-      lin(F(s->rao), B, E.wo, E.bo.f(), P32_NONE, F(s->rh0), F(s->rT1));
-      ln(F(s->rT1), B, E.g1, E.be1, F(s->rh1));
+      lin(F(s->rao), B, E.wo, E.bo.f(), P32_NONE, F(s->rh0), F(s->rT1), &E.g1, &E.be1, F(s->rh1));
       lin(F(s->rh1), B, E.w1, E.b1.f(), P32_RELU, nullptr, F(s->rf));
-      lin(F(s->rf), B, E.w2, E.b2.f(), P32_NONE, F(s->rh1), F(s->rT1));
-      ln(F(s->rT1), B, E.g2, E.be2, F(s->rh0));
+      lin(F(s->rf), B, E.w2, E.b2.f(), P32_NONE, F(s->rh1), F(s->rT1), &E.g2, &E.be2, F(s->rh0));
     }
     launch_p32_hist_append(F(s->rh0), F(s->hist32), B, s->cap, 0, st, enc_pos);
   } else {
@@ -898,9 +903,10 @@ void stream_launch_rv(fseend_fs_stream* s, const float* x_in, bool decode, float
     p.w_inv_scale = 1.f;
     p.out = F(s->remb);
     p.ldo = D;
+    p.row_epi_counter = static_cast<unsigned int*>(s->epi_ctr.p);     // L2 normalisation fused (last-CTA ticket)
+    p.l2norm = 1;
     if (!launch_p32_rowvec(static_cast<const __half*>(m->w_conv.buf.p), nullptr, p, st))
       throw std::runtime_error("row-vector kernel rejected the conv shape");
-    launch_p32_l2norm(F(s->remb), B, st);
   }
   lin(F(s->remb), B, m->w_cvt, nullptr, P32_NONE, nullptr, F(s->rY));
   launch_p32_convert(F(s->rY), m->pe_proj.f(), B, S, F(s->ra0), st);
@@ -908,15 +914,12 @@ void stream_launch_rv(fseend_fs_stream* s, const float* x_in, bool decode, float
     DecLayer& Dl = *m->dec[l];
     lin(F(s->ra0), Rd, Dl.wqkv1, Dl.bqkv1.f(), P32_NONE, nullptr, F(s->rqkv));
     launch_p32_step_attn(F(s->rqkv), F(*s->dec_k32[l]), F(*s->dec_v32[l]), Rd, s->cap, 0, scale, F(s->rao), st, dec_pos);
-    lin(F(s->rao), Rd, Dl.wo1, Dl.bo1.f(), P32_NONE, F(s->ra0), F(s->rT1));
-    ln(F(s->rT1), Rd, Dl.g11, Dl.be11, F(s->ra1));
+    lin(F(s->rao), Rd, Dl.wo1, Dl.bo1.f(), P32_NONE, F(s->ra0), F(s->rT1), &Dl.g11, &Dl.be11, F(s->ra1));
     lin(F(s->ra1), Rd, Dl.wqkv2, Dl.bqkv2.f(), P32_NONE, nullptr, F(s->rqkv));
     launch_p32_spk_attn(F(s->rqkv), F(s->rao), B, S, scale, st);
-    lin(F(s->rao), Rd, Dl.wo2, Dl.bo2.f(), P32_NONE, F(s->ra1), F(s->rT1));
-    ln(F(s->rT1), Rd, Dl.g21, Dl.be21, F(s->ra2));
+    lin(F(s->rao), Rd, Dl.wo2, Dl.bo2.f(), P32_NONE, F(s->ra1), F(s->rT1), &Dl.g21, &Dl.be21, F(s->ra2));
     lin(F(s->ra2), Rd, Dl.w1, Dl.b1.f(), P32_RELU, nullptr, F(s->rf));
-    lin(F(s->rf), Rd, Dl.w2, Dl.b2.f(), P32_NONE, F(s->ra2), F(s->rT1));
-    ln(F(s->rT1), Rd, Dl.g22, Dl.be22, F(s->ra0));
+    lin(F(s->rf), Rd, Dl.w2, Dl.b2.f(), P32_NONE, F(s->ra2), F(s->rT1), &Dl.g22, &Dl.be22, F(s->ra0));
   }
   launch_p32_head(F(s->remb), F(s->ra0), B, S, y_out, nullptr, nullptr, st);
   launch_advance_counters(static_cast<int*>(s->ctr.p), 1, 1, 0, 0, st);

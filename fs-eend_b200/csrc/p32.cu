@@ -242,6 +242,8 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
 // Small-row form of the same product (see p32.cuh): at most 16 output rows.  CTA = 8 warps x 2 output columns; K is
 // walked in blocks of 512 whose activations (R x 512 fp32) are staged in shared memory once per CTA.
 constexpr int kRvMaxRows = 16, kRvKB = 512, kRvCols = 2, kRvWarps = 8;
+__device__ __forceinline__ void warp_ln8(float (&v)[8], const float* g, const float* b, int lane, float eps);
+__device__ __forceinline__ void rowvec_row_epilogue(const P32GemmParams& p, int R);
 
 template <int kAct>
 __global__ void __launch_bounds__(kRvWarps * 32)
@@ -321,7 +323,7 @@ p32_rowvec_kernel(const __half* __restrict__ whi, const __half* __restrict__ wlo
       }
     }
   }
-  if (n0 >= p.N) return;
+  if (n0 < p.N) {
 #pragma unroll
   for (int cc = 0; cc < kRvCols; ++cc)
 #pragma unroll
@@ -346,6 +348,53 @@ p32_rowvec_kernel(const __half* __restrict__ whi, const __half* __restrict__ wlo
         p.out[static_cast<size_t>(r) * p.ldo + n] = x;
       }
     }
+  }
+  if (p.row_epi_counter) rowvec_row_epilogue(p, R);
+}
+
+// Fused row epilogue of the row-vector product (see P32GemmParams::row_epi_counter): runs in the last CTA to finish.
+__device__ __forceinline__ void rowvec_row_epilogue(const P32GemmParams& p, int R) {
+  __shared__ bool is_last;
+  __threadfence();                                   // this CTA's output columns are visible device-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(p.row_epi_counter, 1u);
+    is_last = prev == gridDim.x - 1;
+    if (is_last) *p.row_epi_counter = 0u;            // ready for the next launch on this stream
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < R; r += kRvWarps) {
+    const float4* xp = reinterpret_cast<const float4*>(p.out + static_cast<size_t>(r) * p.ldo);
+    const float4 a = __ldcg(xp + lane), b = __ldcg(xp + 32 + lane);      // L2 (other CTAs wrote these): bypass L1
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (p.l2norm) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+      const float inv = 1.f / sqrtf(ss);
+      float4* op = reinterpret_cast<float4*>(p.out + static_cast<size_t>(r) * p.ldo);
+      op[lane] = make_float4(v[0] * inv, v[1] * inv, v[2] * inv, v[3] * inv);
+      op[32 + lane] = make_float4(v[4] * inv, v[5] * inv, v[6] * inv, v[7] * inv);
+      continue;
+    }
+    if (p.ln_g1) warp_ln8(v, p.ln_g1, p.ln_b1, lane, p.ln_eps);
+    if (p.ln_out1) {
+      float4* op = reinterpret_cast<float4*>(p.ln_out1 + static_cast<size_t>(r) * 256);
+      op[lane] = make_float4(v[0], v[1], v[2], v[3]);
+      op[32 + lane] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (p.ln_out2) {
+      warp_ln8(v, p.ln_g2, p.ln_b2, lane, p.ln_eps);
+      float4* op = reinterpret_cast<float4*>(p.ln_out2 + static_cast<size_t>(r) * 256);
+      op[lane] = make_float4(v[0], v[1], v[2], v[3]);
+      op[32 + lane] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
 }
 
 // Streaming attention step in fp32 (see elementwise.cu: step_attn_kernel for the fp16-cache form).
@@ -982,6 +1031,7 @@ void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P
 bool launch_p32_rowvec(const __half* whi, const __half* wlo, const P32GemmParams& p, cudaStream_t st) {
   const int R = p.n_seq * p.rows_per_seq;
   if (R < 1 || R > kRvMaxRows || (p.k_blocks * 64) % 8 || p.lda % 4) return false;
+  if (p.row_epi_counter && (p.N != 256 || p.ldo != 256)) return false;
   const int grid = (p.N + kRvWarps * kRvCols - 1) / (kRvWarps * kRvCols);
   if (p.act == P32_RELU) p32_rowvec_kernel<P32_RELU><<<grid, kRvWarps * 32, 0, st>>>(whi, wlo, p);
   else if (p.act == P32_SWISH) p32_rowvec_kernel<P32_SWISH><<<grid, kRvWarps * 32, 0, st>>>(whi, wlo, p);

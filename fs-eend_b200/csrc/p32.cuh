@@ -35,6 +35,19 @@ struct P32GemmParams {
   int ldr;
   float* out;
   int ldo;
+  // Row-vector kernel only (N == 256): fused row epilogue, executed by the LAST CTA of the launch to finish (threadfence +
+  // atomic ticket; the counter is reset for the next launch): y1 = ln_g1 ? LN(out row; g1, b1) : out row -> ln_out1
+  // (optional); ln_out2 = LN(y1; g2, b2) (optional); or, with l2norm != 0, out row /= ||out row||_2 in place.
+  // Saves one dependent launch per LayerNorm in the per-frame streaming steps.
+  unsigned int* row_epi_counter = nullptr;
+  const float* ln_g1 = nullptr;
+  const float* ln_b1 = nullptr;
+  float* ln_out1 = nullptr;
+  const float* ln_g2 = nullptr;
+  const float* ln_b2 = nullptr;
+  float* ln_out2 = nullptr;
+  float ln_eps = 1e-5f;
+  int l2norm = 0;
 };
 // tmWhi / tmWlo: 2-D (K, taps*N) fp16, box (64, 128), 128B swizzle
 void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P32GemmParams& p, cudaStream_t st);

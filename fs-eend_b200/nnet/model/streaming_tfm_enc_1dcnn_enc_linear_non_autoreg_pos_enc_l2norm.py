@@ -69,10 +69,11 @@ class StreamingTransformerEDADiarization(NativeCacheMixin, nn.Module):
         dev = self.cnn.conv.weight.device
         if dev.type != "cuda":
             raise RuntimeError("fseend_b200 runs on a CUDA sm_100 device only (move the model with .cuda())")
-        native = self.native()
         B = x_t.shape[0]
         if self._stream is None:
-            self._stream = FsStream(native, B, max_nspks)
+            # the parameter check (native()) walks every tensor of the model: done when a recording starts, not once per
+            # 100-ms frame — weights edited mid-recording take effect after reset() / invalidate_native()
+            self._stream = FsStream(self.native(), B, max_nspks)
             self.cnn.t = 0
         if self._stream.B != B or self._stream.S != max_nspks:
             raise ValueError("batch size / max_nspks changed mid-stream; call reset() first")
