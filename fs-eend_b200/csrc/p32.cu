@@ -5,6 +5,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 
@@ -236,6 +237,219 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =====================================================================================================================
+// Persistent, warp-specialised form of the split-precision GEMM (the batch path's kernel; the one-tile kernel above stays
+// for small grids).  One CTA (16 warps) per SM walks output tiles; inside it
+//   warps 0-6  : A producers — fp32 rows from global, fetched TWO k-blocks ahead into registers (ncu on the first
+//                persistent version, one k-block ahead: 2700 clk per k-block = the loaded-L2/HBM latency, tensor pipe 28 %
+//                active; bandwidth x latency asks for ~100 KB in flight per SM, the register budget allows 64 KB), hi / lo split with packed
+//                conversions, swizzled smem stores, arrive on the stage's `full` barrier; thread 0 also issues the TMA
+//                for W_hi / W_lo
+//   warp 7     : MMA issuer — 12 tcgen05.mma per k-block into one of FOUR 128-column TMEM accumulators (fresh per k-block:
+//                the tensor core truncates on accumulate, see above), commits `empty[stage]` and `acc_full[buf]`
+//   warps 8-15 : fold each finished k-block accumulator into fp32 registers (64 columns per thread, round-to-nearest) and
+//                release it; after a tile's last k-block write the row through a padded smem tile and store whole rows
+// so the operand split, the register fold and the epilogue of tile i all overlap the MMAs (of tile i+1).  16 warps keep
+// the register budget at 128 per thread (17 warps are allocated as 20: 96 registers and spills in both hot roles).
+constexpr int kPStages = 2, kPAcc = 4;
+constexpr int kPLdT = BN + 4;
+constexpr int kPersistSmem = kPStages * kStageBytes + BM * kPLdT * 4 + 1024;
+constexpr int kPThreads = 16 * 32;
+constexpr int kPProd = 7 * 32;                       // producer threads
+
+template <int kAct>
+__global__ void __launch_bounds__(kPThreads, 1)
+p32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
+                        const P32GemmParams p, const int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kPStages];
+  __shared__ __align__(8) uint64_t empty_bar[kPStages];
+  __shared__ __align__(8) uint64_t acc_full[kPAcc];
+  __shared__ __align__(8) uint64_t acc_empty[kPAcc];
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* tile_s = reinterpret_cast<float*>(smem + kPStages * kStageBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kPStages; ++s) {
+      mbar_init(&full_bar[s], kPProd);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < kPAcc; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 256);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmWhi);
+    tma_prefetch_desc(&tmWlo);
+  }
+  if (warp == 7) tmem_alloc(&tmem_base_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int n_tiles_n = p.N / BN;
+  const int tiles_per_seq = (p.rows_per_seq + BM - 1) / BM;
+  const int total_it = p.taps * p.k_blocks;
+  const int a_off = p.a_row_offset + (p.a_row_offset_dev ? *p.a_row_offset_dev : 0);
+  const int n_local = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const uint32_t G = static_cast<uint32_t>(n_local) * total_it;        // k-blocks this CTA processes, in order
+
+  if (warp < 7) {
+    // ------------------------------------------------------------ A producers (+ W TMA by thread 0)
+    // k-block gi of this CTA = (tile blockIdx.x + (gi / total_it) * gridDim.x, it = gi % total_it)
+    auto fetch = [&](float4 (&buf)[10], uint32_t gi) {
+      if (gi >= G) return;
+      const int tile = blockIdx.x + (gi / total_it) * gridDim.x, it = gi % total_it;
+      const int m_tile = tile / n_tiles_n;
+      const int seq = m_tile / tiles_per_seq, t0 = (m_tile % tiles_per_seq) * BM;
+      const int tap = it / p.k_blocks, kb = it - tap * p.k_blocks;
+      const float* a_seq = p.A + static_cast<size_t>(seq) * p.a_seq_rows * p.lda;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int q = tid + kPProd * i;                     // 1024 chunks of 8 floats over 224 threads
+        const int r = q >> 3, c = q & 7;
+        const int t = t0 + r;
+        const int arow = t + tap + p.tap_shift + a_off;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (q < 1024 && t < p.rows_per_seq && arow >= 0 && arow < p.a_seq_rows) {
+          const float4* src = reinterpret_cast<const float4*>(a_seq + static_cast<size_t>(arow) * p.lda + kb * BK + c * 8);
+          v0 = __ldg(src);
+          v1 = __ldg(src + 1);
+        }
+        buf[2 * i] = v0;
+        buf[2 * i + 1] = v1;
+      }
+    };
+    auto step = [&](float4 (&buf)[10], uint32_t gi) {
+      const int s = gi % kPStages;
+      mbar_wait(&empty_bar[s], ((gi / kPStages) & 1) ^ 1, 81);
+      uint8_t* sAhi = smem + s * kStageBytes;
+      uint8_t* sAlo = sAhi + kTileBytes;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int q = tid + kPProd * i;
+        if (q < 1024) {
+          const int r = q >> 3, c = q & 7;
+          uint4 hi, lo;
+          split8(buf[2 * i], buf[2 * i + 1], hi, lo);
+          const uint32_t off = sw128_offset(r, c);
+          *reinterpret_cast<uint4*>(sAhi + off) = hi;
+          *reinterpret_cast<uint4*>(sAlo + off) = lo;
+        }
+      }
+      fetch(buf, gi + 2);                                   // refill this register set two k-blocks ahead
+      fence_proxy_async_smem();
+      if (tid == 0) {
+        const int tile = blockIdx.x + (gi / total_it) * gridDim.x, it = gi % total_it;
+        const int n0 = (tile % n_tiles_n) * BN;
+        const int tap = it / p.k_blocks, kb = it - tap * p.k_blocks;
+        mbar_arrive_expect_tx(&full_bar[s], 2 * kTileBytes);
+        tma_load_2d(sAlo + kTileBytes, &tmWhi, &full_bar[s], kb * BK, tap * p.N + n0);
+        tma_load_2d(sAlo + 2 * kTileBytes, &tmWlo, &full_bar[s], kb * BK, tap * p.N + n0);
+      } else {
+        mbar_arrive(&full_bar[s]);
+      }
+    };
+    float4 b0[10], b1[10];
+    fetch(b0, 0);
+    fetch(b1, 1);
+    for (uint32_t gi = 0; gi < G; gi += 2) {
+      step(b0, gi);
+      if (gi + 1 < G) step(b1, gi + 1);
+    }
+  } else if (warp == 7) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN, false);
+    for (uint32_t g = 0; g < G; ++g) {
+      const int s = g % kPStages, buf = g % kPAcc;
+      mbar_wait(&full_bar[s], (g / kPStages) & 1, 82);
+      mbar_wait(&acc_empty[buf], ((g / kPAcc) & 1) ^ 1, 83);
+      tc_fence_after();
+      const uint32_t sb = smem_u32(smem + s * kStageBytes);
+      const uint64_t dAhi = smem_desc_sw128(sb), dAlo = smem_desc_sw128(sb + kTileBytes);
+      const uint64_t dWhi = smem_desc_sw128(sb + 2 * kTileBytes), dWlo = smem_desc_sw128(sb + 3 * kTileBytes);
+      const uint32_t d = tmem_base + buf * 128;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          umma_f16(d, dAlo + 2 * kk, dWhi + 2 * kk, idesc, kk > 0 ? 1u : 0u);
+          umma_f16(d, dAhi + 2 * kk, dWlo + 2 * kk, idesc, 1u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) umma_f16(d, dAhi + 2 * kk, dWhi + 2 * kk, idesc, 1u);
+        umma_commit(&empty_bar[s]);
+        umma_commit(&acc_full[buf]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------ fold + epilogue warps 8-15: thread <-> (row, column half)
+    const int wq = warp & 3, half = (warp - 8) >> 2;
+    const int r = wq * 32 + lane;
+    const uint32_t t_addr = (static_cast<uint32_t>(wq * 32) << 16) + half * 64;
+    const int ew = warp - 8;                               // 0..7: rows ew, ew + 8, ... in the store phase
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m_tile = tile / n_tiles_n;
+      const int seq = m_tile / tiles_per_seq, t0 = (m_tile % tiles_per_seq) * BM;
+      const int n0 = (tile % n_tiles_n) * BN;
+      float acc[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      for (int it = 0; it < total_it; ++it, ++g) {
+        const int buf = g % kPAcc;
+        mbar_wait(&acc_full[buf], (g / kPAcc) & 1, 84);
+        tc_fence_after();
+        uint32_t ra[32], rb[32];
+        tmem_ld32(tmem_base + buf * 128 + t_addr, ra);
+        tmem_ld32(tmem_base + buf * 128 + t_addr + 32, rb);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);                     // the accumulator is in registers: release it before the adds
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          acc[j] += __uint_as_float(ra[j]);
+          acc[32 + j] += __uint_as_float(rb[j]);
+        }
+      }
+      // row -> padded smem tile -> whole rows out (512-byte coalesced residual loads and stores)
+      named_bar_sync(1, 256);                             // the previous tile's rows have been read out of tile_s
+      {
+        float* trow = tile_s + r * kPLdT + half * 64;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) *reinterpret_cast<float4*>(trow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      }
+      named_bar_sync(1, 256);
+      const int col = n0 + 4 * lane;
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      const float wsc = p.w_inv_scale, alpha = p.alpha;
+      for (int rr = ew; rr < BM; rr += 8) {
+        const int t = t0 + rr;
+        if (t >= p.rows_per_seq) break;
+        const size_t orow = static_cast<size_t>(seq) * p.rows_per_seq + t;
+        const float4 a = *reinterpret_cast<const float4*>(tile_s + rr * kPLdT + 4 * lane);
+        float4 v;
+        v.x = alpha * act_apply<kAct>(fmaf(a.x, wsc, bb.x));
+        v.y = alpha * act_apply<kAct>(fmaf(a.y, wsc, bb.y));
+        v.z = alpha * act_apply<kAct>(fmaf(a.z, wsc, bb.z));
+        v.w = alpha * act_apply<kAct>(fmaf(a.w, wsc, bb.w));
+        if (p.residual) {
+          const float4 rs = *reinterpret_cast<const float4*>(p.residual + orow * p.ldr + col);
+          v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w;
+        }
+        *reinterpret_cast<float4*>(p.out + orow * p.ldo + col) = v;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 7) tmem_dealloc(tmem_base, 512);
 }
 
 // =====================================================================================================================
@@ -1023,6 +1237,23 @@ void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P
   }
   const int tiles_per_seq = (p.rows_per_seq + BM - 1) / BM;
   const int grid = p.n_seq * tiles_per_seq * (p.N / BN);
+  // persistent warp-specialised kernel once there is more than one tile per SM (FSEEND_P32_GEMM=0: always one-tile)
+  static int num_sms = 0, use_persist = 1;
+  if (!num_sms) {
+    cudaFuncSetAttribute(p32_gemm_persist_kernel<P32_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmem);
+    cudaFuncSetAttribute(p32_gemm_persist_kernel<P32_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmem);
+    cudaFuncSetAttribute(p32_gemm_persist_kernel<P32_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmem);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (const char* e = getenv("FSEEND_P32_GEMM")) use_persist = e[0] != '0';
+  }
+  if (use_persist && grid > num_sms) {
+    if (p.act == P32_RELU) p32_gemm_persist_kernel<P32_RELU><<<num_sms, kPThreads, kPersistSmem, st>>>(tmWhi, tmWlo, p, grid);
+    else if (p.act == P32_SWISH) p32_gemm_persist_kernel<P32_SWISH><<<num_sms, kPThreads, kPersistSmem, st>>>(tmWhi, tmWlo, p, grid);
+    else p32_gemm_persist_kernel<P32_NONE><<<num_sms, kPThreads, kPersistSmem, st>>>(tmWhi, tmWlo, p, grid);
+    return;
+  }
   if (p.act == P32_RELU) p32_gemm_kernel<P32_RELU><<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
   else if (p.act == P32_SWISH) p32_gemm_kernel<P32_SWISH><<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
   else p32_gemm_kernel<P32_NONE><<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
