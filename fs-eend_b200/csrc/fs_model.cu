@@ -1599,6 +1599,16 @@ int fseend_op_bce_loss(const float* logits, int ld_logits, const float* target, 
   });
 }
 
+int fseend_op_pit_costs(const float* logits, const float* labels, int B, int T, int C, const int* lens_dev,
+                        int label_delay, int pad_term, double* cost_dev, void* stream) {
+  return guarded([&] {
+    if (launch_pit_costs(logits, labels, B, T, C, lens_dev, label_delay, pad_term, cost_dev,
+                         static_cast<cudaStream_t>(stream)) != 0)
+      throw std::invalid_argument("pit_costs: need B, T >= 1, 1 <= C <= 16, label_delay >= 0");
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
 int fseend_op_splice_subsample(const float* feat, int T, int F, int context_size, int subsampling, float* out,
                                void* stream) {
   return guarded([&] {

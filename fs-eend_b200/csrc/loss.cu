@@ -105,7 +105,47 @@ __global__ void bce_finalize_kernel(const float* __restrict__ partial, int B, in
   *loss = static_cast<float>(tot / static_cast<double>(frames));
 }
 
+// PIT pair costs (reference train/utils/loss.py:69-96 pit_loss, :257-327 batch_pit_n_speaker_loss, :329-403 its
+// label-delay form): cost[b][i][j] = sum over frames t in [0, len_b - delay) of BCEWithLogits(y[b][t + delay][i],
+// lab[b][t][j]) (+ pad_frames_b * BCEWithLogits(-1, -1) when `pad_term`: the reference pads predictions AND labels of
+// shorter recordings with -1 and sums over the padded frames too).  Element-wise fp32 as torch computes it, fixed-order
+// fp64 accumulation (bit-reproducible).  One block per (b, i * C + j).
+__global__ void __launch_bounds__(256)
+pit_cost_kernel(const float* __restrict__ logits, const float* __restrict__ labels, int T, int C,
+                const int* __restrict__ lens, int delay, int pad_term, double* __restrict__ cost) {
+  const int b = blockIdx.y, i = blockIdx.x / C, j = blockIdx.x % C, tid = threadIdx.x;
+  const int len = min(lens[b], T);
+  const int n = max(len - delay, 0);
+  const float* y = logits + static_cast<size_t>(b) * T * C;
+  const float* z = labels + static_cast<size_t>(b) * T * C;
+  double acc = 0.0;
+  for (int t = tid; t < n; t += 256) {
+    const float x = y[static_cast<size_t>(t + delay) * C + i];
+    const float tg = z[static_cast<size_t>(t) * C + j];
+    acc += static_cast<double>(fmaxf(x, 0.f) - x * tg + log1pf(expf(-fabsf(x))));
+  }
+  __shared__ double red[256];
+  red[tid] = acc;
+  __syncthreads();
+  for (int sft = 128; sft > 0; sft >>= 1) {
+    if (tid < sft) red[tid] += red[tid + sft];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double v = red[0];
+    if (pad_term) v += static_cast<double>(T - len) * static_cast<double>(0.f - (-1.f) * (-1.f) + log1pf(expf(-1.f)));
+    cost[(static_cast<size_t>(b) * C + i) * C + j] = v;
+  }
+}
+
 }  // namespace
+
+int launch_pit_costs(const float* logits, const float* labels, int B, int T, int C, const int* lens, int delay,
+                     int pad_term, double* cost, cudaStream_t stream) {
+  if (C < 1 || C > 16 || B < 1 || T < 1 || delay < 0) return -1;
+  pit_cost_kernel<<<dim3(C * C, B), 256, 0, stream>>>(logits, labels, T, C, lens, delay, pad_term, cost);
+  return 0;
+}
 
 int launch_label_prepare(const float* labels, int B, int T, int C, int* perm, float* out, cudaStream_t stream) {
   if (C < 1 || C > kMaxSpk) return -1;

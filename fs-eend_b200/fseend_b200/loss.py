@@ -1,8 +1,14 @@
 """Drop-in for the part of the reference's FS-EEND/train/utils/loss.py that the FS-EEND training / validation step uses
 (train/oln_tfm_enc_dec.py:35,82,122): ``standard_loss(ys, ts, label_delay=0)``, plus the label pipeline that the
-reference keeps inline in ``training_step`` (:51-76) as ``prepare_labels``.  Both run on the GPU through the C ABI
-(csrc/loss.cu); the list <-> padded-tensor plumbing stays in torch.  Forward values only: backward is SURVEY §8f N1.
+reference keeps inline in ``training_step`` (:51-76) as ``prepare_labels``, plus the permutation-invariant losses of the
+fine-tuning / offline harnesses (``batch_pit_loss`` :98-116, ``batch_pit_n_speaker_loss`` :257-327 and its label-delay
+form :329-403).  The frame sums run on the GPU through the C ABI (csrc/loss.cu); the list <-> padded-tensor plumbing
+and the search over the C! permutations of a C x C cost matrix stay on the host.  Forward values only: backward is
+SURVEY §8f N1.
 """
+from itertools import permutations
+
+
 import torch
 from torch.nn.utils.rnn import pad_sequence
 
@@ -46,3 +52,68 @@ def prepare_labels(labels, clip_lengths=None):
                         for l in labels], batch_first=True).contiguous()
     out, _ = op_label_prepare(lab)
     return [o[:ilen, :n + 2] for o, ilen, n in zip(out, lens, n_spks)]
+
+
+def _pit_costs(ys, ts, label_delay, pad_term, C):
+    from fseend_b200.native import op_pit_costs
+    dev = _device(ys)
+    y = pad_sequence([torch.nn.functional.pad(v.detach().to(device=dev, dtype=torch.float32), (0, C - v.shape[1]))
+                      for v in ys], batch_first=True).contiguous()
+    t = pad_sequence([torch.nn.functional.pad(v.detach().to(device=dev, dtype=torch.float32), (0, C - v.shape[1]))
+                      for v in ts], batch_first=True).contiguous()
+    lens = torch.tensor([v.shape[0] for v in ts], device=dev, dtype=torch.int32)
+    return op_pit_costs(y, t, lens, label_delay, pad_term).cpu()
+
+
+def batch_pit_loss(ys, ts, label_delay=0):
+    """Reference loss.py:98-116 (pit_loss :69-96 per recording).  ys, ts: B-length lists of (T_b, C_b) logits / labels.
+    Returns (loss, list of permuted labels)."""
+    for y, t in zip(ys, ts):
+        if tuple(y.shape) != tuple(t.shape):
+            raise ValueError("each prediction must have exactly its label's shape (frames, classes)")
+    C = max(t.shape[1] for t in ts)
+    cost = _pit_costs(ys, ts, label_delay, False, C)
+    total, labels = 0.0, []
+    for b, t in enumerate(ts):
+        cb = t.shape[1]
+        best, best_p = None, None
+        for p in permutations(range(cb)):                       # same enumeration order as the reference: first minimum
+            v = sum(float(cost[b, i, p[i]]) for i in range(cb)) / cb
+            if best is None or v < best:
+                best, best_p = v, p
+        total += best
+        labels.append(t[..., list(best_p)])
+    n_frames = sum(t.shape[0] for t in ts)
+    return torch.tensor(total / n_frames, dtype=torch.float32, device=_device(ys)), labels
+
+
+def batch_pit_n_speaker_loss(ys, ts, n_speakers_list, label_delay=None):
+    """Reference loss.py:257-327 (label_delay None) and :329-403 (label_delay given: frames beyond each recording's length
+    are excluded instead of entering as -1-padded frames).  ys, ts: B-length lists of (T_b, C) with the same C =
+    max(n_speakers_list) columns (pad_labels / pad_preds upstream, as in the reference's callers).
+    Returns (loss, list of permuted labels cut to n_speakers columns)."""
+    C = max(n_speakers_list)
+    for y, t in zip(ys, ts):
+        if y.shape[1] != C or t.shape[1] != C or y.shape[0] != t.shape[0]:
+            raise ValueError("every prediction / label must be (T_b, max(n_speakers_list))")
+    cost = _pit_costs(ys, ts, 0 if label_delay is None else label_delay, label_delay is None, C)
+    perms = list(permutations(range(C)))
+    total, labels = 0.0, []
+    for b, (t, n) in enumerate(zip(ts, n_speakers_list)):
+        # admissible permutations: every ordering of the n real speakers, the remaining columns kept in ascending order
+        # (the reference's select_perm_indices: first permutation, in enumeration order, with that prefix)
+        best, best_p = None, None
+        for p in perms:
+            if list(p[n:]) != sorted(p[n:]):
+                continue
+            v = float(torch.tensor([float(cost[b, i, p[i]]) for i in range(C)], dtype=torch.float32).mean())
+            if best is None or v < best:
+                best, best_p = v, p
+        total += best
+        labels.append(t[:, list(best_p)][:, :n])
+    n_frames = sum(t.shape[0] for t in ts)
+    return torch.tensor(total / n_frames, dtype=torch.float32, device=_device(ys)), labels
+
+
+def batch_pit_n_speaker_loss_label_delay(ys, ts, n_speakers_list, label_delay=0):
+    return batch_pit_n_speaker_loss(ys, ts, n_speakers_list, label_delay=label_delay)

@@ -48,7 +48,7 @@ EXPORTS = [
     "fseend_op_ffn", "fseend_op_causal_attn", "fseend_op_spk_attn", "fseend_op_spk_attn_tc", "fseend_op_head",
     "fseend_op_prep_input", "fseend_op_embloss", "fseend_op_embloss_workspace_bytes", "fseend_op_spk_qkv_attn", "fseend_op_decide_median", "fseend_op_label_prepare", "fseend_op_splice_subsample",
     "fseend_op_bce_loss", "fseend_op_bce_loss_workspace_bytes",
-    "fseend_fs_forward_host_async", "fseend_fs_host_wait", "fseend_ls_forward_host", "fseend_ls_set_option", "fseend_ls_get_option", "fseend_p32_linear_create",
+    "fseend_fs_forward_host_async", "fseend_fs_host_wait", "fseend_op_pit_costs", "fseend_ls_forward_host", "fseend_ls_set_option", "fseend_ls_get_option", "fseend_p32_linear_create",
     "fseend_p32_linear_destroy", "fseend_p32_linear_apply", "fseend_op_p32_retention",
 ]
 
@@ -164,6 +164,8 @@ def lib() -> C.CDLL:
     L.fseend_op_bce_loss_workspace_bytes.argtypes = [ip, ip]
     L.fseend_op_bce_loss.restype = ip
     L.fseend_op_bce_loss.argtypes = [vp, ip, vp, ip, ip, ip, vp, vp, ip, vp, vp, vp]
+    L.fseend_op_pit_costs.restype = ip
+    L.fseend_op_pit_costs.argtypes = [vp, vp, ip, ip, ip, vp, ip, ip, vp, vp]
     L.fseend_op_splice_subsample.restype = ip
     L.fseend_op_splice_subsample.argtypes = [vp, ip, ip, ip, ip, vp, vp]
     L.fseend_op_decide_median.restype = ip
@@ -737,6 +739,21 @@ def op_bce_loss(logits: torch.Tensor, target: torch.Tensor, lens: torch.Tensor, 
     _check(L.fseend_op_bce_loss(_ptr(logits), Cy, _ptr(target), target.shape[2], B, T, _ptr(lens), _ptr(n_cls),
                                 int(label_delay), _ptr(ws), _ptr(loss), _stream()))
     return loss
+
+
+def op_pit_costs(logits: torch.Tensor, labels: torch.Tensor, lens: torch.Tensor, label_delay: int = 0,
+                 pad_term: bool = False) -> torch.Tensor:
+    """logits, labels: CUDA fp32 [B, T, C] (zero padded), lens int32 [B] on the device -> fp64 [B, C, C] pair costs."""
+    _require_cuda(logits, labels, lens)
+    if logits.dtype != torch.float32 or labels.dtype != torch.float32 or lens.dtype != torch.int32:
+        raise FseendError("logits / labels must be float32 and lens int32")
+    if logits.shape != labels.shape or logits.dim() != 3:
+        raise FseendError("logits and labels must both be [B, T, C]")
+    B, T, Cn = logits.shape
+    cost = torch.empty(B, Cn, Cn, device=logits.device, dtype=torch.float64)
+    _check(lib().fseend_op_pit_costs(_ptr(logits), _ptr(labels), B, T, Cn, _ptr(lens), int(label_delay),
+                                     1 if pad_term else 0, _ptr(cost), _stream()))
+    return cost
 
 
 def op_splice_subsample(feat: torch.Tensor, context_size: int = 7, subsampling: int = 10) -> torch.Tensor:

@@ -8,8 +8,9 @@ who wants them under the reference's names calls ``patch_reference()`` AFTER the
 
     import fseend_b200.patch as P; P.patch_reference()           # replaces three functions, nothing else
 
-``train.utils.loss.standard_loss`` (reference train/utils/loss.py:119-125), ``train.utils.make_rttm.make_rttm``
-(:10-28) are replaced; ``datasets.feature`` gains ``splice_subsample`` (splice :111-133 + subsample :103-108 fused) and
+``train.utils.loss.standard_loss`` (reference train/utils/loss.py:119-125), the PIT losses (``batch_pit_loss`` :98-116,
+``batch_pit_n_speaker_loss`` :257-327, ``..._label_delay`` :329-403), ``train.utils.make_rttm.make_rttm`` (:10-28) are
+replaced; ``datasets.feature`` gains ``splice_subsample`` (splice :111-133 + subsample :103-108 fused) and
 keeps every reference function (``extract_fbank``, ``stft`` ... are untouched).
 """
 import importlib
@@ -29,9 +30,10 @@ def patch_reference(loss: bool = True, rttm: bool = True, feature: bool = True):
         m = _try("train.utils.loss")
         if m is not None:
             from . import loss as L
-            m.standard_loss = L.standard_loss
-            m.prepare_labels = L.prepare_labels
-            done += ["train.utils.loss.standard_loss", "train.utils.loss.prepare_labels"]
+            for fn in ("standard_loss", "prepare_labels", "batch_pit_loss", "batch_pit_n_speaker_loss",
+                       "batch_pit_n_speaker_loss_label_delay"):
+                setattr(m, fn, getattr(L, fn))
+                done.append("train.utils.loss." + fn)
     if rttm:
         m = _try("train.utils.make_rttm")
         if m is not None:

@@ -224,6 +224,14 @@ size_t fseend_op_bce_loss_workspace_bytes(int B, int T);
 int fseend_op_bce_loss(const float* logits, int ld_logits, const float* target, int ld_target, int B, int T,
                        const int* lens_dev, const int* n_cls_dev, int label_delay, float* workspace, float* loss_dev,
                        void* stream);
+/* Permutation-invariant-training pair costs (reference train/utils/loss.py:69-96 pit_loss / :98-116 batch_pit_loss,
+ * :257-327 batch_pit_n_speaker_loss, :329-403 its label-delay form): cost[b][i][j] = sum over frames t < len_b - delay
+ * of BCEWithLogits(logits[b][t + delay][i], labels[b][t][j]); pad_term != 0 adds (T - len_b) * BCE(-1, -1), the
+ * contribution of the reference's -1-padded frames.  logits, labels: fp32 [B][T][C] on the device, lens: int [B] on the
+ * device, cost: fp64 [B][C][C] on the device (fixed-order reduction).  The permutation search over the C x C costs is the
+ * host-side part (fseend_b200.loss.batch_pit_loss / batch_pit_n_speaker_loss). */
+int fseend_op_pit_costs(const float* logits, const float* labels, int B, int T, int C, const int* lens_dev,
+                        int label_delay, int pad_term, double* cost_dev, void* stream);
 
 /* Feature front-end tail (reference datasets/feature.py: splice :111-133 then subsample :103-108, as called at
  * :259-261 / :348-352): feat fp32 [T][F] (e.g. 23-dim log-mel) -> out fp32 [ceil(T / subsampling)][(2 context_size + 1) F],

@@ -57,3 +57,72 @@ def synthetic_batch(seed, lens, n_spks):
         labels.append(act)
         logits.append(torch.randn(T, n + 2, generator=g) * 2.0)
     return labels, logits
+
+
+# ----------------------------------------------------------------------------- permutation-invariant losses
+def _bce(x, t):
+    return torch.clamp(x, min=0) - x * t + torch.log1p(torch.exp(-x.abs()))
+
+
+def pit_pair_costs(y, t, label_delay=0):
+    """cost[i][j] = sum_t BCE(y[t + delay, i], t[t, j]) in fp64 (the quantity every PIT variant permutes)."""
+    yy, tt = y[label_delay:].double(), t[:len(t) - label_delay].double()
+    return torch.stack([torch.stack([_bce(yy[:, i], tt[:, j]).sum() for j in range(t.shape[1])])
+                        for i in range(y.shape[1])])
+
+
+def batch_pit_loss(ys, ts, label_delay=0):
+    """loss.py:98-116 with pit_loss :69-96: per recording the minimum over label permutations of the mean BCE, times the
+    number of frames; summed and divided by the total number of frames."""
+    from itertools import permutations
+    total, labels = 0.0, []
+    for y, t in zip(ys, ts):
+        C = t.shape[1]
+        cost = pit_pair_costs(y, t, label_delay)
+        best, best_p = None, None
+        for p in permutations(range(C)):
+            v = sum(cost[i, p[i]].item() for i in range(C)) / C
+            if best is None or v < best:
+                best, best_p = v, p
+        total += best
+        labels.append(t[..., list(best_p)])
+    return total / sum(t.shape[0] for t in ts), labels
+
+
+def batch_pit_n_speaker_loss(ys, ts, n_speakers_list, label_delay=None):
+    """loss.py:257-327 (label_delay None: shorter recordings enter with their -1-padded frames, BCE(-1, -1) each) and
+    :329-403 (label_delay given: padded frames excluded)."""
+    from itertools import permutations
+    C = max(n_speakers_list)
+    Tmax = max(t.shape[0] for t in ts)
+    pad_bce = _bce(torch.tensor(-1.0, dtype=torch.float64), torch.tensor(-1.0, dtype=torch.float64)).item()
+    total, labels = 0.0, []
+    for y, t, n in zip(ys, ts, n_speakers_list):
+        cost = pit_pair_costs(y, t, 0 if label_delay is None else label_delay)
+        if label_delay is None:
+            cost = cost + (Tmax - t.shape[0]) * pad_bce
+        best, best_p = None, None
+        for p in permutations(range(C)):
+            if list(p[n:]) != sorted(p[n:]):
+                continue
+            v = sum(cost[i, p[i]].item() for i in range(C)) / C
+            if best is None or v < best:
+                best, best_p = v, p
+        total += best
+        labels.append(t[:, list(best_p)][:, :n])
+    return total / sum(t.shape[0] for t in ts), labels
+
+
+def synthetic_pit_batch(seed, lens, n_spks):
+    """Labels (T_b, n_b) 0/1 and logits correlated with a random permutation of them (so that the best permutation is not
+    the identity), both padded to C = max(n_spks) columns as the reference's callers do (pad_labels / pad_preds)."""
+    g = torch.Generator().manual_seed(seed)
+    C = max(n_spks)
+    ys, ts = [], []
+    for T, n in zip(lens, n_spks):
+        lab = (torch.rand(T, n, generator=g) > 0.5).float()
+        perm = torch.randperm(n, generator=g)
+        y = (lab[:, perm] * 2 - 1) * 1.5 + torch.randn(T, n, generator=g)
+        ts.append(torch.nn.functional.pad(lab, (0, C - n)))
+        ys.append(torch.nn.functional.pad(y, (0, C - n), value=-4.0))
+    return ys, ts

@@ -98,7 +98,7 @@ def test_recipe_against_real_reference(tree):
 
 
 def test_patch_hook_replaces_only_the_named_functions(tmp_path):
-    """fseend_b200.patch.patch_reference() on a synthetic reference tree: the three functions are swapped, everything
+    """fseend_b200.patch.patch_reference() on a synthetic reference tree: the named functions are swapped, everything
     else in the reference modules is untouched (no CUDA needed: nothing is called)."""
     ref = tmp_path / "FS-EEND"
     (ref / "train" / "utils").mkdir(parents=True)
@@ -118,9 +118,9 @@ def test_patch_hook_replaces_only_the_named_functions(tmp_path):
         if getattr(datasets, '__file__', None) is None:      # namespace dir = the reference's (no unrelated installed
             import datasets.feature as F                     # `datasets` distribution shadowing it in this environment)
             assert F.extract_fbank() == 'ref' and F.splice_subsample.__module__ == 'fseend_b200.feature'
-            assert len(done) == 4
+            assert len(done) == 7
         else:
-            assert len(done) >= 3
+            assert len(done) >= 6
         print('ok')
     """)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
