@@ -437,7 +437,7 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    launches = native.launches_per_forward * args.steps
+    launches = native.launches_per_forward * args.steps * world      # whole job: every rank launches the same sequence
 
     # ---- sustained figure: the same loop for >= 200 steps (a 20-step region is ~45 ms: boost clocks, no power cap yet)
     sustained = None
@@ -562,7 +562,7 @@ def run_ours(args):
                    "parallelism": f"dp{world} (no data-path collective)"},
         "tflops_algorithmic": total_flops(B, T, S) * world * args.steps / (ms * 1e-3) / 1e12,
         "e2e": {"value": frames * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": B * T * DIN * 4, "d2h_bytes_per_step": B * T * S * 4,
+                "h2d_bytes_per_step": world * B * T * DIN * 4, "d2h_bytes_per_step": world * B * T * S * 4,
                 "steps": e2e_steps, "api": "fseend_fs_forward_host_async + fseend_fs_host_wait (pinned host buffers, two "
                                              "calls in flight: H2D of step i+1 overlaps the kernels of step i)",
                 "blocking_call": {"value": frames / (e2e_sync_ms * 1e-3), "unit": UNIT, "steps": sync_steps,

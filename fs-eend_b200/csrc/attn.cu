@@ -30,6 +30,7 @@
 // the A operand of the PV MMA.  Both were correct and no faster: with five 64-wide KV tiles per item the kernel is
 // bound by the per-tile handshake chain (MMA commit -> mbarrier -> TMEM read -> ... -> arrive -> MMA issue), not by
 // TMEM bandwidth, MUFU, DRAM or the tensor pipe.
+#include "once.h"
 #include <stdlib.h>
 
 #include "attn.cuh"
@@ -485,7 +486,8 @@ void launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmKV, __half* out, c
     }
   }
   static int num_sms = 0;
-  if (!num_sms) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     int dev = 0;
     cudaGetDevice(&dev);

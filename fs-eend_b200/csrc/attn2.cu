@@ -18,6 +18,7 @@
 // PERSISTENT, one CTA per SM, 320 threads: warps 0-3 softmax of tile A, warps 4-7 softmax of tile B (thread r <-> query
 // row r, TMEM lane r), warp 8 TMA producer, warp 9 tcgen05 issuer.
 // TMEM (512 columns): S_A [0,128), S_B [128,256), O_A [256,320), O_B [320,384).
+#include "once.h"
 #include <stdlib.h>
 
 #include "attn.cuh"
@@ -419,7 +420,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 void launch_attn2(const CUtensorMap& tmQ, const CUtensorMap& tmKV, __half* out, const AttnParams& p,
                   cudaStream_t stream) {
   static int num_sms = 0;
-  if (!num_sms) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     int dev = 0;
     cudaGetDevice(&dev);

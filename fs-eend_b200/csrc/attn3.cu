@@ -24,6 +24,7 @@
 // taken from the rounded P).
 #include <stdlib.h>
 
+#include "once.h"
 #include "attn.cuh"
 #include "ptx.cuh"
 
@@ -358,17 +359,19 @@ constexpr int kCounterRing = 256;
 // tmQ: box (64,1,128,1) over (768, S, T, B).  step_keys: 128 (4 CTAs / SM, default) or 256 (2 CTAs / SM).
 void launch_attn3(const CUtensorMap& tmQ, __half* out, const AttnParams& p, int step_keys, cudaStream_t stream) {
   static int num_sms = 0;
-  static int* counters = nullptr;
+  static int* counters_dev[64] = {};
   static int next_counter = 0;
+  static PerDeviceOnce once;
   constexpr int smem256 = kQBytes + 2 * 256 * 128 + 128, smem128 = kQBytes + 2 * 128 * 128 + 128;
-  if (!num_sms) {
+  if (once.first()) {
     cudaFuncSetAttribute(attn3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem256);
     cudaFuncSetAttribute(attn3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaMalloc(&counters, kCounterRing * sizeof(int));
+    cudaMalloc(&counters_dev[once.device], kCounterRing * sizeof(int));
   }
+  int* counters = counters_dev[once.device];
   // one work counter per launch from a ring (launches on different streams may overlap; 256 launches in flight never do)
   int* counter = counters + next_counter;
   next_counter = (next_counter + 1) % kCounterRing;

@@ -10,6 +10,7 @@
 // 128B-swizzled K-major operand layout (plain loads: the op has no TMA descriptor to build and no alignment demands
 // beyond 16 bytes).  Row norms are computed from the same fp16 values the MMA consumes.
 // Partial sums go to a workspace and are reduced in a fixed order in fp64 by embloss_finalize_kernel (deterministic).
+#include "once.h"
 #include "embloss.cuh"
 #include "ptx.cuh"
 
@@ -216,10 +217,9 @@ int embloss_num_partials(int B, int T) {
 }
 
 void launch_embloss(EmbLossParams p, double divisor, float* loss, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(embloss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    attr_set = true;
   }
   const int nt = (p.T + kTile - 1) / kTile;
   p.n_pairs = nt * (nt + 1) / 2;

@@ -12,6 +12,7 @@
 // two CTAs of a cluster work on adjacent row tiles and share every weight slot: each CTA fetches half of the
 // slots and TMA-multicasts them into both CTAs' rings, halving L2->SM weight traffic (the binding limit of this
 // block: 2 MB of weights per 268 MFLOP tile).
+#include "once.h"
 #include "ffn.cuh"
 #include "ffn_tile.cuh"
 #include "ptx.cuh"
@@ -353,10 +354,9 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 template <int kCluster, bool kTS>
 void launch_ffn_t(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmO,
                   const FfnParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(ffn_kernel<kCluster, kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    attr_set = true;
   }
   const int tiles = p.n_seq * p.tiles_per_seq;
   cudaLaunchConfig_t cfg{};

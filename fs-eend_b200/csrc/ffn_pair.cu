@@ -18,6 +18,7 @@
 //
 // Reference: torch.nn.TransformerEncoderLayer._ff_block + norm2 (FS:model:147) and
 // TransformerEncoderFusionLayer._ff_block + norm22 (FS-EEND/nnet/modules/merge_tfm_encoder.py:373,397-399).
+#include "once.h"
 #include "ffn.cuh"
 #include "ffn_tile.cuh"
 #include "pair.cuh"
@@ -346,10 +347,9 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
 void launch_ffn_pair(const CUtensorMap& tmX, const CUtensorMap& tmW1_box64, const CUtensorMap& tmW2,
                      const CUtensorMap& tmO, const FfnParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    attr_set = true;
   }
   const int tiles = p.n_seq * p.tiles_per_seq;
   ffn_pair_kernel<<<(tiles + 1) / 2 * 2, 320, kSmemBytes, stream>>>(tmX, tmW1_box64, tmW2, tmO, p);

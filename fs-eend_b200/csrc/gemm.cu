@@ -9,6 +9,7 @@
 //                               bound, so they get all the warps the register file allows at 2 CTAs/SM.
 // Two CTAs are resident per SM (2 x ~97 KB smem, 2 x 256 TMEM columns): one CTA's epilogue overlaps the
 // other's main loop.
+#include "once.h"
 #include <stdlib.h>
 
 #include "gemm.cuh"
@@ -206,10 +207,9 @@ void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     launch_gemm_persist(tmA, tmB, tmR, tmO, tmO2, p, stream);
     return;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    attr_set = true;
   }
   const int grid = p.n_seq * p.tiles_per_seq * p.n_tiles;
   gemm_kernel<<<grid, 256, kSmemBytes, stream>>>(tmA, tmB, tmR, tmO, tmO2, p);

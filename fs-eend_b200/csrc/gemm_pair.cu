@@ -16,6 +16,7 @@
 // per item; fp16 x 1.0 accumulates exactly in fp32).  That keeps the residual on the deep TMA prefetch path instead of
 // a strided per-thread global load or a second staging buffer that shared memory has no room for.
 // Epilogues: EPI_BIAS (+ReLU/Swish) and EPI_LN (bias, optional residual, zero rows beyond seq_len).
+#include "once.h"
 #include "gemm.cuh"
 #include "gemm_epilogue.cuh"
 #include "pair.cuh"
@@ -331,7 +332,8 @@ bool gemm_pair_supported(const GemmParams& p) {
 void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmR, const CUtensorMap& tmO, const GemmParams& p,
                       cudaStream_t stream) {
   static int num_sms = 0;
-  if (!num_sms) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(gemm_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(gemm_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(gemm_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);

@@ -8,6 +8,7 @@
 //   warp 1     : tcgen05 issuer — two 256-column TMEM accumulators, so the MMAs of item i+1 overlap the epilogue of i;
 //   warps 2-9  : epilogue (gemm_epilogue.cuh), two threads per row (128 columns each; the row epilogues are
 //                instruction/latency-bound, not memory-bound) -> 64 KB staging tile -> TMA store.
+#include "once.h"
 #include "gemm.cuh"
 #include "gemm_epilogue.cuh"
 #include "ptx.cuh"
@@ -179,7 +180,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 void launch_gemm_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
                          const CUtensorMap& tmO2, const GemmParams& p, cudaStream_t stream) {
   static int num_sms = 0;
-  if (!num_sms) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(gemm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     int dev = 0;
     cudaGetDevice(&dev);

@@ -1,6 +1,7 @@
 // Parity-precision kernels (see p32.cuh): split-precision tcgen05 GEMM on fp32 activations, fp32 retention core,
 // fp32 normalisation / activation kernels.  Reference arithmetic restated per kernel below (paths relative to
 // /root/reference/LS-EEND/nnet).
+#include "once.h"
 #include "p32.cuh"
 
 #include <math.h>
@@ -1228,18 +1229,18 @@ __global__ void p32_hist_append_kernel(const float* __restrict__ src, float* __r
 
 // =====================================================================================================================
 void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P32GemmParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(p32_gemm_kernel<P32_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
     cudaFuncSetAttribute(p32_gemm_kernel<P32_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
     cudaFuncSetAttribute(p32_gemm_kernel<P32_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
-    attr_set = true;
   }
   const int tiles_per_seq = (p.rows_per_seq + BM - 1) / BM;
   const int grid = p.n_seq * tiles_per_seq * (p.N / BN);
   // persistent warp-specialised kernel once there is more than one tile per SM (FSEEND_P32_GEMM=0: always one-tile)
   static int num_sms = 0, use_persist = 1;
-  if (!num_sms) {
+  static PerDeviceOnce once_p;
+  if (once_p.first()) {
     cudaFuncSetAttribute(p32_gemm_persist_kernel<P32_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmem);
     cudaFuncSetAttribute(p32_gemm_persist_kernel<P32_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmem);
     cudaFuncSetAttribute(p32_gemm_persist_kernel<P32_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmem);
@@ -1333,10 +1334,9 @@ void launch_p32_ret_chunk_state(const float* qkvg, int B, int S, int T, int chun
 
 void launch_p32_retention(const float* qkvg, const float* state, const float* cross_scale, int B, int S, int T,
                           int chunk, float* out, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(p32_retention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRetSmem);
-    attr_set = true;
   }
   const int nc = T / chunk;
   dim3 grid((chunk + 63) / 64, 4, B * S * nc);

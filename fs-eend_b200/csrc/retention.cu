@@ -12,6 +12,7 @@
 // Kernel structure = attn.cu without the softmax: one CTA per (sequence, chunk, head, 128-row tile); warp 4 lane 0
 // drives TMA and the MMAs S = Q K^T, O1 += P V (P = masked raw scores as fp16) and O2 = Q R'; warps 0-3 own one row
 // each: mask, |.|-sum, fp16 pack, and the final scale / group norm / gate.
+#include "once.h"
 #include "retention.cuh"
 #include "ptx.cuh"
 
@@ -416,10 +417,9 @@ void launch_ret_chunk_state(const __half* qkvg, const RetParams& p, __half* stat
 
 void launch_retention(const CUtensorMap& tmQKVG, const CUtensorMap& tmState, const CUtensorMap& tmO, const RetParams& p,
                       cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(retention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    attr_set = true;
   }
   dim3 grid((p.chunk + kTile - 1) / kTile, p.H, p.B * p.S * p.n_chunks);
   retention_kernel<<<grid, 160, kSmemBytes, stream>>>(tmQKVG, tmState, tmO, p);

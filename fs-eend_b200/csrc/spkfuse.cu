@@ -18,6 +18,7 @@
 // History (B=64, T=500, S=6, in-model): one item per CTA, 2 CTAs/SM: 0.206 ms (every latency exposed once per item);
 // persistent with 8 warps in lock step on one item (two threads per row): 0.219 ms with the row reads emitted as
 // generic loads (pointer re-alignment arithmetic hid the shared address space), 0.167 ms as LDS.
+#include "once.h"
 #include "ptx.cuh"
 #include "spkfuse.cuh"
 
@@ -290,7 +291,8 @@ spkfuse_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 void launch_spkfuse(const CUtensorMap& tmX, const CUtensorMap& tmW, const SpkFuseParams& p, cudaStream_t stream) {
   static int num_sms = 0;
-  if (!num_sms) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(spkfuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynBytes);
     int dev = 0;
     cudaGetDevice(&dev);

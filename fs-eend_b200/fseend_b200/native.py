@@ -215,6 +215,11 @@ class NativeCacheMixin:
         if hasattr(self, "_stream"):
             self._stream = None
 
+    def _on_device(self):
+        """Context that makes the model's GPU the current device for a native call (kernels launch on the current
+        device; workspaces and weights live on the model's)."""
+        return torch.cuda.device(next(self.parameters()).device)
+
     def _native_cached(self, build):
         tensors = list(self.parameters()) + list(self.buffers())
         dev = tensors[0].device

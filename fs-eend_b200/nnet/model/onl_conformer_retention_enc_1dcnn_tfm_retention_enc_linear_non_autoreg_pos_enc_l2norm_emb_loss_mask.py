@@ -170,7 +170,8 @@ class OnlineConformerRetentionDADiarization(NativeCacheMixin, nn.Module):
         """Fused one-step driver (encoder + look-ahead conv + decoder + head per call): ``stream.step(x_t)`` with
         x_t (B, in_size) returns (B, max_nspks) logits of frame t - conv_delay or None; ``stream.step(None)`` flushes."""
         from fseend_b200.native import LsStream
-        return LsStream(self.native(), batch_size, max_nspks)
+        with self._on_device():
+            return LsStream(self.native(), batch_size, max_nspks)
 
     def _native_cfg(self):
         return dict(in_size=self.enc.in_size, n_units=self.n_units, n_heads=self.enc.n_heads,
@@ -217,14 +218,16 @@ class OnlineConformerRetentionDADiarization(NativeCacheMixin, nn.Module):
     def test(self, src, ilens, max_nspks=6):
         """Reference :125-147.  Returns (list[logits (ilen, max_nspks)], list[emb (ilen, D)], list[attractors])."""
         x, lens = self._pack(src, ilens)
-        y, emb, att = self.native().forward(x, lens, max_nspks, want_emb=True, want_att=True)
+        with self._on_device():
+            y, emb, att = self.native().forward(x, lens, max_nspks, want_emb=True, want_att=True)
         return ([o[:l] for o, l in zip(y, lens)], [e[:l] for e, l in zip(emb, lens)],
                 [a[:l] for a, l in zip(att, lens)])
 
     @torch.no_grad()
     def test_logits(self, src, ilens, max_nspks=6):
         x, lens = self._pack(src, ilens)
-        y, _, _ = self.native().forward(x, lens, max_nspks)
+        with self._on_device():
+            y, _, _ = self.native().forward(x, lens, max_nspks)
         return [o[:l] for o, l in zip(y, lens)]
 
     def forward(self, src, tgt, ilens):
@@ -234,7 +237,7 @@ class OnlineConformerRetentionDADiarization(NativeCacheMixin, nn.Module):
             raise NotImplementedError(
                 "fseend_b200 round 1 implements the forward hot path only; training backward is SURVEY §8(f) N1")
         from fseend_b200.native import op_embloss
-        with torch.no_grad():
+        with torch.no_grad(), self._on_device():
             n_speakers = [t.shape[1] for t in tgt]
             max_nspks = max(n_speakers)
             x, lens = self._pack(src, ilens)

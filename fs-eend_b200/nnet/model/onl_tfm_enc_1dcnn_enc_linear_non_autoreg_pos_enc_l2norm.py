@@ -135,7 +135,8 @@ class OnlineTransformerDADiarization(NativeCacheMixin, nn.Module):
     def test(self, src, ilens, max_nspks=6):
         """Reference :67-84.  Returns (list[logits (ilen, max_nspks)], list[emb (ilen, D)], list[attractors])."""
         x, lens = self._pack(src, ilens)
-        y, emb, att = self.native().forward(x, lens, max_nspks, want_emb=True, want_att=True)
+        with self._on_device():
+            y, emb, att = self.native().forward(x, lens, max_nspks, want_emb=True, want_att=True)
         output = [o[:l] for o, l in zip(y, lens)]
         emb = [e[:l] for e, l in zip(emb, lens)]
         attractors = [a[:l] for a, l in zip(att, lens)]
@@ -145,7 +146,8 @@ class OnlineTransformerDADiarization(NativeCacheMixin, nn.Module):
     def test_logits(self, src, ilens, max_nspks=6):
         """test() without materialising the fp32 embedding / attractor by-products (bench path)."""
         x, lens = self._pack(src, ilens)
-        y, _, _ = self.native().forward(x, lens, max_nspks)
+        with self._on_device():
+            y, _, _ = self.native().forward(x, lens, max_nspks)
         return [o[:l] for o, l in zip(y, lens)]
 
     def forward(self, src, tgt, ilens):
@@ -154,7 +156,7 @@ class OnlineTransformerDADiarization(NativeCacheMixin, nn.Module):
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
                 "fseend_b200 round 1 implements the forward hot path only; training backward is SURVEY §8(f) N1")
-        with torch.no_grad():
+        with torch.no_grad(), self._on_device():
             n_speakers = [t.shape[1] for t in tgt]
             max_nspks = max(n_speakers)
             x, lens = self._pack(src, ilens)

@@ -73,14 +73,16 @@ class StreamingTransformerEDADiarization(NativeCacheMixin, nn.Module):
         if self._stream is None:
             # the parameter check (native()) walks every tensor of the model: done when a recording starts, not once per
             # 100-ms frame — weights edited mid-recording take effect after reset() / invalidate_native()
-            self._stream = FsStream(self.native(), B, max_nspks)
+            with self._on_device():
+                self._stream = FsStream(self.native(), B, max_nspks)
             self.cnn.t = 0
         if self._stream.B != B or self._stream.S != max_nspks:
             raise ValueError("batch size / max_nspks changed mid-stream; call reset() first")
-        if dummy_conv_input:
-            y = self._stream.step(None)
-        else:
-            assert x_t.shape[1] == 1, "Input should be a single time frame"
-            y = self._stream.step(x_t[:, 0].to(device=dev, dtype=torch.float32).contiguous())
+        with torch.cuda.device(dev):
+            if dummy_conv_input:
+                y = self._stream.step(None)
+            else:
+                assert x_t.shape[1] == 1, "Input should be a single time frame"
+                y = self._stream.step(x_t[:, 0].to(device=dev, dtype=torch.float32).contiguous())
         self.cnn.t += 1
         return None if y is None else y.unsqueeze(1)

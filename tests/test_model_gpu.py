@@ -288,3 +288,25 @@ def _streaming_equals_batch():
     stream.reset()
     again = _run_stream(stream, x[:, :40], 4)
     assert (again[:, :31] - ys[:, :31]).abs().max().item() < 1e-6    # deterministic restart after reset()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_model_on_second_gpu_while_first_is_current():
+    """A model that lives on cuda:1 while cuda:0 is the current device (advisor finding, round 1): the native model is
+    built on the parameters' device, kernels launch there, per-device launch setup (dynamic-smem opt-in, work-queue
+    counters) is repeated for the new device; results equal the cuda:0 run bit for bit."""
+    sd, src, lens, S, cfg, g = load_case("ragged_S6")
+    torch.cuda.set_device(0)
+    m0 = make_model(sd)
+    out0 = m0.test_logits([s.cuda(0) for s in src], lens, S)
+    from nnet.model.onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import OnlineTransformerDADiarization
+    m1 = OnlineTransformerDADiarization(n_speakers=4, in_size=345, n_units=256, n_heads=4, enc_n_layers=4,
+                                        dec_n_layers=2, dropout=0.1, has_mask=True, max_seqlen=500,
+                                        dec_dim_feedforward=2048)
+    m1.load_state_dict(sd, strict=True)
+    m1 = m1.to("cuda:1").eval()
+    assert torch.cuda.current_device() == 0
+    out1 = m1.test_logits([s.to("cuda:1") for s in src], lens, S)
+    assert all(o.device.index == 1 for o in out1)
+    for a, b in zip(out0, out1):
+        assert torch.equal(a.cpu(), b.cpu())
