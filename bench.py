@@ -528,7 +528,29 @@ def run_ours(args):
                              "frac_of_sustained_peak": a / pk["tflops"], "avg_launch_ms": a_ms, "flops": "causal-exact",
                              "traffic": traffic.get(k)}
 
+    # ---- N > 1: the one collective of the reference's training step (DDP gradient all-reduce, train_dia.py:145-160),
+    # measured on its own: 9,974,450 fp32 gradients = 39.9 MB over NCCL.  NOT part of `value` (the forward path has no
+    # exchange step; the backward kernels that would produce these gradients are not built) — it states
+    # what the collective costs next to a forward of `ms_per_step`.
+    grad_allreduce = None
     if world > 1:
+        gbuf = torch.zeros(9_974_450, device=dev, dtype=torch.float32)
+        for _ in range(3):
+            dist.all_reduce(gbuf)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        a0.record()
+        n_ar = 20
+        for _ in range(n_ar):
+            dist.all_reduce(gbuf)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = max_over_ranks([a0.elapsed_time(a1) / n_ar], dev)[0]
+        nbytes = gbuf.numel() * 4
+        grad_allreduce = {"bytes": nbytes, "ms": ar_ms, "algbw_gbs": nbytes / (ar_ms * 1e-3) / 1e9,
+                          "busbw_gbs": nbytes / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
+                          "note": "NCCL all-reduce of the FS-EEND gradient volume alone; not included in value"}
         dist.barrier()
     if rank != 0:
         if world > 1:
@@ -574,6 +596,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "sustained": sustained,
         "secondary": secondary,
+        "grad_allreduce": grad_allreduce,
         "kernels": prof_table,
         "options": os.environ.get("FSEEND_OPTS", "default"),
     }

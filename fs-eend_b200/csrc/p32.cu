@@ -454,6 +454,221 @@ p32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_
 }
 
 // =====================================================================================================================
+// A-stationary persistent form for K <= 256, one tap, N >= 256 (QKV(G) projections, FFN up-projections, speaker-attention
+// in-projection: most launches of the parity path).  ncu on the persistent kernel above (r02_final_p32persist.txt): 844 M
+// warp-instructions for one decoder FFN up-projection, i.e. ~900 issue cycles per k-block against 768 clk of MMAs — the A
+// tile is re-fetched and re-split for every one of the N / 128 column tiles.  Here a work item is a 128-row tile: its
+// hi / lo planes for the whole K (up to 128 KB) are built ONCE and stay in shared memory while the CTA walks all column
+// tiles, streaming only the weights (TMA, 3-stage ring).  Per-k-block barriers let the next row tile's planes be built
+// as soon as the last column tile has consumed the corresponding k-block.
+//   warps 0-5 : A producers;  warp 6 : W loader (TMA);  warp 7 : MMA issuer;  warps 8-15 : fold + epilogue (registers ->
+//   global, 64 consecutive floats per thread).
+constexpr int kSWStages = 3;
+constexpr int kSMaxKB = 4;
+constexpr int kSWStageBytes = 2 * kTileBytes;                                   // W_hi | W_lo
+constexpr int kAstatSmem = kSMaxKB * 2 * kTileBytes + kSWStages * kSWStageBytes + 1024;   // 128 KB + 96 KB
+constexpr int kSProd = 6 * 32;
+
+template <int kAct>
+__global__ void __launch_bounds__(kPThreads, 1)
+p32_gemm_astat_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
+                      const P32GemmParams p, const int n_m_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kSMaxKB];
+  __shared__ __align__(8) uint64_t a_empty[kSMaxKB];
+  __shared__ __align__(8) uint64_t w_full[kSWStages];
+  __shared__ __align__(8) uint64_t w_empty[kSWStages];
+  __shared__ __align__(8) uint64_t acc_full[kPAcc];
+  __shared__ __align__(8) uint64_t acc_empty[kPAcc];
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smemW = smem + kSMaxKB * 2 * kTileBytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int k = 0; k < kSMaxKB; ++k) {
+      mbar_init(&a_full[k], kSProd);
+      mbar_init(&a_empty[k], 1);
+    }
+    for (int s = 0; s < kSWStages; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int b = 0; b < kPAcc; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 256);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmWhi);
+    tma_prefetch_desc(&tmWlo);
+  }
+  if (warp == 7) tmem_alloc(&tmem_base_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int n_tiles_n = p.N / BN;
+  const int tiles_per_seq = (p.rows_per_seq + BM - 1) / BM;
+  const int KB = p.k_blocks;
+
+  if (warp < 6) {
+    // ------------------------------------------------------------ A producers: planes of one row tile, once
+    float4 pre[12];
+    auto fetch = [&](int m_tile, int kb) {
+      const int seq = m_tile / tiles_per_seq, t0 = (m_tile % tiles_per_seq) * BM;
+      const float* a_seq = p.A + static_cast<size_t>(seq) * p.a_seq_rows * p.lda;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int q = tid + kSProd * i;                     // 1024 chunks of 8 floats over 192 threads
+        const int r = q >> 3, c = q & 7;
+        const int t = t0 + r;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (q < 1024 && t < p.rows_per_seq) {
+          const float4* src = reinterpret_cast<const float4*>(a_seq + static_cast<size_t>(t) * p.lda + kb * BK + c * 8);
+          v0 = __ldg(src);
+          v1 = __ldg(src + 1);
+        }
+        pre[2 * i] = v0;
+        pre[2 * i + 1] = v1;
+      }
+    };
+    int m_tile = blockIdx.x;
+    if (m_tile < n_m_tiles) fetch(m_tile, 0);
+    for (uint32_t j = 0; m_tile < n_m_tiles; m_tile += gridDim.x, ++j) {
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&a_empty[kb], (j & 1) ^ 1, 91);           // the previous row tile's last column tile has consumed it
+        uint8_t* sAhi = smem + kb * 2 * kTileBytes;
+        uint8_t* sAlo = sAhi + kTileBytes;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int q = tid + kSProd * i;
+          if (q < 1024) {
+            const int r = q >> 3, c = q & 7;
+            uint4 hi, lo;
+            split8(pre[2 * i], pre[2 * i + 1], hi, lo);
+            const uint32_t off = sw128_offset(r, c);
+            *reinterpret_cast<uint4*>(sAhi + off) = hi;
+            *reinterpret_cast<uint4*>(sAlo + off) = lo;
+          }
+        }
+        if (kb + 1 < KB) fetch(m_tile, kb + 1);
+        else if (m_tile + static_cast<int>(gridDim.x) < n_m_tiles) fetch(m_tile + gridDim.x, 0);
+        fence_proxy_async_smem();
+        mbar_arrive(&a_full[kb]);
+      }
+    }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------ W loader
+    uint32_t g = 0;
+    for (int m_tile = blockIdx.x; m_tile < n_m_tiles; m_tile += gridDim.x) {
+      for (int nt = 0; nt < n_tiles_n; ++nt) {
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int s = g % kSWStages;
+          mbar_wait(&w_empty[s], ((g / kSWStages) & 1) ^ 1, 92);
+          if (elect_one()) {
+            uint8_t* sW = smemW + s * kSWStageBytes;
+            mbar_arrive_expect_tx(&w_full[s], kSWStageBytes);
+            tma_load_2d(sW, &tmWhi, &w_full[s], kb * BK, nt * BN);
+            tma_load_2d(sW + kTileBytes, &tmWlo, &w_full[s], kb * BK, nt * BN);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 7) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN, false);
+    uint32_t g = 0, j = 0;
+    for (int m_tile = blockIdx.x; m_tile < n_m_tiles; m_tile += gridDim.x, ++j) {
+      for (int nt = 0; nt < n_tiles_n; ++nt) {
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int s = g % kSWStages, buf = g % kPAcc;
+          mbar_wait(&w_full[s], (g / kSWStages) & 1, 93);
+          if (nt == 0) mbar_wait(&a_full[kb], j & 1, 94);
+          mbar_wait(&acc_empty[buf], ((g / kPAcc) & 1) ^ 1, 95);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + kb * 2 * kTileBytes);
+          const uint32_t sw = smem_u32(smemW + s * kSWStageBytes);
+          const uint64_t dAhi = smem_desc_sw128(sa), dAlo = smem_desc_sw128(sa + kTileBytes);
+          const uint64_t dWhi = smem_desc_sw128(sw), dWlo = smem_desc_sw128(sw + kTileBytes);
+          const uint32_t d = tmem_base + buf * 128;
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              umma_f16(d, dAlo + 2 * kk, dWhi + 2 * kk, idesc, kk > 0 ? 1u : 0u);
+              umma_f16(d, dAhi + 2 * kk, dWlo + 2 * kk, idesc, 1u);
+            }
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) umma_f16(d, dAhi + 2 * kk, dWhi + 2 * kk, idesc, 1u);
+            umma_commit(&w_empty[s]);
+            umma_commit(&acc_full[buf]);
+            if (nt == n_tiles_n - 1) umma_commit(&a_empty[kb]);   // this k-block's planes may be rebuilt for the next row tile
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ fold + epilogue warps 8-15
+    const int wq = warp & 3, half = (warp - 8) >> 2;
+    const int r = wq * 32 + lane;
+    const uint32_t t_addr = (static_cast<uint32_t>(wq * 32) << 16) + half * 64;
+    uint32_t g = 0;
+    for (int m_tile = blockIdx.x; m_tile < n_m_tiles; m_tile += gridDim.x) {
+      const int seq = m_tile / tiles_per_seq, t0 = (m_tile % tiles_per_seq) * BM;
+      const int t = t0 + r;
+      const size_t orow = static_cast<size_t>(seq) * p.rows_per_seq + t;
+      for (int nt = 0; nt < n_tiles_n; ++nt) {
+        float acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int buf = g % kPAcc;
+          mbar_wait(&acc_full[buf], (g / kPAcc) & 1, 96);
+          tc_fence_after();
+          uint32_t ra[32], rb[32];
+          tmem_ld32(tmem_base + buf * 128 + t_addr, ra);
+          tmem_ld32(tmem_base + buf * 128 + t_addr + 32, rb);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&acc_empty[buf]);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            acc[i] += __uint_as_float(ra[i]);
+            acc[32 + i] += __uint_as_float(rb[i]);
+          }
+        }
+        if (t < p.rows_per_seq) {
+          const int col0 = nt * BN + half * 64;
+          float* op = p.out + orow * p.ldo + col0;
+          const float* rp = p.residual ? p.residual + orow * p.ldr + col0 : nullptr;
+          const float wsc = p.w_inv_scale, alpha = p.alpha;
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+            float4 v;
+            v.x = alpha * act_apply<kAct>(fmaf(acc[i + 0], wsc, bb.x));
+            v.y = alpha * act_apply<kAct>(fmaf(acc[i + 1], wsc, bb.y));
+            v.z = alpha * act_apply<kAct>(fmaf(acc[i + 2], wsc, bb.z));
+            v.w = alpha * act_apply<kAct>(fmaf(acc[i + 3], wsc, bb.w));
+            if (rp) {
+              const float4 rs = *reinterpret_cast<const float4*>(rp + i);
+              v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w;
+            }
+            *reinterpret_cast<float4*>(op + i) = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 7) tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================================
 // Small-row form of the same product (see p32.cuh): at most 16 output rows.  CTA = 8 warps x 2 output columns; K is
 // walked in blocks of 512 whose activations (R x 512 fp32) are staged in shared memory once per CTA.
 constexpr int kRvMaxRows = 16, kRvKB = 512, kRvCols = 2, kRvWarps = 8;
@@ -1238,7 +1453,8 @@ void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P
   const int tiles_per_seq = (p.rows_per_seq + BM - 1) / BM;
   const int grid = p.n_seq * tiles_per_seq * (p.N / BN);
   // persistent warp-specialised kernel once there is more than one tile per SM (FSEEND_P32_GEMM=0: always one-tile)
-  static int num_sms = 0, use_persist = 1;
+  static int num_sms = 0;
+  int use_persist = 1;
   static PerDeviceOnce once_p;
   if (once_p.first()) {
     cudaFuncSetAttribute(p32_gemm_persist_kernel<P32_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmem);
@@ -1247,7 +1463,26 @@ void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (const char* e = getenv("FSEEND_P32_GEMM")) use_persist = e[0] != '0';
+    cudaFuncSetAttribute(p32_gemm_astat_kernel<P32_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAstatSmem);
+    cudaFuncSetAttribute(p32_gemm_astat_kernel<P32_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAstatSmem);
+    cudaFuncSetAttribute(p32_gemm_astat_kernel<P32_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAstatSmem);
+  }
+  {
+    // read per launch (tests flip it): 0 = one-tile kernel only, 1 (default) = + persistent kernel, 2 = + A-stationary
+    // kernel where it applies.  The A-stationary form is correct but measured NO faster (26.1 vs 26.0 ms per parity forward):
+    // its profile (profiles/r02_p32astat.txt) moves the bound to the fold / epilogue warps (accurate expf + reciprocal of
+    // the swish epilogue: 20 % of the samples; tail imbalance at the final barrier: 21 %), i.e. re-splitting A per column
+    // tile was not what limits the persistent kernel.
+    use_persist = 1;
+    if (const char* e = getenv("FSEEND_P32_GEMM")) use_persist = (e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  if (use_persist >= 2 && p.taps == 1 && p.k_blocks <= kSMaxKB && p.N >= 2 * BN && p.n_seq * tiles_per_seq > num_sms &&
+      p.a_row_offset == 0 && p.a_row_offset_dev == nullptr && p.tap_shift == 0 && p.a_seq_rows == p.rows_per_seq) {
+    const int n_m = p.n_seq * tiles_per_seq;
+    if (p.act == P32_RELU) p32_gemm_astat_kernel<P32_RELU><<<num_sms, kPThreads, kAstatSmem, st>>>(tmWhi, tmWlo, p, n_m);
+    else if (p.act == P32_SWISH) p32_gemm_astat_kernel<P32_SWISH><<<num_sms, kPThreads, kAstatSmem, st>>>(tmWhi, tmWlo, p, n_m);
+    else p32_gemm_astat_kernel<P32_NONE><<<num_sms, kPThreads, kAstatSmem, st>>>(tmWhi, tmWlo, p, n_m);
+    return;
   }
   if (use_persist && grid > num_sms) {
     if (p.act == P32_RELU) p32_gemm_persist_kernel<P32_RELU><<<num_sms, kPThreads, kPersistSmem, st>>>(tmWhi, tmWlo, p, grid);

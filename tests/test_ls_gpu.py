@@ -191,6 +191,26 @@ def test_p32_split_gemm_matches_fp64(N):
     assert torch.isfinite(out2).all() and rel < 3e-6
 
 
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
+def test_p32_gemm_kernel_variants_agree(N, monkeypatch, variant):
+    """FSEEND_P32_GEMM = 0 one-tile kernel, 1 persistent warp-specialised kernel (default), 2 A-stationary kernel: the same
+    product (20 000 rows: more row tiles than SMs, K = 256, N = 512 with residual / 1024 with swish) against fp64."""
+    monkeypatch.setenv("FSEEND_P32_GEMM", variant)
+    a = rnd(20000, 256, seed=51) * 2.0
+    w = rnd(512, 256, scale=1 / 16, seed=52)
+    bias = rnd(512, seed=53) * 0.3
+    res = rnd(20000, 512, seed=54)
+    lin = N.P32Linear(w)
+    out = lin(a, bias=bias, alpha=0.5, residual=res)
+    ref = res.double() + 0.5 * (a.double() @ w.double().T + bias.double())
+    assert (out.double() - ref).abs().max().item() < 1e-5
+    w2 = rnd(1024, 256, scale=1 / 16, seed=55)
+    out2 = N.P32Linear(w2)(a, act=2)
+    h = a.double() @ w2.double().T
+    ref2 = h * torch.sigmoid(h)
+    assert (out2.double() - ref2).abs().max().item() < 1e-5
+
+
 def test_p32_linear_handle_reuse_and_small_rows(N):
     lin = N.P32Linear(rnd(128, 4864, scale=0.02, seed=46))
     for rows in (1, 5, 130):
