@@ -1,0 +1,204 @@
+"""torch.autograd.Functions over the native training kernels (csrc/train_ops.cu, csrc/train_attn.cu).
+
+SURVEY.md §8f "N1" — STARTED, not a training step: forward AND backward of Linear(+ReLU), residual + LayerNorm and
+causal multi-head attention run in this library's kernels (fp32 tensors, split-precision tcgen05 products), composed
+here into the reference's post-norm encoder layer (``nn.TransformerEncoderLayer`` as constructed at ``FS:model:147``
+and looped at ``FS:fusion:129-131``).  Gradients are pinned against torch autograd in tests/test_train_ops_gpu.py.
+Dropout is not implemented (p = 0 only); there is no optimizer or DDP wrapper.
+
+No CPU path: every Function raises FseendError on non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import native as N
+from .native import FseendError, _check, _ptr, _stream, lib
+
+_ws: dict = {}
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    """One grow-only scratch buffer per device (kernels of one stream run in order, so it is reused by every call)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=dev)
+        _ws[key] = buf
+    return buf
+
+
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise FseendError(f"{what}: CUDA float32 tensor required (fseend_b200 has no CPU fallback)")
+    return t.contiguous()
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b); x [..., K], W [N, K] (N % 128 == 0), act in {"none", "relu"}."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act: str = "none"):
+        x2 = _f32c(x, "LinearFn x").reshape(-1, x.shape[-1])
+        w = _f32c(w, "LinearFn w")
+        rows, K = x2.shape
+        Nn = w.shape[0]
+        if w.shape[1] != K:
+            raise FseendError("LinearFn: x / w shape mismatch")
+        a = {"none": 0, "relu": 1}[act]
+        y = torch.empty(rows, Nn, device=x.device, dtype=torch.float32)
+        nb = lib().fseend_train_linear_workspace_bytes(rows, K, Nn)
+        ws = _workspace(x.device, nb)
+        with torch.cuda.device(x.device):
+            _check(lib().fseend_train_linear_fwd(_ptr(x2), rows, K, _ptr(w), Nn, _ptr(None if b is None else _f32c(b, "b")), a,
+                                                 _ptr(y), _ptr(ws), ws.numel(), _stream()))
+        ctx.save_for_backward(x2, w, y if a == 1 else None)
+        ctx.act, ctx.has_bias, ctx.xshape = a, b is not None, x.shape
+        return y.view(*x.shape[:-1], Nn)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, y = ctx.saved_tensors
+        rows, K = x2.shape
+        Nn = w.shape[0]
+        dy2 = _f32c(dy, "LinearFn dy").reshape(rows, Nn)
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(Nn, device=w.device, dtype=torch.float32) if ctx.has_bias else None
+        nb = lib().fseend_train_linear_workspace_bytes(rows, K, Nn)
+        ws = _workspace(w.device, nb)
+        with torch.cuda.device(w.device):
+            _check(lib().fseend_train_linear_bwd(_ptr(x2), _ptr(w), _ptr(y), _ptr(dy2), rows, K, Nn, ctx.act, _ptr(dx), _ptr(dw),
+                                                 _ptr(db), _ptr(ws), ws.numel(), _stream()))
+        return (None if dx is None else dx.view(ctx.xshape)), dw, db, None
+
+
+class AddLayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(x + r) over the last dim (256); r may be None.  Gradient flows equally into x and r."""
+
+    @staticmethod
+    def forward(ctx, x, r, g, b, eps: float = 1e-5):
+        x2 = _f32c(x, "AddLayerNormFn x").reshape(-1, 256)
+        r2 = None if r is None else _f32c(r, "AddLayerNormFn r").reshape(-1, 256)
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        s = torch.empty_like(x2) if r2 is not None else None
+        with torch.cuda.device(x.device):
+            _check(lib().fseend_train_add_layernorm_fwd(_ptr(x2), _ptr(r2), _ptr(_f32c(g, "g")), _ptr(_f32c(b, "b")), rows,
+                                                        float(eps), _ptr(s), _ptr(y), _stream()))
+        ctx.save_for_backward(x2 if s is None else s, g)
+        ctx.eps, ctx.has_r, ctx.shape = float(eps), r is not None, x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        s, g = ctx.saved_tensors
+        rows = s.shape[0]
+        dy2 = _f32c(dy, "AddLayerNormFn dy").reshape(rows, 256)
+        dx = torch.empty_like(s)
+        dg = torch.empty(256, device=s.device, dtype=torch.float32)
+        db = torch.empty(256, device=s.device, dtype=torch.float32)
+        nb = lib().fseend_train_layernorm_workspace_bytes(rows)
+        ws = _workspace(s.device, nb)
+        with torch.cuda.device(s.device):
+            _check(lib().fseend_train_layernorm_bwd(_ptr(s), _ptr(g.contiguous()), _ptr(dy2), rows, ctx.eps, _ptr(dx), _ptr(dg),
+                                                    _ptr(db), _ptr(ws), ws.numel(), _stream()))
+        dxv = dx.view(ctx.shape)
+        return dxv, (dxv if ctx.has_r else None), dg, db, None
+
+
+class CausalAttnFn(torch.autograd.Function):
+    """qkv [n_seq, T, 768] (already projected, q | k | v) -> [n_seq, T, 256]; key j visible to query i iff j <= i + delay."""
+
+    @staticmethod
+    def forward(ctx, qkv, mask_delay: int = 0):
+        qkv = _f32c(qkv, "CausalAttnFn qkv")
+        if qkv.dim() != 3 or qkv.shape[-1] != 768:
+            raise FseendError("CausalAttnFn: qkv must be [n_seq, T, 768]")
+        n, T, _ = qkv.shape
+        out = torch.empty(n, T, 256, device=qkv.device, dtype=torch.float32)
+        lse = torch.empty(n, 4, T, device=qkv.device, dtype=torch.float32)
+        with torch.cuda.device(qkv.device):
+            _check(lib().fseend_train_attn_fwd(_ptr(qkv), n, T, int(mask_delay), _ptr(out), _ptr(lse), _stream()))
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.delay = int(mask_delay)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        n, T, _ = qkv.shape
+        dout = _f32c(dout, "CausalAttnFn dout")
+        dqkv = torch.empty_like(qkv)
+        dsum = torch.empty_like(lse)
+        with torch.cuda.device(qkv.device):
+            _check(lib().fseend_train_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), n, T, ctx.delay, _ptr(dqkv),
+                                               _ptr(dsum), _stream()))
+        return dqkv, None
+
+
+class SpeakerAttnFn(torch.autograd.Function):
+    """qkv [n_frames, S, 768] -> [n_frames, S, 256]: unmasked 4-head attention over the speaker axis (FS:fusion:390)."""
+
+    @staticmethod
+    def forward(ctx, qkv):
+        qkv = _f32c(qkv, "SpeakerAttnFn qkv")
+        if qkv.dim() != 3 or qkv.shape[-1] != 768 or qkv.shape[1] > 16:
+            raise FseendError("SpeakerAttnFn: qkv must be [n_frames, S <= 16, 768]")
+        n, S, _ = qkv.shape
+        out = torch.empty(n, S, 256, device=qkv.device, dtype=torch.float32)
+        with torch.cuda.device(qkv.device):
+            _check(lib().fseend_train_spk_attn_fwd(_ptr(qkv), n, S, _ptr(out), _stream()))
+        ctx.save_for_backward(qkv)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        n, S, _ = qkv.shape
+        dout = _f32c(dout, "SpeakerAttnFn dout")
+        dqkv = torch.empty_like(qkv)
+        with torch.cuda.device(qkv.device):
+            _check(lib().fseend_train_spk_attn_bwd(_ptr(qkv), _ptr(dout), n, S, _ptr(dqkv), _stream()))
+        return dqkv
+
+
+def _mha(sa: nn.MultiheadAttention, x: torch.Tensor, attend) -> torch.Tensor:
+    qkv = LinearFn.apply(x, sa.in_proj_weight, sa.in_proj_bias, "none")
+    return LinearFn.apply(attend(qkv), sa.out_proj.weight, sa.out_proj.bias, "none")
+
+
+def _ffn(layer, x: torch.Tensor) -> torch.Tensor:
+    h = LinearFn.apply(x, layer.linear1.weight, layer.linear1.bias, "relu")
+    return LinearFn.apply(h, layer.linear2.weight, layer.linear2.bias, "none")
+
+
+def fusion_layer_forward(layer, x: torch.Tensor, mask_delay: int = 0) -> torch.Tensor:
+    """The reference's attractor-decoder layer, live path ``FS:fusion:356-376`` (post-norm, dropout 0), differentiable.
+
+    x: [B, T, S, 256].  Time attention runs over [B*S, T, 256] (causal), speaker attention over [B*T, S, 256] (no mask);
+    ``norm12`` is unused, as in the reference.  The two layout changes are torch copies."""
+    B, T, S, D = x.shape
+    y = x.transpose(1, 2).reshape(B * S, T, D)
+    y = AddLayerNormFn.apply(_mha(layer.self_attn1, y, lambda qkv: CausalAttnFn.apply(qkv, mask_delay)), y,
+                             layer.norm11.weight, layer.norm11.bias, layer.norm11.eps)
+    y = y.reshape(B, S, T, D).transpose(1, 2).reshape(B * T, S, D)
+    y = AddLayerNormFn.apply(_mha(layer.self_attn2, y, SpeakerAttnFn.apply), y, layer.norm21.weight, layer.norm21.bias,
+                             layer.norm21.eps)
+    y = AddLayerNormFn.apply(_ffn(layer, y), y, layer.norm22.weight, layer.norm22.bias, layer.norm22.eps)
+    return y.reshape(B, T, S, D)
+
+
+def encoder_layer_forward(layer: nn.TransformerEncoderLayer, x: torch.Tensor, mask_delay: int = 0) -> torch.Tensor:
+    """The reference's post-norm encoder layer (``FS:model:147``; dropout 0) on native kernels, differentiable.
+
+    x: [n_seq, T, 256] (batch-first; the reference runs (T, B, 256) — the math is per sequence, the layout is ours).
+    ``layer`` only provides the parameters (reference names: self_attn.in_proj_*, self_attn.out_proj, linear1/2, norm1/2).
+    """
+    if layer.norm_first:
+        raise FseendError("encoder_layer_forward: the reference layer is post-norm")
+    o = _mha(layer.self_attn, x, lambda qkv: CausalAttnFn.apply(qkv, mask_delay))
+    x = AddLayerNormFn.apply(o, x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
+    f = _ffn(layer, x)
+    return AddLayerNormFn.apply(f, x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)

@@ -9,7 +9,7 @@ PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_DIR = os.path.join(PKG_ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libfseend_b200.so")
-SOURCES = ["gemm.cu", "gemm_persist.cu", "gemm_pair.cu", "attn.cu", "attn2.cu", "attn3.cu", "ffn.cu", "ffn_pair.cu", "retention.cu", "p32.cu", "elementwise.cu", "embloss.cu", "spkfuse.cu", "loss.cu",
+SOURCES = ["gemm.cu", "gemm_persist.cu", "gemm_pair.cu", "attn.cu", "attn2.cu", "attn3.cu", "ffn.cu", "ffn_pair.cu", "retention.cu", "p32.cu", "elementwise.cu", "embloss.cu", "spkfuse.cu", "loss.cu", "train_ops.cu", "train_attn.cu",
            "fs_model.cu"]
 
 

@@ -3,8 +3,8 @@
 reference keeps inline in ``training_step`` (:51-76) as ``prepare_labels``, plus the permutation-invariant losses of the
 fine-tuning / offline harnesses (``batch_pit_loss`` :98-116, ``batch_pit_n_speaker_loss`` :257-327 and its label-delay
 form :329-403).  The frame sums run on the GPU through the C ABI (csrc/loss.cu); the list <-> padded-tensor plumbing
-and the search over the C! permutations of a C x C cost matrix stay on the host.  Forward values only: backward is
-SURVEY §8f N1.
+and the search over the C! permutations of a C x C cost matrix stay on the host.  ``standard_loss`` is differentiable (native value, closed-form
+gradient); the PIT losses return values only.
 """
 from itertools import permutations
 
@@ -19,12 +19,37 @@ def _device(ts):
     return ts[0].device if ts[0].is_cuda else torch.device("cuda")
 
 
+class _BceLossFn(torch.autograd.Function):
+    """standard_loss value from the native kernel (csrc/loss.cu); gradient (sigmoid(y) - label) / (classes * frames) on
+    the frames / classes the loss covers, as the reference's autograd produces for loss.py:119-125."""
+
+    @staticmethod
+    def forward(ctx, y, t, lens, ncls, label_delay):
+        from fseend_b200.native import op_bce_loss
+        ctx.save_for_backward(y, t, lens, ncls)
+        ctx.delay = int(label_delay)
+        return op_bce_loss(y.detach().contiguous(), t.contiguous(), lens, ncls, label_delay)
+
+    @staticmethod
+    def backward(ctx, g):
+        y, t, lens, ncls = ctx.saved_tensors
+        B, T, Cn = y.shape
+        d = ctx.delay
+        tt = torch.zeros_like(y)
+        tt[:, d:, :t.shape[2]] = t[:, :T - d]
+        fr = torch.arange(T, device=y.device)[None, :, None]
+        valid = (fr >= d) & (fr < lens[:, None, None]) & (torch.arange(Cn, device=y.device)[None, None, :] < ncls[:, None, None])
+        n_frames = (lens.sum() - d * B).to(torch.float32)
+        grad = (torch.sigmoid(y) - tt) * valid / (ncls[:, None, None].to(torch.float32) * n_frames)
+        return grad * g, None, None, None, None
+
+
 def standard_loss(ys, ts, label_delay=0):
-    """Reference loss.py:119-125.  ys: B-length list of logits (T_b, C_b); ts: B-length list of labels (T_b, C_b)."""
-    from fseend_b200.native import op_bce_loss
+    """Reference loss.py:119-125.  ys: B-length list of logits (T_b, C_b); ts: B-length list of labels (T_b, C_b).
+    Differentiable w.r.t. ys when they carry autograd history (the training step, train/oln_tfm_enc_dec.py:82)."""
     dev = _device(ys)
     ymax = max(v.shape[1] for v in ys)
-    y = pad_sequence([torch.nn.functional.pad(v.detach().to(device=dev, dtype=torch.float32), (0, ymax - v.shape[1]))
+    y = pad_sequence([torch.nn.functional.pad(v.to(device=dev, dtype=torch.float32), (0, ymax - v.shape[1]))
                       for v in ys], batch_first=True)
     cmax = max(t.shape[1] for t in ts)
     t = pad_sequence([torch.nn.functional.pad(v.detach().to(device=dev, dtype=torch.float32), (0, cmax - v.shape[1]))
@@ -37,7 +62,9 @@ def standard_loss(ys, ts, label_delay=0):
         if tuple(yy.shape) != tuple(tt.shape):
             # the reference's binary_cross_entropy_with_logits raises on any shape mismatch (loss.py:121-123)
             raise ValueError("each prediction must have exactly its label's shape (frames, classes)")
-    return op_bce_loss(y.contiguous(), t.contiguous(), lens, ncls, label_delay)
+    if t.shape[2] != y.shape[2]:
+        t = torch.nn.functional.pad(t, (0, y.shape[2] - t.shape[2]))
+    return _BceLossFn.apply(y, t, lens, ncls, label_delay)
 
 
 def prepare_labels(labels, clip_lengths=None):

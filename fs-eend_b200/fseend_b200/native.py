@@ -50,6 +50,9 @@ EXPORTS = [
     "fseend_op_bce_loss", "fseend_op_bce_loss_workspace_bytes",
     "fseend_fs_forward_host_async", "fseend_fs_host_wait", "fseend_op_pit_costs", "fseend_ls_forward_host", "fseend_ls_set_option", "fseend_ls_get_option", "fseend_p32_linear_create",
     "fseend_p32_linear_destroy", "fseend_p32_linear_apply", "fseend_op_p32_retention",
+    "fseend_train_linear_workspace_bytes", "fseend_train_linear_fwd", "fseend_train_linear_bwd", "fseend_train_add_layernorm_fwd",
+    "fseend_train_layernorm_workspace_bytes", "fseend_train_layernorm_bwd", "fseend_train_attn_fwd", "fseend_train_attn_bwd",
+    "fseend_train_spk_attn_fwd", "fseend_train_spk_attn_bwd",
 ]
 
 
@@ -174,6 +177,27 @@ def lib() -> C.CDLL:
     L.fseend_op_embloss_workspace_bytes.argtypes = [ip, ip]
     L.fseend_op_embloss.restype = ip
     L.fseend_op_embloss.argtypes = [vp, vp, vp, ip, ip, ip, C.c_double, vp, vp, vp]
+    sz = C.c_size_t
+    L.fseend_train_linear_workspace_bytes.restype = sz
+    L.fseend_train_linear_workspace_bytes.argtypes = [ip, ip, ip]
+    L.fseend_train_linear_fwd.restype = ip
+    L.fseend_train_linear_fwd.argtypes = [vp, ip, ip, vp, ip, vp, ip, vp, vp, sz, vp]
+    L.fseend_train_linear_bwd.restype = ip
+    L.fseend_train_linear_bwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, vp, vp, vp, vp, sz, vp]
+    L.fseend_train_add_layernorm_fwd.restype = ip
+    L.fseend_train_add_layernorm_fwd.argtypes = [vp, vp, vp, vp, ip, fp, vp, vp, vp]
+    L.fseend_train_layernorm_workspace_bytes.restype = sz
+    L.fseend_train_layernorm_workspace_bytes.argtypes = [ip]
+    L.fseend_train_layernorm_bwd.restype = ip
+    L.fseend_train_layernorm_bwd.argtypes = [vp, vp, vp, ip, fp, vp, vp, vp, vp, sz, vp]
+    L.fseend_train_attn_fwd.restype = ip
+    L.fseend_train_attn_fwd.argtypes = [vp, ip, ip, ip, vp, vp, vp]
+    L.fseend_train_attn_bwd.restype = ip
+    L.fseend_train_attn_bwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, vp, vp, vp]
+    L.fseend_train_spk_attn_fwd.restype = ip
+    L.fseend_train_spk_attn_fwd.argtypes = [vp, ip, ip, vp, vp]
+    L.fseend_train_spk_attn_bwd.restype = ip
+    L.fseend_train_spk_attn_bwd.argtypes = [vp, vp, ip, ip, vp, vp]
     _lib = L
     return L
 

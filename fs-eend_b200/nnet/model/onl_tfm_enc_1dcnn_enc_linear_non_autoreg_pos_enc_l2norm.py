@@ -151,11 +151,13 @@ class OnlineTransformerDADiarization(NativeCacheMixin, nn.Module):
         return [o[:l] for o, l in zip(y, lens)]
 
     def forward(self, src, tgt, ilens):
-        """Reference :32-65 (eval-mode arithmetic).  Gradients are not produced: backward kernels are
-        SURVEY.md §8(f) N1."""
+        """Reference :32-65.  Without gradients (eval, or no_grad): the inference pipeline of the shared library.  In
+        train mode with gradients enabled: the differentiable path of fseend_b200.train_graph (native forward + backward
+        kernels for the GEMMs / attention / LayerNorm; SURVEY §8f N1, started)."""
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "fseend_b200 round 1 implements the forward hot path only; training backward is SURVEY §8(f) N1")
+            from fseend_b200.train_graph import fs_forward_train
+            with self._on_device():
+                return fs_forward_train(self, src, tgt, ilens)
         with torch.no_grad(), self._on_device():
             n_speakers = [t.shape[1] for t in tgt]
             max_nspks = max(n_speakers)

@@ -278,6 +278,42 @@ int fseend_p32_linear_apply(const fseend_p32_linear* h, const float* a_dev, int 
                             float alpha, const float* residual_dev, float* out_dev, void* stream);
 int fseend_op_p32_retention(const float* qkvg_dev, int B, int S, int T, int chunk, float* out_dev, void* stream);
 
+/* Training building blocks (csrc/train_ops.cu, csrc/train_attn.cu) — SURVEY.md §8f "N1", STARTED: forward + backward of
+ * the operators that carry the FS-EEND encoder layer (nn.TransformerEncoderLayer, post-norm, ReLU; constructed at
+ * FS-EEND/nnet/model/onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm.py:147, looped at
+ * nnet/modules/transformer_encoder_fusion.py:129-131), in the parity arithmetic (fp32 tensors, split-precision tcgen05
+ * products, fixed-order reductions).  All pointers are DEVICE fp32; calls are asynchronous on `stream`.  The weights
+ * are re-split on the device on every call (they change every optimizer step); |w| must stay below 1000.
+ * The torch.autograd.Functions over these live in fseend_b200/autograd.py; gradients are pinned against torch autograd
+ * in tests/test_train_ops_gpu.py.  There is no optimizer / DDP loop here. */
+size_t fseend_train_linear_workspace_bytes(int rows, int K, int N);
+/* y[rows][N] = act(x[rows][K] w[N][K]^T + bias); act 0 none, 1 ReLU; N % 128 == 0, any K. */
+int fseend_train_linear_fwd(const float* x, int rows, int K, const float* w, int N, const float* bias, int act, float* y,
+                            void* workspace, size_t ws_bytes, void* stream);
+/* dx[rows][K] (nullable) = dy' w;  dw[N][K] = dy'^T x;  db[N] (nullable) = column sums of dy';  dy' = dy masked by
+ * y > 0 when act == 1 (y = the saved forward output, else may be null). */
+int fseend_train_linear_bwd(const float* x, const float* w, const float* y, const float* dy, int rows, int K, int N,
+                            int act, float* dx, float* dw, float* db, void* workspace, size_t ws_bytes, void* stream);
+/* y = LayerNorm(x + r; g, b), rows of 256, biased variance, eps inside the sqrt; r and sum_out (= x + r) nullable. */
+int fseend_train_add_layernorm_fwd(const float* x, const float* r, const float* g, const float* b, int rows, float eps,
+                                   float* sum_out, float* y, void* stream);
+size_t fseend_train_layernorm_workspace_bytes(int rows);
+/* LayerNorm backward: x = the normalised tensor's input (x + r of the forward). */
+int fseend_train_layernorm_bwd(const float* x, const float* g, const float* dy, int rows, float eps, float* dx, float* dg,
+                               float* db, void* workspace, size_t ws_bytes, void* stream);
+/* Causal 4-head self-attention on projected qkv fp32 [n_seq][T][768] -> out fp32 [n_seq][T][256]; key j is visible to
+ * query i iff j <= i + mask_delay (FS model file :152-155); lse fp32 [n_seq][4][T] is saved for the backward. */
+int fseend_train_attn_fwd(const float* qkv, int n_seq, int T, int mask_delay, float* out, float* lse, void* stream);
+/* dqkv fp32 [n_seq][T][768] from dout [n_seq][T][256]; dsum: scratch fp32 [n_seq][4][T]. */
+int fseend_train_attn_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int n_seq, int T,
+                          int mask_delay, float* dqkv, float* dsum, void* stream);
+
+/* Speaker-axis attention (FS-EEND/nnet/modules/transformer_encoder_fusion.py:390 self_attn2: S x S per frame, no mask)
+ * on projected qkv fp32 [n_frames][S][768] -> out fp32 [n_frames][S][256]; S <= 16.  The backward recomputes the
+ * probabilities: dqkv fp32 [n_frames][S][768] from dout [n_frames][S][256]. */
+int fseend_train_spk_attn_fwd(const float* qkv, int n_frames, int S, float* out, void* stream);
+int fseend_train_spk_attn_bwd(const float* qkv, const float* dout, int n_frames, int S, float* dqkv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
