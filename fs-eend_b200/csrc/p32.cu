@@ -59,7 +59,7 @@ __device__ __forceinline__ float act_apply(float v) {
   return v;
 }
 
-template <int kAct>
+template <int kAct, bool kTrain = false>
 __global__ void __launch_bounds__(256, 1)
 p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                 const P32GemmParams p) {
@@ -121,9 +121,30 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
   // global-load latency hides behind the MMAs of the current k-block (the first version loaded and consumed in the same
   // iteration: ~1000 clk of exposed L2 latency per k-block)
   float4 pre[8];
+  const float ascale = (kTrain && p.a_scale_dev) ? __ldg(p.a_scale_dev) : 1.f;
   auto fetch = [&](int it) {
     const int tap = it / p.k_blocks;
     const int kb = it - tap * p.k_blocks;
+    if (kTrain && p.a_transposed) {
+      // lanes walk the tile's rows m (consecutive floats of one source row): coalesced scalar loads
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = tid + 256 * i;
+        const int m = q & 127, c = q >> 7;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        if (t0 + m < p.rows_per_seq) {
+          const int kbase = seq * (p.k_blocks * BK) + kb * BK + c * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)      // raw loads only: anything computed here would serialise them on their latency
+            if (kbase + j < p.a_k_rows) v[j] = __ldg(p.A + static_cast<size_t>(kbase + j) * p.lda + t0 + m);
+        }
+        pre[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+        pre[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int q = tid + 256 * i;
@@ -132,7 +153,8 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
       const int arow = t + tap + p.tap_shift + a_off;
       float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
       if (t < p.rows_per_seq && arow >= 0 && arow < p.a_seq_rows) {
-        const float4* src = reinterpret_cast<const float4*>(a_seq + static_cast<size_t>(arow) * p.lda + kb * BK + c * 8);
+        const size_t o = static_cast<size_t>(arow) * p.lda + kb * BK + c * 8;
+        const float4* src = reinterpret_cast<const float4*>(a_seq + o);
         v0 = __ldg(src);
         v1 = __ldg(src + 1);
       }
@@ -159,14 +181,22 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
     uint8_t* sWlo = sWhi + kTileBytes;
     if (tid == 0) {
       mbar_arrive_expect_tx(&full_bar[s], 2 * kTileBytes);
-      tma_load_2d(sWhi, &tmWhi, &full_bar[s], kb * BK, tap * p.N + n0);
-      tma_load_2d(sWlo, &tmWlo, &full_bar[s], kb * BK, tap * p.N + n0);
+      const int wrow = tap * p.N + n0 + (kTrain ? seq * p.w_seq_stride : 0);
+      tma_load_2d(sWhi, &tmWhi, &full_bar[s], kb * BK, wrow);
+      tma_load_2d(sWlo, &tmWlo, &full_bar[s], kb * BK, wrow);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int q = tid + 256 * i;
-      const int r = q >> 3, c = q & 7;
+      const bool tr = kTrain && p.a_transposed;
+      const int r = tr ? (q & 127) : (q >> 3), c = tr ? (q >> 7) : (q & 7);
       uint4 hi, lo;
+      if (kTrain) {
+        float4& a = pre[2 * i];
+        float4& b = pre[2 * i + 1];
+        a.x *= ascale; a.y *= ascale; a.z *= ascale; a.w *= ascale;
+        b.x *= ascale; b.y *= ascale; b.z *= ascale; b.w *= ascale;
+      }
       split8(pre[2 * i], pre[2 * i + 1], hi, lo);
       const uint32_t off = sw128_offset(r, c);
       *reinterpret_cast<uint4*>(sAhi + off) = hi;
@@ -216,7 +246,7 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
     }
     __syncthreads();
     const float4 bb = *reinterpret_cast<const float4*>(&bias_s[4 * lane]);
-    const float wsc = p.w_inv_scale, alpha = p.alpha;
+    const float wsc = p.w_inv_scale * ((kTrain && p.out_scale_dev) ? __ldg(p.out_scale_dev) : 1.f), alpha = p.alpha;
     const int col = n0 + 4 * lane;
     for (int r = warp; r < BM; r += 8) {
       const int t = t0 + r;
@@ -231,6 +261,10 @@ p32_gemm_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
       if (p.residual) {
         const float4 rr = *reinterpret_cast<const float4*>(p.residual + orow * p.ldr + col);
         v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+      }
+      if (kTrain && p.out_mask) {
+        const float4 mk = __ldg(reinterpret_cast<const float4*>(p.out_mask + orow * p.ldo + col));
+        v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
       }
       *reinterpret_cast<float4*>(p.out + orow * p.ldo + col) = v;
     }
@@ -260,7 +294,7 @@ constexpr int kPersistSmem = kPStages * kStageBytes + BM * kPLdT * 4 + 1024;
 constexpr int kPThreads = 16 * 32;
 constexpr int kPProd = 7 * 32;                       // producer threads
 
-template <int kAct>
+template <int kAct, bool kTrain = false>
 __global__ void __launch_bounds__(kPThreads, 1)
 p32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                         const P32GemmParams p, const int n_tiles) {
@@ -303,12 +337,32 @@ p32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_
   if (warp < 7) {
     // ------------------------------------------------------------ A producers (+ W TMA by thread 0)
     // k-block gi of this CTA = (tile blockIdx.x + (gi / total_it) * gridDim.x, it = gi % total_it)
+    const float ascale = (kTrain && p.a_scale_dev) ? __ldg(p.a_scale_dev) : 1.f;
     auto fetch = [&](float4 (&buf)[10], uint32_t gi) {
       if (gi >= G) return;
       const int tile = blockIdx.x + (gi / total_it) * gridDim.x, it = gi % total_it;
       const int m_tile = tile / n_tiles_n;
       const int seq = m_tile / tiles_per_seq, t0 = (m_tile % tiles_per_seq) * BM;
       const int tap = it / p.k_blocks, kb = it - tap * p.k_blocks;
+      if (kTrain && p.a_transposed) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int q = tid + kPProd * i;
+          const int m = q & 127, c = q >> 7;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+          if (q < 1024 && t0 + m < p.rows_per_seq) {
+            const int kbase = seq * (p.k_blocks * BK) + kb * BK + c * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)    // raw loads only: anything computed here would serialise them on their latency
+              if (kbase + j < p.a_k_rows) v[j] = __ldg(p.A + static_cast<size_t>(kbase + j) * p.lda + t0 + m);
+          }
+          buf[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+          buf[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        return;
+      }
       const float* a_seq = p.A + static_cast<size_t>(seq) * p.a_seq_rows * p.lda;
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
@@ -318,7 +372,8 @@ p32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_
         const int arow = t + tap + p.tap_shift + a_off;
         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
         if (q < 1024 && t < p.rows_per_seq && arow >= 0 && arow < p.a_seq_rows) {
-          const float4* src = reinterpret_cast<const float4*>(a_seq + static_cast<size_t>(arow) * p.lda + kb * BK + c * 8);
+          const size_t o = static_cast<size_t>(arow) * p.lda + kb * BK + c * 8;
+          const float4* src = reinterpret_cast<const float4*>(a_seq + o);
           v0 = __ldg(src);
           v1 = __ldg(src + 1);
         }
@@ -335,8 +390,15 @@ p32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_
       for (int i = 0; i < 5; ++i) {
         const int q = tid + kPProd * i;
         if (q < 1024) {
-          const int r = q >> 3, c = q & 7;
+          const bool tr = kTrain && p.a_transposed;
+          const int r = tr ? (q & 127) : (q >> 3), c = tr ? (q >> 7) : (q & 7);
           uint4 hi, lo;
+          if (kTrain) {
+            float4& a = buf[2 * i];
+            float4& b = buf[2 * i + 1];
+            a.x *= ascale; a.y *= ascale; a.z *= ascale; a.w *= ascale;
+            b.x *= ascale; b.y *= ascale; b.z *= ascale; b.w *= ascale;
+          }
           split8(buf[2 * i], buf[2 * i + 1], hi, lo);
           const uint32_t off = sw128_offset(r, c);
           *reinterpret_cast<uint4*>(sAhi + off) = hi;
@@ -349,9 +411,10 @@ p32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_
         const int tile = blockIdx.x + (gi / total_it) * gridDim.x, it = gi % total_it;
         const int n0 = (tile % n_tiles_n) * BN;
         const int tap = it / p.k_blocks, kb = it - tap * p.k_blocks;
+        const int wrow = tap * p.N + n0 + (kTrain ? ((tile / n_tiles_n) / tiles_per_seq) * p.w_seq_stride : 0);
         mbar_arrive_expect_tx(&full_bar[s], 2 * kTileBytes);
-        tma_load_2d(sAlo + kTileBytes, &tmWhi, &full_bar[s], kb * BK, tap * p.N + n0);
-        tma_load_2d(sAlo + 2 * kTileBytes, &tmWlo, &full_bar[s], kb * BK, tap * p.N + n0);
+        tma_load_2d(sAlo + kTileBytes, &tmWhi, &full_bar[s], kb * BK, wrow);
+        tma_load_2d(sAlo + 2 * kTileBytes, &tmWlo, &full_bar[s], kb * BK, wrow);
       } else {
         mbar_arrive(&full_bar[s]);
       }
@@ -429,7 +492,7 @@ p32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_
       const int col = n0 + 4 * lane;
       float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      const float wsc = p.w_inv_scale, alpha = p.alpha;
+      const float wsc = p.w_inv_scale * ((kTrain && p.out_scale_dev) ? __ldg(p.out_scale_dev) : 1.f), alpha = p.alpha;
       for (int rr = ew; rr < BM; rr += 8) {
         const int t = t0 + rr;
         if (t >= p.rows_per_seq) break;
@@ -443,6 +506,10 @@ p32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_
         if (p.residual) {
           const float4 rs = *reinterpret_cast<const float4*>(p.residual + orow * p.ldr + col);
           v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w;
+        }
+        if (kTrain && p.out_mask) {
+          const float4 mk = __ldg(reinterpret_cast<const float4*>(p.out_mask + orow * p.ldo + col));
+          v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
         }
         *reinterpret_cast<float4*>(p.out + orow * p.ldo + col) = v;
       }
@@ -1471,6 +1538,7 @@ void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P
   }
   const int tiles_per_seq = (p.rows_per_seq + BM - 1) / BM;
   const int grid = p.n_seq * tiles_per_seq * (p.N / BN);
+  const bool train = p.a_transposed || p.w_seq_stride || p.a_scale_dev || p.out_scale_dev || p.out_mask;
   // persistent warp-specialised kernel once there is more than one tile per SM (FSEEND_P32_GEMM=0: always one-tile)
   static int num_sms = 0;
   int use_persist = 1;
@@ -1482,6 +1550,8 @@ void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(p32_gemm_kernel<P32_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    cudaFuncSetAttribute(p32_gemm_persist_kernel<P32_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmem);
     cudaFuncSetAttribute(p32_gemm_astat_kernel<P32_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAstatSmem);
     cudaFuncSetAttribute(p32_gemm_astat_kernel<P32_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAstatSmem);
     cudaFuncSetAttribute(p32_gemm_astat_kernel<P32_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAstatSmem);
@@ -1494,6 +1564,11 @@ void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P
     // tile was not what limits the persistent kernel.
     use_persist = 1;
     if (const char* e = getenv("FSEEND_P32_GEMM")) use_persist = (e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  if (train) {        // backward products (train_ops.cu): transposed / scaled / masked A, per-sequence W; no activation
+    if (grid > num_sms) p32_gemm_persist_kernel<P32_NONE, true><<<num_sms, kPThreads, kPersistSmem, st>>>(tmWhi, tmWlo, p, grid);
+    else p32_gemm_kernel<P32_NONE, true><<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
+    return;
   }
   if (use_persist >= 2 && p.taps == 1 && p.k_blocks <= kSMaxKB && p.N >= 2 * BN && p.n_seq * tiles_per_seq > num_sms &&
       p.a_row_offset == 0 && p.a_row_offset_dev == nullptr && p.tap_shift == 0 && p.a_seq_rows == p.rows_per_seq) {

@@ -48,6 +48,21 @@ struct P32GemmParams {
   float* ln_out2 = nullptr;
   float ln_eps = 1e-5f;
   int l2norm = 0;
+  // Training (backward) products only — any of these selects the kTrain instantiation (act must be P32_NONE):
+  //  a_transposed: A is read through its transpose, A[m][k] = src[(seq * k_blocks * 64 + k) * lda + m] for k rows below
+  //                a_k_rows (zero beyond): the weight-gradient product reads dY / X as they lie, no transposed copy;
+  //                sequences are then split-K slices, their partial products land in out[seq][rows_per_seq][N]
+  //  w_seq_stride: W rows per sequence (the TMA row coordinate is tap * N + n0 + seq * w_seq_stride)
+  //  a_scale_dev : device float, A is multiplied by it before the fp16 split (a power of two: gradients are ~1e-6 and
+  //                would be fp16-subnormal); out_scale_dev: device float multiplied into the epilogue (its inverse)
+  //  out_mask    : same layout / ldo as out; outputs whose mask value is <= 0 are written as zero (ReLU backward fused
+  //                into the product that creates the gradient of the ReLU's output)
+  int a_transposed = 0;
+  int a_k_rows = 0;
+  int w_seq_stride = 0;
+  const float* a_scale_dev = nullptr;
+  const float* out_scale_dev = nullptr;
+  const float* out_mask = nullptr;
 };
 // tmWhi / tmWlo: 2-D (K, taps*N) fp16, box (64, 128), 128B swizzle
 void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P32GemmParams& p, cudaStream_t st);

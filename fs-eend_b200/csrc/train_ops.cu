@@ -5,14 +5,20 @@
 //
 //   Linear  y = act(x W^T + b)           reference call sites: every nn.Linear of FS:model / FS:fusion
 //     dX = dY W            p32 GEMM, A = dY [rows][N], planes = W^T [K][N]
-//     dW = dY^T X          p32 GEMM, A = dY^T [N][rows], planes = X^T [K][rows]   (both operands transposed on the device)
+//     dW = dY^T X          split-K p32 GEMM over the rows: the LARGER of dY / X is the A operand, read through its transpose
+//                          in place (no copy); the smaller one is transposed once into fp16 hi / lo planes laid out per
+//                          K-slice; the slices' partial products are summed in fixed order by a reduce kernel
 //     db = column sums of dY (two-stage, fixed order)
+//   Gradients are ~1e-6 in magnitude (the loss is a mean over B*T frames) — fp16-subnormal — so every backward product
+//   first takes max|dY| (one pass) and multiplies dY by a power of two that brings the maximum to [512, 1024); the
+//   epilogue multiplies by the inverse.  The ReLU mask (y > 0) is applied while dY is read, never materialised.
 //   LayerNorm (biased variance, eps inside the sqrt): dx per row, dgamma / dbeta as two-stage column sums
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 
@@ -63,45 +69,116 @@ __global__ void split_planes_kernel(const float* __restrict__ src, int R, int C,
   lo[i] = l;
 }
 
-// src fp32 [R][C] -> transposed [Cp][Rp] (zero padded): fp32 (dst32) and / or split planes (hi, lo), 32 x 32 smem tiles
+// src fp32 [R][C] -> fp16 hi / lo planes of its transpose, laid out per K-slice: plane[(r / ks) * Cp + c][r % ks] for
+// r < n_slices * ks, c < Cp (zero where r >= R or c >= C); values are multiplied by scale_host * (*scale_dev) and read as
+// zero where mask[r][c] <= 0.  32 x 32 smem tiles; ks % 32 == 0 so a tile never straddles two slices.
 __global__ void __launch_bounds__(256)
-transpose_kernel(const float* __restrict__ src, int R, int C, int Rp, int Cp, float scale, float* __restrict__ dst32,
-                 __half* __restrict__ hi, __half* __restrict__ lo) {
+transpose_split_kernel(const float* __restrict__ src, const float* __restrict__ mask, int R, int C, int ks, int Cp,
+                       float scale_host, const float* __restrict__ scale_dev, __half* __restrict__ hi,
+                       __half* __restrict__ lo) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+  const float scale = scale_host * (scale_dev ? __ldg(scale_dev) : 1.f);
   for (int j = ty; j < 32; j += 8) {
     const int r = r0 + j, c = c0 + tx;
-    tile[j][tx] = (r < R && c < C) ? src[static_cast<size_t>(r) * C + c] : 0.f;
+    float v = 0.f;
+    if (r < R && c < C) {
+      const size_t o = static_cast<size_t>(r) * C + c;
+      v = src[o];
+      if (mask && mask[o] <= 0.f) v = 0.f;
+    }
+    tile[j][tx] = v * scale;
+  }
+  __syncthreads();
+  const int slice = r0 / ks, rin0 = r0 - slice * ks;
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;                                        // output row = source column
+    if (c < Cp) {
+      const size_t o = (static_cast<size_t>(slice) * Cp + c) * ks + rin0 + tx;
+      __half h, l;
+      split1(tile[tx][j], h, l);
+      hi[o] = h;
+      lo[o] = l;
+    }
+  }
+}
+
+// max |x| over n floats into *slot (float bits of a non-negative value order like unsigned integers); slot zeroed before
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ slot) {
+  float m = 0.f;
+  const size_t n4 = n / 4;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(x[n4 * 4 + threadIdx.x]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float wm[8];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
+    if (m > 0.f) atomicMax(slot, __float_as_uint(m));            // NaN / inf propagate as "huge": scale falls back to 1
+  }
+}
+// sc[0] = 2^e with max * 2^e in [512, 1024), sc[1] = 2^-e  (1, 1 for an all-zero or non-finite tensor)
+__global__ void make_scale_kernel(const unsigned int* __restrict__ slot, float* __restrict__ sc) {
+  const float m = __uint_as_float(*slot);
+  float s = 1.f;
+  if (m > 0.f && m < 3e38f) {
+    int e = 9 - ilogbf(m);
+    e = max(-100, min(100, e));
+    s = exp2f(static_cast<float>(e));
+  }
+  sc[0] = s;
+  sc[1] = 1.f / s;
+}
+
+// dw[n][k] = sum over slices of partial[s][n][k]   (k < K; partial rows are n_out floats)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int n_slices, int M, int n_out, int K, float* __restrict__ dw) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(M) * K) return;
+  const int n = static_cast<int>(i / K), k = static_cast<int>(i % K);
+  float s = 0.f;
+  for (int sl = 0; sl < n_slices; ++sl) s += partial[(static_cast<size_t>(sl) * M + n) * n_out + k];
+  dw[i] = s;
+}
+// the swapped product: partial[s][k][n] (M = K rows of N floats) -> dw[n][k]
+__global__ void __launch_bounds__(256)
+splitk_reduce_t_kernel(const float* __restrict__ partial, int n_slices, int K, int N, float* __restrict__ dw) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int k = k0 + j, n = n0 + tx;
+    float s = 0.f;
+    if (k < K && n < N)
+      for (int sl = 0; sl < n_slices; ++sl) s += partial[(static_cast<size_t>(sl) * K + k) * N + n];
+    tile[j][tx] = s;
   }
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
-    const int c = c0 + j, r = r0 + tx;                           // output row = source column
-    if (c < Cp && r < Rp) {
-      const float v = tile[tx][j] * scale;
-      const size_t o = static_cast<size_t>(c) * Rp + r;
-      if (dst32) dst32[o] = v;
-      if (hi) {
-        __half h, l;
-        split1(v, h, l);
-        hi[o] = h;
-        lo[o] = l;
-      }
-    }
+    const int n = n0 + j, k = k0 + tx;
+    if (n < N && k < K) dw[static_cast<size_t>(n) * K + k] = tile[tx][j];
   }
 }
 
 // partial[blk][c] = sum over the block's rows of f(row, c); then out[c] = sum over blocks (fixed order)
 constexpr int kRowsPerBlk = 256;
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int R, int C, float* __restrict__ partial) {
-  // a [R][C]; b optional [R][C]: sums a * b (LayerNorm dgamma) or a alone
+colsum_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mask, int R, int C,
+                      float* __restrict__ partial) {
+  // a [R][C]; b optional [R][C]: sums a * b (LayerNorm dgamma) or a alone; mask optional: rows' elements with mask <= 0 skipped
   const int c = blockIdx.y * 256 + threadIdx.x;
   if (c >= C) return;
   const int r0 = blockIdx.x * kRowsPerBlk, r1 = min(R, r0 + kRowsPerBlk);
   float s = 0.f;
   for (int r = r0; r < r1; ++r) {
-    const float v = a[static_cast<size_t>(r) * C + c];
+    float v = a[static_cast<size_t>(r) * C + c];
+    if (mask && mask[static_cast<size_t>(r) * C + c] <= 0.f) v = 0.f;
     s += b ? v * b[static_cast<size_t>(r) * C + c] : v;
   }
   partial[static_cast<size_t>(blockIdx.x) * C + c] = s;
@@ -115,10 +192,13 @@ colsum_final_kernel(const float* __restrict__ partial, int n_blk, int C, float* 
   out[c] = static_cast<float>(s);
 }
 
-// dy *= (y > 0)   (ReLU backward on the saved output)
-__global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, size_t n, float* __restrict__ out) {
+// out = dy where y > 0 else 0   (ReLU backward on the saved output; only the stand-alone Linear(+ReLU) backward needs it —
+// the FFN pair folds the mask into the epilogue of the product that creates dY, see relu_input below)
+__global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, size_t n4, float* __restrict__ out) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = y[i] > 0.f ? dy[i] : 0.f;
+  if (i >= n4) return;
+  const float4 a = reinterpret_cast<const float4*>(y)[i], d = reinterpret_cast<const float4*>(dy)[i];
+  reinterpret_cast<float4*>(out)[i] = make_float4(a.x > 0.f ? d.x : 0.f, a.y > 0.f ? d.y : 0.f, a.z > 0.f ? d.z : 0.f, a.w > 0.f ? d.w : 0.f);
 }
 
 // LayerNorm backward, one warp per row of 256: dx = rstd * (dy g - mean(dy g) - xhat mean(dy g xhat)); also writes
@@ -214,6 +294,26 @@ inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 inline int pad64(int x) { return (x + 63) / 64 * 64; }
 inline int pad128(int x) { return (x + 127) / 128 * 128; }
 
+// Weight-gradient product dW[N][K] = dY^T X, split over the rows.  The operand with the larger feature dimension is A
+// (M = that dimension, read through its transpose); the other one becomes the per-slice planes (n_out columns).
+struct WgradPlan {
+  bool swap;        // false: A = dY (M = N), planes = X^T (n_out = pad128(K));  true: A = X (M = K), planes = dY^T (n_out = N)
+  int M, n_out, n_slices, ks;
+};
+inline WgradPlan wgrad_plan(int rows, int K, int N) {
+  WgradPlan pl;
+  pl.swap = K > N;
+  pl.M = pl.swap ? K : N;
+  pl.n_out = pl.swap ? N : pad128(K);
+  const int tiles = ((pl.M + 127) / 128) * (pl.n_out / 128);
+  int sl = (2 * 148 + tiles - 1) / tiles;
+  sl = std::min(sl, std::max(1, rows / 512));
+  sl = std::max(1, std::min(sl, 64));
+  pl.ks = pad64((rows + sl - 1) / sl);
+  pl.n_slices = (rows + pl.ks - 1) / pl.ks;
+  return pl;
+}
+
 CUtensorMap plane_map(const void* base, int rows, int K) {
   uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows)};
   uint64_t str[1] = {static_cast<uint64_t>(K)};
@@ -252,15 +352,16 @@ extern "C" {
 
 // Workspace (bytes) of fseend_train_linear_fwd / _bwd for a [rows][K] x [N][K]^T layer.
 size_t fseend_train_linear_workspace_bytes(int rows, int K, int N) {
-  const size_t Kp = pad64(K), Np = pad128(N), Kp128 = pad128(K), Rp = pad64(rows);
-  size_t fwd = 2 * align256(Np * Kp * 2) + align256(static_cast<size_t>(rows) * Kp * 4) + align256(static_cast<size_t>(rows) * Np * 4);
-  size_t bwd = 2 * align256(Kp128 * pad64(N) * 2)                  // W^T planes [K][N]
-               + align256(static_cast<size_t>(rows) * pad64(N) * 4)   // dY (relu-masked / column padded)
-               + align256(static_cast<size_t>(rows) * Kp128 * 4)      // dX padded
-               + align256(Np * Rp * 4)                                // dY^T fp32
-               + 2 * align256(Kp128 * Rp * 2)                         // X^T planes
-               + align256(Np * Kp128 * 4)                             // dW padded
-               + align256((static_cast<size_t>(rows) / kRowsPerBlk + 1) * N * 4);   // column-sum partials
+  const size_t Kp = pad64(K), Np = pad128(N), Kp128 = pad128(K);
+  const size_t fwd = 2 * align256(Np * Kp * 2) + align256(static_cast<size_t>(rows) * Kp * 4);
+  const WgradPlan pl = wgrad_plan(rows, K, N);
+  const size_t bwd = 256                                                        // max slot + scale pair
+                     + 2 * align256(Kp128 * Np * 2)                             // W^T planes [K][N]
+                     + align256(static_cast<size_t>(rows) * Kp128 * 4)          // dX padded
+                     + 2 * align256(static_cast<size_t>(pl.n_slices) * pl.n_out * pl.ks * 2)   // small operand's planes
+                     + align256(static_cast<size_t>(pl.n_slices) * pl.M * pl.n_out * 4)        // split-K partial products
+                     + align256((static_cast<size_t>(rows) / kRowsPerBlk + 1) * N * 4)         // column-sum partials
+                     + align256(static_cast<size_t>(rows) * N * 4);                            // ReLU-masked dY (act == 1 only)
   return (fwd > bwd ? fwd : bwd) + 4096;
 }
 
@@ -294,58 +395,111 @@ int fseend_train_linear_fwd(const float* x, int rows, int K, const float* w, int
 }
 
 // dx[rows][K] (nullable), dw[N][K], db[N] (nullable) from dy[rows][N]; act 1: dy is first masked with y > 0 (y = saved output).
+// relu_input != 0: x is itself the output of a ReLU and dx is written as zero where x <= 0 (the FFN pair: the ReLU's
+// backward rides in the epilogue of the down-projection's dgrad; the up-projection's backward then runs with act 0).
 int fseend_train_linear_bwd(const float* x, const float* w, const float* y, const float* dy, int rows, int K, int N, int act,
-                            float* dx, float* dw, float* db, void* workspace, size_t ws_bytes, void* stream) {
+                            int relu_input, float* dx, float* dw, float* db, void* workspace, size_t ws_bytes, void* stream) {
   return tguard([&] {
     if (!x || !w || !dy || !dw || !workspace || rows < 1) throw std::invalid_argument("linear_bwd: bad arguments");
     if (N % 128) throw std::invalid_argument("linear_bwd: N must be a multiple of 128");
     if (act == 1 && !y) throw std::invalid_argument("linear_bwd: ReLU backward needs the saved output");
+    if (relu_input && K % 128) throw std::invalid_argument("linear_bwd: relu_input needs K % 128 == 0");
     if (ws_bytes < fseend_train_linear_workspace_bytes(rows, K, N)) throw std::invalid_argument("linear_bwd: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int Kp = pad128(K), Rp = pad64(rows);
+    const int Kp = pad128(K);
+    const WgradPlan pl = wgrad_plan(rows, K, N);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     auto take = [&](size_t bytes) {
       uint8_t* p = ws;
       ws += align256(bytes);
       return p;
     };
+    unsigned int* slot = reinterpret_cast<unsigned int*>(take(256));
+    float* sc = reinterpret_cast<float*>(slot) + 4;                 // sc[0] scale, sc[1] inverse
     __half* wt_hi = reinterpret_cast<__half*>(take(static_cast<size_t>(Kp) * N * 2));
     __half* wt_lo = reinterpret_cast<__half*>(take(static_cast<size_t>(Kp) * N * 2));
-    float* dym = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * N * 4));
     float* dxp = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * Kp * 4));
-    float* dyt = reinterpret_cast<float*>(take(static_cast<size_t>(N) * Rp * 4));
-    __half* xt_hi = reinterpret_cast<__half*>(take(static_cast<size_t>(Kp) * Rp * 2));
-    __half* xt_lo = reinterpret_cast<__half*>(take(static_cast<size_t>(Kp) * Rp * 2));
-    float* dwp = reinterpret_cast<float*>(take(static_cast<size_t>(N) * Kp * 4));
+    const size_t plane_elems = static_cast<size_t>(pl.n_slices) * pl.n_out * pl.ks;
+    __half* sp_hi = reinterpret_cast<__half*>(take(plane_elems * 2));
+    __half* sp_lo = reinterpret_cast<__half*>(take(plane_elems * 2));
+    float* partial = reinterpret_cast<float*>(take(static_cast<size_t>(pl.n_slices) * pl.M * pl.n_out * 4));
     float* part = reinterpret_cast<float*>(take((static_cast<size_t>(rows) / kRowsPerBlk + 1) * N * 4));
-    const float* g = dy;
     if (act == 1) {
-      const size_t n = static_cast<size_t>(rows) * N;
-      relu_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(y, dy, n, dym);
-      g = dym;
+      float* dym = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * N * 4));
+      const size_t n4 = static_cast<size_t>(rows) * N / 4;
+      relu_bwd_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(y, dy, n4, dym);
+      dy = dym;
     }
+
+    // gradient scale: a power of two from max |dY|
+    TCHECK(cudaMemsetAsync(slot, 0, 4, st));
+    absmax_kernel<<<592, 256, 0, st>>>(dy, static_cast<size_t>(rows) * N, slot);
+    make_scale_kernel<<<1, 1, 0, st>>>(slot, sc);
+
     if (db) {
       const int nb = (rows + kRowsPerBlk - 1) / kRowsPerBlk;
-      colsum_partial_kernel<<<dim3(nb, (N + 255) / 256), 256, 0, st>>>(g, nullptr, rows, N, part);
+      colsum_partial_kernel<<<dim3(nb, (N + 255) / 256), 256, 0, st>>>(dy, nullptr, nullptr, rows, N, part);
       colsum_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(part, nb, N, db);
     }
     if (dx) {
-      // W^T planes [Kp][N] (rows >= K zero): transpose of w [N][K]
-      transpose_kernel<<<dim3((N + 31) / 32, (Kp + 31) / 32), 256, 0, st>>>(w, N, K, N, Kp, kWScale, nullptr, wt_hi, wt_lo);
+      // W^T planes [Kp][N] (rows >= K zero): one slice of N "rows"
+      transpose_split_kernel<<<dim3(N / 32, Kp / 32), 256, 0, st>>>(w, nullptr, N, K, N, Kp, kWScale, nullptr, wt_hi, wt_lo);
       float* out = (Kp == K) ? dx : dxp;
-      run_gemm(g, N, rows, N, wt_hi, wt_lo, Kp, nullptr, 0, 1.f / kWScale, out, Kp, st);
+      P32GemmParams p{};
+      p.A = dy;
+      p.lda = N;
+      p.a_seq_rows = rows;
+      p.rows_per_seq = rows;
+      p.n_seq = 1;
+      p.k_blocks = N / 64;
+      p.taps = 1;
+      p.N = Kp;
+      p.alpha = 1.f;
+      p.w_inv_scale = 1.f / kWScale;
+      p.out = out;
+      p.ldo = Kp;
+      p.a_scale_dev = sc;
+      p.out_scale_dev = sc + 1;
+      p.out_mask = relu_input ? x : nullptr;            // Kp == K here (checked above): same layout as out
+      launch_p32_gemm(plane_map(wt_hi, Kp, N), plane_map(wt_lo, Kp, N), p, st);
       if (Kp != K)
         TCHECK(cudaMemcpy2DAsync(dx, static_cast<size_t>(K) * 4, dxp, static_cast<size_t>(Kp) * 4, static_cast<size_t>(K) * 4, rows,
                                  cudaMemcpyDeviceToDevice, st));
     }
-    // dW[N][K] = sum_r dY[r][n] X[r][k]: A = dY^T [N][Rp] fp32, planes = X^T [Kp][Rp]
-    transpose_kernel<<<dim3(Rp / 32, (N + 31) / 32), 256, 0, st>>>(g, rows, N, Rp, N, 1.f, dyt, nullptr, nullptr);    // the grid covers the zero padding too
-    transpose_kernel<<<dim3(Rp / 32, (Kp + 31) / 32), 256, 0, st>>>(x, rows, K, Rp, Kp, 1.f, nullptr, xt_hi, xt_lo);
-    float* out = (Kp == K) ? dw : dwp;
-    run_gemm(dyt, Rp, N, Rp, xt_hi, xt_lo, Kp, nullptr, 0, 1.f, out, Kp, st);
-    if (Kp != K)
-      TCHECK(cudaMemcpy2DAsync(dw, static_cast<size_t>(K) * 4, dwp, static_cast<size_t>(Kp) * 4, static_cast<size_t>(K) * 4, N,
-                               cudaMemcpyDeviceToDevice, st));
+    {
+      // dW: A = the larger operand, read transposed in place; planes = the smaller one, transposed per K-slice
+      const float* a_src = pl.swap ? x : dy;
+      const int a_cols = pl.swap ? K : N;                      // = M
+      const float* s_src = pl.swap ? dy : x;
+      const int s_cols = pl.swap ? N : K;
+      transpose_split_kernel<<<dim3(pl.n_slices * pl.ks / 32, pl.n_out / 32), 256, 0, st>>>(
+          s_src, nullptr, rows, s_cols, pl.ks, pl.n_out, 1.f, pl.swap ? sc : nullptr, sp_hi, sp_lo);
+      P32GemmParams p{};
+      p.A = a_src;
+      p.lda = a_cols;
+      p.a_seq_rows = pl.M;
+      p.rows_per_seq = pl.M;
+      p.n_seq = pl.n_slices;
+      p.k_blocks = pl.ks / 64;
+      p.taps = 1;
+      p.N = pl.n_out;
+      p.alpha = 1.f;
+      p.w_inv_scale = 1.f;
+      p.out = partial;
+      p.ldo = pl.n_out;
+      p.a_transposed = 1;
+      p.a_k_rows = rows;
+      p.w_seq_stride = pl.n_out;
+      p.a_scale_dev = pl.swap ? nullptr : sc;
+      p.out_scale_dev = sc + 1;
+      const int plane_rows = pl.n_slices * pl.n_out;
+      launch_p32_gemm(plane_map(sp_hi, plane_rows, pl.ks), plane_map(sp_lo, plane_rows, pl.ks), p, st);
+      if (pl.swap)
+        splitk_reduce_t_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), 256, 0, st>>>(partial, pl.n_slices, K, N, dw);
+      else
+        splitk_reduce_kernel<<<static_cast<unsigned>((static_cast<size_t>(N) * K + 255) / 256), 256, 0, st>>>(
+            partial, pl.n_slices, N, pl.n_out, K, dw);
+    }
     TCHECK(cudaGetLastError());
   });
 }
@@ -376,9 +530,9 @@ int fseend_train_layernorm_bwd(const float* x, const float* g, const float* dy, 
     float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align256(static_cast<size_t>(rows) * 256 * 4));
     ln_bwd_row_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, g, dy, rows, eps, dx, xhat);
     const int nb = (rows + kRowsPerBlk - 1) / kRowsPerBlk;
-    colsum_partial_kernel<<<dim3(nb, 1), 256, 0, st>>>(dy, xhat, rows, 256, part);
+    colsum_partial_kernel<<<dim3(nb, 1), 256, 0, st>>>(dy, xhat, nullptr, rows, 256, part);
     colsum_final_kernel<<<1, 256, 0, st>>>(part, nb, 256, dg);
-    colsum_partial_kernel<<<dim3(nb, 1), 256, 0, st>>>(dy, nullptr, rows, 256, part);
+    colsum_partial_kernel<<<dim3(nb, 1), 256, 0, st>>>(dy, nullptr, nullptr, rows, 256, part);
     colsum_final_kernel<<<1, 256, 0, st>>>(part, nb, 256, db);
     TCHECK(cudaGetLastError());
   });

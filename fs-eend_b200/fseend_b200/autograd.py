@@ -69,9 +69,58 @@ class LinearFn(torch.autograd.Function):
         nb = lib().fseend_train_linear_workspace_bytes(rows, K, Nn)
         ws = _workspace(w.device, nb)
         with torch.cuda.device(w.device):
-            _check(lib().fseend_train_linear_bwd(_ptr(x2), _ptr(w), _ptr(y), _ptr(dy2), rows, K, Nn, ctx.act, _ptr(dx), _ptr(dw),
-                                                 _ptr(db), _ptr(ws), ws.numel(), _stream()))
+            _check(lib().fseend_train_linear_bwd(_ptr(x2), _ptr(w), _ptr(y), _ptr(dy2), rows, K, Nn, ctx.act, 0, _ptr(dx),
+                                                 _ptr(dw), _ptr(db), _ptr(ws), ws.numel(), _stream()))
         return (None if dx is None else dx.view(ctx.xshape)), dw, db, None
+
+
+def _linear_fwd(x2, w, b, act):
+    rows, K = x2.shape
+    Nn = w.shape[0]
+    y = torch.empty(rows, Nn, device=x2.device, dtype=torch.float32)
+    ws = _workspace(x2.device, lib().fseend_train_linear_workspace_bytes(rows, K, Nn))
+    _check(lib().fseend_train_linear_fwd(_ptr(x2), rows, K, _ptr(w), Nn, _ptr(b), act, _ptr(y), _ptr(ws), ws.numel(), _stream()))
+    return y
+
+
+def _linear_bwd(x2, w, dy2, relu_input, want_dx, want_db):
+    rows, K = x2.shape
+    Nn = w.shape[0]
+    dx = torch.empty_like(x2) if want_dx else None
+    dw = torch.empty_like(w)
+    db = torch.empty(Nn, device=w.device, dtype=torch.float32) if want_db else None
+    ws = _workspace(w.device, lib().fseend_train_linear_workspace_bytes(rows, K, Nn))
+    _check(lib().fseend_train_linear_bwd(_ptr(x2), _ptr(w), None, _ptr(dy2), rows, K, Nn, 0, 1 if relu_input else 0, _ptr(dx),
+                                         _ptr(dw), _ptr(db), _ptr(ws), ws.numel(), _stream()))
+    return dx, dw, db
+
+
+class FfnFn(torch.autograd.Function):
+    """y = relu(x W1^T + b1) W2^T + b2 (``_ff_block``, FS:fusion:397-399 / nn.TransformerEncoderLayer).  One Function so
+    that the ReLU's backward is folded into the epilogue of the down-projection's input-gradient product instead of a
+    separate pass over the [rows, 2048] gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x2 = _f32c(x, "FfnFn x").reshape(-1, x.shape[-1])
+        w1, b1, w2, b2 = (_f32c(t, "FfnFn parameter") for t in (w1, b1, w2, b2))
+        if w1.shape[0] % 128 or w2.shape[0] % 128 or w2.shape[1] != w1.shape[0] or w1.shape[1] != x2.shape[1]:
+            raise FseendError("FfnFn: shapes must be x [.., K], W1 [F, K], W2 [N, F] with F, N multiples of 128")
+        with torch.cuda.device(x.device):
+            h = _linear_fwd(x2, w1, b1, 1)
+            y = _linear_fwd(h, w2, b2, 0)
+        ctx.save_for_backward(x2, w1, w2, h)
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w1, w2, h = ctx.saved_tensors
+        dy2 = _f32c(dy, "FfnFn dy").reshape(h.shape[0], w2.shape[0])
+        with torch.cuda.device(x2.device):
+            dh, dw2, db2 = _linear_bwd(h, w2, dy2, True, True, True)           # dh already carries the ReLU mask
+            dx, dw1, db1 = _linear_bwd(x2, w1, dh, False, ctx.needs_input_grad[0], True)
+        return (None if dx is None else dx.view(ctx.xshape)), dw1, db1, dw2, db2
 
 
 class AddLayerNormFn(torch.autograd.Function):
@@ -170,8 +219,7 @@ def _mha(sa: nn.MultiheadAttention, x: torch.Tensor, attend) -> torch.Tensor:
 
 
 def _ffn(layer, x: torch.Tensor) -> torch.Tensor:
-    h = LinearFn.apply(x, layer.linear1.weight, layer.linear1.bias, "relu")
-    return LinearFn.apply(h, layer.linear2.weight, layer.linear2.bias, "none")
+    return FfnFn.apply(x, layer.linear1.weight, layer.linear1.bias, layer.linear2.weight, layer.linear2.bias)
 
 
 def fusion_layer_forward(layer, x: torch.Tensor, mask_delay: int = 0) -> torch.Tensor:

@@ -183,7 +183,7 @@ def lib() -> C.CDLL:
     L.fseend_train_linear_fwd.restype = ip
     L.fseend_train_linear_fwd.argtypes = [vp, ip, ip, vp, ip, vp, ip, vp, vp, sz, vp]
     L.fseend_train_linear_bwd.restype = ip
-    L.fseend_train_linear_bwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, vp, vp, vp, vp, sz, vp]
+    L.fseend_train_linear_bwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, ip, vp, vp, vp, vp, sz, vp]
     L.fseend_train_add_layernorm_fwd.restype = ip
     L.fseend_train_add_layernorm_fwd.argtypes = [vp, vp, vp, vp, ip, fp, vp, vp, vp]
     L.fseend_train_layernorm_workspace_bytes.restype = sz

@@ -291,9 +291,11 @@ size_t fseend_train_linear_workspace_bytes(int rows, int K, int N);
 int fseend_train_linear_fwd(const float* x, int rows, int K, const float* w, int N, const float* bias, int act, float* y,
                             void* workspace, size_t ws_bytes, void* stream);
 /* dx[rows][K] (nullable) = dy' w;  dw[N][K] = dy'^T x;  db[N] (nullable) = column sums of dy';  dy' = dy masked by
- * y > 0 when act == 1 (y = the saved forward output, else may be null). */
+ * y > 0 when act == 1 (y = the saved forward output, else may be null).  relu_input != 0: x is the output of a ReLU
+ * and dx is zeroed where x <= 0 (that ReLU's backward, fused; K % 128 == 0). */
 int fseend_train_linear_bwd(const float* x, const float* w, const float* y, const float* dy, int rows, int K, int N,
-                            int act, float* dx, float* dw, float* db, void* workspace, size_t ws_bytes, void* stream);
+                            int act, int relu_input, float* dx, float* dw, float* db, void* workspace, size_t ws_bytes,
+                            void* stream);
 /* y = LayerNorm(x + r; g, b), rows of 256, biased variance, eps inside the sqrt; r and sum_out (= x + r) nullable. */
 int fseend_train_add_layernorm_fwd(const float* x, const float* r, const float* g, const float* b, int rows, float eps,
                                    float* sum_out, float* y, void* stream);

@@ -31,6 +31,12 @@ class _AddLn:
         return F.layer_norm(x if r is None else x + r, (256,), g, b, eps)
 
 
+class _Ffn:
+    @staticmethod
+    def apply(x, w1, b1, w2, b2):
+        return F.linear(torch.relu(F.linear(x, w1, b1)), w2, b2)
+
+
 class _Causal:
     apply = staticmethod(_attn)
 
@@ -47,6 +53,7 @@ def test_train_graph_wiring_matches_oracle_autograd(monkeypatch, mask_delay):
     for mod in (A, G):
         monkeypatch.setattr(mod, "LinearFn", _Lin)
         monkeypatch.setattr(mod, "AddLayerNormFn", _AddLn)
+    monkeypatch.setattr(A, "FfnFn", _Ffn)
     monkeypatch.setattr(A, "CausalAttnFn", _Causal)
     monkeypatch.setattr(A, "SpeakerAttnFn", _Spk)
     monkeypatch.setattr(G, "_require_device", lambda dev: None)

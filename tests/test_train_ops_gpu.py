@@ -45,6 +45,32 @@ def test_linear_fwd_bwd(built_lib, rows, K, N, act):
     close(b.grad, br.grad, "db")
 
 
+@pytest.mark.parametrize("rows", [1000, 130])
+def test_ffn_fwd_bwd(built_lib, rows):
+    """The fused FFN pair (ReLU backward folded into the down-projection's dgrad epilogue); gradients as small as the
+    training loss produces them (1e-6): the power-of-two gradient scaling keeps them out of the fp16-subnormal range."""
+    from fseend_b200.autograd import FfnFn, LinearFn
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, 256, generator=g).cuda().requires_grad_()
+    w1 = (torch.randn(2048, 256, generator=g) / 16).cuda().requires_grad_()
+    b1 = (0.1 * torch.randn(2048, generator=g)).cuda().requires_grad_()
+    w2 = (torch.randn(256, 2048, generator=g) / 45).cuda().requires_grad_()
+    b2 = (0.1 * torch.randn(256, generator=g)).cuda().requires_grad_()
+    dy = (1e-6 * torch.randn(rows, 256, generator=g)).cuda()
+    y = FfnFn.apply(x, w1, b1, w2, b2)
+    y.backward(dy)
+    ps = [t.detach().double().requires_grad_() for t in (x, w1, b1, w2, b2)]
+    h = ps[0] @ ps[1].t() + ps[2]
+    # gate with the native forward's sign pattern (pre-activations within rounding of zero would flip whole elements):
+    # the same kernel on the same inputs reproduces the hidden layer bit for bit
+    gate = (LinearFn.apply(x.detach(), w1.detach(), b1.detach(), "relu") > 0).double()
+    yr = (h * gate) @ ps[3].t() + ps[4]
+    yr.backward(dy.double())
+    close(y, yr, "y")
+    for t, r, name in zip((x, w1, b1, w2, b2), ps, ("dx", "dw1", "db1", "dw2", "db2")):
+        close(t.grad, r.grad, name, rel=1e-4 if name in ("dx", "dw1", "db1") else REL)
+
+
 def test_linear_no_input_grad_no_bias(built_lib):
     from fseend_b200.autograd import LinearFn
     x = torch.randn(130, 256).cuda()

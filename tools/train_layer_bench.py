@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--native-only", action="store_true", help="one native forward+backward and exit (for ncu launch lists)")
     a = ap.parse_args()
     from fseend_b200.autograd import encoder_layer_forward
     torch.manual_seed(0)
@@ -62,6 +63,10 @@ def main():
         for p in list(layers.parameters()) + [x]:
             p.grad = None
 
+    if a.native_only:
+        native()
+        torch.cuda.synchronize()
+        return
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
 

@@ -1,0 +1,141 @@
+"""One FS-EEND training step (forward + standard_loss + emb loss + backward + Adam) at BASELINE config 1's shape
+(B=64 chunks of 500 frames, 345-d features, 4 enc + 2 dec layers) through the drop-in model — native forward/backward
+kernels — against the same graph in plain torch eager ops on the same GPU (float32 with TF32 off, and TF32 on).
+The torch arm is the stand-in graph of tests/test_train_graph_cpu.py (F.linear / F.layer_norm / explicit softmax
+attention), i.e. what the reference's nn.TransformerEncoderLayer stack executes; the reference package itself is not on
+the GPU box.  Prints one JSON line.  SURVEY §8f N1 is started: this is a secondary measurement, not the headline."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "fs-eend_b200")]
+
+
+def _attn(qkv, delay):
+    n, T, _ = qkv.shape
+    q, k, v = (t.reshape(n, T, 4, 64).transpose(1, 2) for t in qkv.split(256, dim=-1))
+    if delay >= T:
+        o = F.scaled_dot_product_attention(q, k, v)
+    elif delay == 0:
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=True)
+    else:
+        i = torch.arange(T, device=qkv.device)
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=i[None, :] <= i[:, None] + delay)
+    return o.transpose(1, 2).reshape(n, T, 256)
+
+
+class _Lin:
+    @staticmethod
+    def apply(x, w, b, act):
+        y = F.linear(x, w, b)
+        return torch.relu(y) if act == "relu" else y
+
+
+class _AddLn:
+    @staticmethod
+    def apply(x, r, g, b, eps):
+        return F.layer_norm(x if r is None else x + r, (256,), g, b, eps)
+
+
+class _Ffn:
+    @staticmethod
+    def apply(x, w1, b1, w2, b2):
+        return F.linear(torch.relu(F.linear(x, w1, b1)), w2, b2)
+
+
+class _Causal:
+    apply = staticmethod(_attn)
+
+
+class _Spk:
+    apply = staticmethod(lambda qkv: _attn(qkv, 1 << 20))
+
+
+def timed(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=500)
+    ap.add_argument("--speakers", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--native-only", action="store_true")
+    a = ap.parse_args()
+    import fseend_b200.autograd as A
+    import fseend_b200.train_graph as G
+    from fseend_b200.loss import standard_loss
+    from nnet.model.onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import OnlineTransformerDADiarization
+    torch.manual_seed(0)
+    m = OnlineTransformerDADiarization(n_speakers=4, in_size=345, n_units=256, n_heads=4, enc_n_layers=4, dec_n_layers=2,
+                                       dropout=0.0, has_mask=True, max_seqlen=500, dec_dim_feedforward=2048).cuda().train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-5)
+    B, T, S = a.batch, a.frames, a.speakers
+    src = [torch.randn(T, 345, device="cuda") for _ in range(B)]
+    tgt = [(torch.rand(T, S, device="cuda") < 0.3).float() for _ in range(B)]
+    # the labels the training step hands to model / loss carry silence + "no speaker" columns: S + 2 classes
+    lab = [torch.cat([1 - t.max(-1, keepdim=True)[0], t, torch.zeros(T, 1, device="cuda")], -1) for t in tgt]
+    lens = [T] * B
+    last = {}
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out, emb_loss, _, _ = m(src, lab, lens)
+        loss = standard_loss(out, lab, label_delay=0) + emb_loss
+        loss.backward()
+        opt.step()
+        last["loss"] = loss
+
+    if a.native_only:
+        step()
+        torch.cuda.synchronize()
+        return
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    state0 = {k: v.clone() for k, v in m.state_dict().items()}
+    t_native = timed(step, a.steps, a.warmup)
+    loss_native = last["loss"].item()
+    peak_native = torch.cuda.max_memory_allocated() / 2**30
+    # torch eager arm: same graph, stand-in ops
+    saved = {(mod, n): getattr(mod, n) for mod in (A, G) for n in ("LinearFn", "AddLayerNormFn")}
+    saved[(A, "CausalAttnFn")], saved[(A, "SpeakerAttnFn")], saved[(A, "FfnFn")] = A.CausalAttnFn, A.SpeakerAttnFn, A.FfnFn
+    for mod in (A, G):
+        mod.LinearFn, mod.AddLayerNormFn = _Lin, _AddLn
+    A.CausalAttnFn, A.SpeakerAttnFn, A.FfnFn = _Causal, _Spk, _Ffn
+    res = {}
+    for name, tf32 in (("torch_fp32", False), ("torch_tf32", True)):
+        m.load_state_dict(state0)
+        opt.state.clear()
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        res[name] = timed(step, a.steps, a.warmup)
+        res[name + "_loss"] = last["loss"].item()
+    for (mod, n), v in saved.items():
+        setattr(mod, n, v)
+    frames = B * T
+    print(json.dumps({"what": "FS-EEND training step (fwd + loss + bwd + Adam)", "batch": B, "frames": T, "label_classes": S + 2,
+                      "native_ms": round(t_native, 2), "torch_fp32_ms": round(res["torch_fp32"], 2),
+                      "torch_tf32_ms": round(res["torch_tf32"], 2), "native_frames_per_s": round(frames / t_native * 1e3),
+                      "loss_after_steps": {"native": loss_native, "torch_fp32": res["torch_fp32_loss"],
+                                           "torch_tf32": res["torch_tf32_loss"]},
+                      "native_peak_mem_gib": round(peak_native, 2)}))
+
+
+if __name__ == "__main__":
+    main()
