@@ -384,6 +384,13 @@ def secondary_measurements(dev):
                               "cpu_baseline": {"ms_per_frame": fs_cpu * 1e3, "cores": cpu_threads, "kind": "port",
                                                "sample": "60 frames + flush, oracle port (first 60 frames: shorter cache "
                                                          "than the GPU figure's 500)"}}
+    # ---------------- FS-EEND training step (started): native forward/backward kernels vs torch eager
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_step_bench
+        out["fs_train_step_B64_T500"] = train_step_bench.measure(steps=3, warmup=2)
+    except Exception as e:  # the headline must not depend on the secondary training measurement
+        out["fs_train_step_B64_T500"] = {"error": repr(e)[:300]}
     return out
 
 

@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 
@@ -96,6 +97,31 @@ __device__ __forceinline__ void mm_tn(const float* A, const float* B, int ty, in
       for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
   }
 }
+// Attention-probability dropout (nn.MultiheadAttention's `dropout`, applied to the softmax output): a counter-based
+// hash of (seed, sequence, head, query, key) decides every element, so forward and backward regenerate the same mask
+// with no stored state.  keep_scale() returns 0 (dropped) or 1 / (1 - p).  tests/test_train_ops_gpu.py carries the same
+// hash in torch integer arithmetic.
+struct Dropout {
+  uint32_t thresh;      // drop iff hash < thresh;  thresh = p * 2^32 (0: no dropout)
+  uint32_t seed_lo, seed_hi;
+  float inv_keep;       // 1 / (1 - p)
+};
+__device__ __forceinline__ uint32_t drop_hash(uint32_t seed_lo, uint32_t seed_hi, uint64_t idx) {
+  uint32_t x = static_cast<uint32_t>(idx) ^ seed_lo;
+  x *= 0x9E3779B1u;
+  x ^= x >> 15;
+  x += static_cast<uint32_t>(idx >> 32) * 0x85EBCA77u + seed_hi;
+  x *= 0xC2B2AE3Du;
+  x ^= x >> 13;
+  x *= 0x27D4EB2Fu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ float keep_scale(const Dropout& d, uint64_t row_base, int col) {
+  if (d.thresh == 0u) return 1.f;
+  return drop_hash(d.seed_lo, d.seed_hi, row_base + static_cast<uint64_t>(col)) < d.thresh ? 0.f : d.inv_keep;
+}
+
 __device__ __forceinline__ float half_warp_max(float v) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -109,7 +135,7 @@ __device__ __forceinline__ float half_warp_sum(float v) {
 
 __global__ void __launch_bounds__(256)
 train_attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ lse, int T, int delay,
-                      float scale) {
+                      float scale, const Dropout drop) {
   extern __shared__ __align__(16) float sm[];
   float *Qs = sm, *Ks = sm + kTile, *Vs = sm + 2 * kTile, *Ps = sm + 3 * kTile;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -140,12 +166,13 @@ train_attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, fl
       mx = half_warp_max(mx);
       const float mnew = fmaxf(m[i], mx);          // finite from the first key tile on (key 0 is visible to every row)
       const float corr = expf(m[i] - mnew);
+      const uint64_t rbase = ((static_cast<uint64_t>(n) * kHeads + h) * T + row) * T;
       float rs = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float p = expf(s[i][j] - mnew);
-        rs += p;
-        Ps[(ty + 16 * i) * kLD + tx + 16 * j] = p;
+        rs += p;                                    // the softmax normaliser sums the undropped probabilities
+        Ps[(ty + 16 * i) * kLD + tx + 16 * j] = p * keep_scale(drop, rbase, j0 + tx + 16 * j);
         o[i][j] *= corr;
       }
       l[i] = l[i] * corr + half_warp_sum(rs);
@@ -168,7 +195,7 @@ train_attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, fl
 __global__ void __launch_bounds__(256)
 train_attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ out, const float* __restrict__ dout,
                          const float* __restrict__ lse, float* __restrict__ dqkv, float* __restrict__ dsum, int T,
-                         int delay, float scale) {
+                         int delay, float scale, const Dropout drop) {
   extern __shared__ __align__(16) float sm[];
   float *Qs = sm, *dOs = sm + kTile, *Ks = sm + 2 * kTile, *Vs = sm + 3 * kTile, *Ps = sm + 4 * kTile;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -203,12 +230,13 @@ train_attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int row = i0 + ty + 16 * i;
+      const uint64_t rbase = ((static_cast<uint64_t>(n) * kHeads + h) * T + row) * T;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int col = j0 + tx + 16 * j;
         const bool ok = row < T && col < T && col <= row + delay;
         const float p = ok ? expf(s[i][j] * scale - L[i]) : 0.f;
-        Ps[(ty + 16 * i) * kLD + tx + 16 * j] = p * (dp[i][j] - D[i]) * scale;
+        Ps[(ty + 16 * i) * kLD + tx + 16 * j] = p * (dp[i][j] * keep_scale(drop, rbase, col) - D[i]) * scale;
       }
     }
     __syncthreads();
@@ -225,7 +253,8 @@ train_attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
 
 __global__ void __launch_bounds__(256)
 train_attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dout, const float* __restrict__ lse,
-                          const float* __restrict__ dsum, float* __restrict__ dqkv, int T, int delay, float scale) {
+                          const float* __restrict__ dsum, float* __restrict__ dqkv, int T, int delay, float scale,
+                          const Dropout drop) {
   extern __shared__ __align__(16) float sm[];
   float *Ks = sm, *Vs = sm + kTile, *Qs = sm + 2 * kTile, *dOs = sm + 3 * kTile, *Ps = sm + 4 * kTile, *dSs = sm + 5 * kTile;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -247,13 +276,15 @@ train_attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict
     for (int i = 0; i < 4; ++i) {
       const int row = i0 + ty + 16 * i;
       const float L = row < T ? lse[stat + row] : 0.f, D = row < T ? dsum[stat + row] : 0.f;
+      const uint64_t rbase = ((static_cast<uint64_t>(n) * kHeads + h) * T + row) * T;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int col = j0 + tx + 16 * j;
         const bool ok = row < T && col < T && col <= row + delay;
         const float p = ok ? expf(s[i][j] * scale - L) : 0.f;
-        Ps[(ty + 16 * i) * kLD + tx + 16 * j] = p;
-        dSs[(ty + 16 * i) * kLD + tx + 16 * j] = p * (dp[i][j] - D) * scale;
+        const float ks = keep_scale(drop, rbase, col);
+        Ps[(ty + 16 * i) * kLD + tx + 16 * j] = p * ks;
+        dSs[(ty + 16 * i) * kLD + tx + 16 * j] = p * (dp[i][j] * ks - D) * scale;
       }
     }
     __syncthreads();
@@ -284,7 +315,7 @@ inline int spk_bwd_smem(int S) { return 4 * (4 * S * kSpkLd + 2 * S * S) * 4; }
 
 __global__ void __launch_bounds__(128)
 train_spk_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dout, float* __restrict__ dqkv,
-                          int n_frames, int S, float scale) {
+                          int n_frames, int S, float scale, const Dropout drop) {
   extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * 4 + warp;                  // (frame, head), heads fastest
@@ -329,13 +360,18 @@ train_spk_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict
       sum += e;
     }
     const float inv = 1.f / sum;
+    const uint64_t rbase = ((static_cast<uint64_t>(f) * kHeads + h) * S + i) * S;
     float D = 0.f;
     for (int j = 0; j < S; ++j) {
       const float pj = P[i * S + j] * inv;
       P[i * S + j] = pj;
+      dS[i * S + j] *= keep_scale(drop, rbase, j);        // gradient w.r.t. the undropped probability
       D = fmaf(pj, dS[i * S + j], D);
     }
-    for (int j = 0; j < S; ++j) dS[i * S + j] = P[i * S + j] * (dS[i * S + j] - D) * scale;
+    for (int j = 0; j < S; ++j) {
+      dS[i * S + j] = P[i * S + j] * (dS[i * S + j] - D) * scale;
+      P[i * S + j] *= keep_scale(drop, rbase, j);         // dV uses the dropped probabilities
+    }
   }
   __syncwarp();
   float* obase = dqkv + static_cast<size_t>(f) * S * 768 + h * 64;
@@ -352,6 +388,64 @@ train_spk_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict
       obase[static_cast<size_t>(a) * 768 + d] = dq;
       obase[static_cast<size_t>(a) * 768 + 256 + d] = dk;
       obase[static_cast<size_t>(a) * 768 + 512 + d] = dv;
+    }
+  }
+}
+
+// Speaker-axis attention forward WITH dropout (the inference kernel p32_spk_attn_kernel serves p = 0): same staging as
+// the backward kernel, one warp per (frame, head).
+__global__ void __launch_bounds__(128)
+train_spk_attn_fwd_drop_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n_frames, int S, float scale,
+                               const Dropout drop) {
+  extern __shared__ __align__(16) float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + warp;
+  if (item >= n_frames * kHeads) return;
+  const int f = item >> 2, h = item & 3;
+  float* q = sm + warp * (3 * S * kSpkLd + S * S);
+  float *k = q + S * kSpkLd, *v = k + S * kSpkLd, *P = v + S * kSpkLd;
+  const float* base = qkv + static_cast<size_t>(f) * S * 768 + h * 64;
+  for (int i = 0; i < S; ++i) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int d = lane + 32 * hh;
+      q[i * kSpkLd + d] = base[static_cast<size_t>(i) * 768 + d];
+      k[i * kSpkLd + d] = base[static_cast<size_t>(i) * 768 + 256 + d];
+      v[i * kSpkLd + d] = base[static_cast<size_t>(i) * 768 + 512 + d];
+    }
+  }
+  __syncwarp();
+  for (int idx = lane; idx < S * S; idx += 32) {
+    const int i = idx / S, j = idx - i * S;
+    float sc = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < 64; ++d) sc = fmaf(q[i * kSpkLd + d], k[j * kSpkLd + d], sc);
+    P[i * S + j] = sc * scale;
+  }
+  __syncwarp();
+  if (lane < S) {
+    const int i = lane;
+    const uint64_t rbase = ((static_cast<uint64_t>(f) * kHeads + h) * S + i) * S;
+    float mx = -INFINITY;
+    for (int j = 0; j < S; ++j) mx = fmaxf(mx, P[i * S + j]);
+    float sum = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float e = expf(P[i * S + j] - mx);
+      P[i * S + j] = e;
+      sum += e;
+    }
+    const float inv = 1.f / sum;
+    for (int j = 0; j < S; ++j) P[i * S + j] *= inv * keep_scale(drop, rbase, j);
+  }
+  __syncwarp();
+  float* obase = out + static_cast<size_t>(f) * S * 256 + h * 64;
+  for (int a = 0; a < S; ++a) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int d = lane + 32 * hh;
+      float o = 0.f;
+      for (int b = 0; b < S; ++b) o = fmaf(P[a * S + b], v[b * kSpkLd + d], o);
+      obase[static_cast<size_t>(a) * 256 + d] = o;
     }
   }
 }
@@ -380,7 +474,17 @@ void set_attrs() {
     cudaFuncSetAttribute(train_attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * kTile * 4);
     cudaFuncSetAttribute(train_attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * kTile * 4);
     cudaFuncSetAttribute(train_spk_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSpkWarpFloats * 4);
+    cudaFuncSetAttribute(train_spk_attn_fwd_drop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSpkWarpFloats * 4);
   }
+}
+Dropout make_dropout(float p, unsigned long long seed) {
+  if (!(p >= 0.f && p < 1.f)) throw std::invalid_argument("dropout probability must be in [0, 1)");
+  Dropout d;
+  d.thresh = p > 0.f ? static_cast<uint32_t>(std::min(4294967295.0, static_cast<double>(p) * 4294967296.0)) : 0u;
+  d.seed_lo = static_cast<uint32_t>(seed);
+  d.seed_hi = static_cast<uint32_t>(seed >> 32);
+  d.inv_keep = 1.f / (1.f - p);
+  return d;
 }
 
 }  // namespace
@@ -390,48 +494,60 @@ using namespace fseend;
 
 extern "C" {
 
-int fseend_train_attn_fwd(const float* qkv, int n_seq, int T, int mask_delay, float* out, float* lse, void* stream) {
+int fseend_train_attn_fwd(const float* qkv, int n_seq, int T, int mask_delay, float dropout_p, unsigned long long seed,
+                          float* out, float* lse, void* stream) {
   return aguard([&] {
     if (!qkv || !out || !lse || n_seq < 1 || T < 1 || mask_delay < 0 || n_seq > 65535)
       throw std::invalid_argument("train_attn_fwd: bad arguments");
     set_attrs();
     train_attn_fwd_kernel<<<dim3((T + 63) / 64, kHeads, n_seq), 256, 4 * kTile * 4, static_cast<cudaStream_t>(stream)>>>(
-        qkv, out, lse, T, mask_delay, 0.125f);
+        qkv, out, lse, T, mask_delay, 0.125f, make_dropout(dropout_p, seed));
     check_launch("train_attn_fwd");
   });
 }
 
 // dsum: scratch fp32 [n_seq][4][T]
 int fseend_train_attn_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int n_seq, int T,
-                          int mask_delay, float* dqkv, float* dsum, void* stream) {
+                          int mask_delay, float dropout_p, unsigned long long seed, float* dqkv, float* dsum, void* stream) {
   return aguard([&] {
     if (!qkv || !out || !dout || !lse || !dqkv || !dsum || n_seq < 1 || T < 1 || mask_delay < 0 || n_seq > 65535)
       throw std::invalid_argument("train_attn_bwd: bad arguments");
     set_attrs();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const dim3 grid((T + 63) / 64, kHeads, n_seq);
-    train_attn_bwd_dq_kernel<<<grid, 256, 5 * kTile * 4, st>>>(qkv, out, dout, lse, dqkv, dsum, T, mask_delay, 0.125f);
-    train_attn_bwd_dkv_kernel<<<grid, 256, 6 * kTile * 4, st>>>(qkv, dout, lse, dsum, dqkv, T, mask_delay, 0.125f);
+    const Dropout drop = make_dropout(dropout_p, seed);
+    train_attn_bwd_dq_kernel<<<grid, 256, 5 * kTile * 4, st>>>(qkv, out, dout, lse, dqkv, dsum, T, mask_delay, 0.125f, drop);
+    train_attn_bwd_dkv_kernel<<<grid, 256, 6 * kTile * 4, st>>>(qkv, dout, lse, dsum, dqkv, T, mask_delay, 0.125f, drop);
     check_launch("train_attn_bwd");
   });
 }
 
 // Speaker-axis attention (no mask) on projected qkv fp32 [n_frames][S][768] -> out fp32 [n_frames][S][256], S <= 16.
-int fseend_train_spk_attn_fwd(const float* qkv, int n_frames, int S, float* out, void* stream) {
+int fseend_train_spk_attn_fwd(const float* qkv, int n_frames, int S, float dropout_p, unsigned long long seed, float* out,
+                              void* stream) {
   return aguard([&] {
     if (!qkv || !out || n_frames < 1 || S < 1 || S > kSpkMaxS) throw std::invalid_argument("train_spk_attn_fwd: bad arguments");
+    if (dropout_p > 0.f) {
+      set_attrs();
+      const int items = n_frames * kHeads;
+      train_spk_attn_fwd_drop_kernel<<<(items + 3) / 4, 128, 4 * (3 * S * kSpkLd + S * S) * 4, static_cast<cudaStream_t>(stream)>>>(
+          qkv, out, n_frames, S, 0.125f, make_dropout(dropout_p, seed));
+      check_launch("train_spk_attn_fwd");
+      return;
+    }
     if (launch_p32_spk_attn(qkv, out, n_frames, S, 0.125f, static_cast<cudaStream_t>(stream)) != 0)
       throw std::invalid_argument("train_spk_attn_fwd: S out of range");
     check_launch("train_spk_attn_fwd");
   });
 }
-int fseend_train_spk_attn_bwd(const float* qkv, const float* dout, int n_frames, int S, float* dqkv, void* stream) {
+int fseend_train_spk_attn_bwd(const float* qkv, const float* dout, int n_frames, int S, float dropout_p,
+                              unsigned long long seed, float* dqkv, void* stream) {
   return aguard([&] {
     if (!qkv || !dout || !dqkv || n_frames < 1 || S < 1 || S > kSpkMaxS) throw std::invalid_argument("train_spk_attn_bwd: bad arguments");
     set_attrs();
     const int items = n_frames * kHeads;
     train_spk_attn_bwd_kernel<<<(items + 3) / 4, 128, spk_bwd_smem(S), static_cast<cudaStream_t>(stream)>>>(
-        qkv, dout, dqkv, n_frames, S, 0.125f);
+        qkv, dout, dqkv, n_frames, S, 0.125f, make_dropout(dropout_p, seed));
     check_launch("train_spk_attn_bwd");
   });
 }

@@ -4,7 +4,8 @@ SURVEY.md §8f "N1" — STARTED, not a training step: forward AND backward of Li
 causal multi-head attention run in this library's kernels (fp32 tensors, split-precision tcgen05 products), composed
 here into the reference's post-norm encoder layer (``nn.TransformerEncoderLayer`` as constructed at ``FS:model:147``
 and looped at ``FS:fusion:129-131``).  Gradients are pinned against torch autograd in tests/test_train_ops_gpu.py.
-Dropout is not implemented (p = 0 only); there is no optimizer or DDP wrapper.
+Residual / FFN dropouts are torch's; the attention-probability dropout is the kernels' own (a counter-based hash mask
+regenerated in the backward).  There is no optimizer or DDP wrapper of our own (torch's work unchanged).
 
 No CPU path: every Function raises FseendError on non-CUDA tensors.
 """
@@ -161,7 +162,7 @@ class CausalAttnFn(torch.autograd.Function):
     """qkv [n_seq, T, 768] (already projected, q | k | v) -> [n_seq, T, 256]; key j visible to query i iff j <= i + delay."""
 
     @staticmethod
-    def forward(ctx, qkv, mask_delay: int = 0):
+    def forward(ctx, qkv, mask_delay: int = 0, dropout_p: float = 0.0, seed: int = 0):
         qkv = _f32c(qkv, "CausalAttnFn qkv")
         if qkv.dim() != 3 or qkv.shape[-1] != 768:
             raise FseendError("CausalAttnFn: qkv must be [n_seq, T, 768]")
@@ -169,9 +170,10 @@ class CausalAttnFn(torch.autograd.Function):
         out = torch.empty(n, T, 256, device=qkv.device, dtype=torch.float32)
         lse = torch.empty(n, 4, T, device=qkv.device, dtype=torch.float32)
         with torch.cuda.device(qkv.device):
-            _check(lib().fseend_train_attn_fwd(_ptr(qkv), n, T, int(mask_delay), _ptr(out), _ptr(lse), _stream()))
+            _check(lib().fseend_train_attn_fwd(_ptr(qkv), n, T, int(mask_delay), float(dropout_p), int(seed), _ptr(out),
+                                               _ptr(lse), _stream()))
         ctx.save_for_backward(qkv, out, lse)
-        ctx.delay = int(mask_delay)
+        ctx.delay, ctx.p, ctx.seed = int(mask_delay), float(dropout_p), int(seed)
         return out
 
     @staticmethod
@@ -182,24 +184,25 @@ class CausalAttnFn(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         dsum = torch.empty_like(lse)
         with torch.cuda.device(qkv.device):
-            _check(lib().fseend_train_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), n, T, ctx.delay, _ptr(dqkv),
-                                               _ptr(dsum), _stream()))
-        return dqkv, None
+            _check(lib().fseend_train_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), n, T, ctx.delay, ctx.p, ctx.seed,
+                                               _ptr(dqkv), _ptr(dsum), _stream()))
+        return dqkv, None, None, None
 
 
 class SpeakerAttnFn(torch.autograd.Function):
     """qkv [n_frames, S, 768] -> [n_frames, S, 256]: unmasked 4-head attention over the speaker axis (FS:fusion:390)."""
 
     @staticmethod
-    def forward(ctx, qkv):
+    def forward(ctx, qkv, dropout_p: float = 0.0, seed: int = 0):
         qkv = _f32c(qkv, "SpeakerAttnFn qkv")
         if qkv.dim() != 3 or qkv.shape[-1] != 768 or qkv.shape[1] > 16:
             raise FseendError("SpeakerAttnFn: qkv must be [n_frames, S <= 16, 768]")
         n, S, _ = qkv.shape
         out = torch.empty(n, S, 256, device=qkv.device, dtype=torch.float32)
         with torch.cuda.device(qkv.device):
-            _check(lib().fseend_train_spk_attn_fwd(_ptr(qkv), n, S, _ptr(out), _stream()))
+            _check(lib().fseend_train_spk_attn_fwd(_ptr(qkv), n, S, float(dropout_p), int(seed), _ptr(out), _stream()))
         ctx.save_for_backward(qkv)
+        ctx.p, ctx.seed = float(dropout_p), int(seed)
         return out
 
     @staticmethod
@@ -209,44 +212,65 @@ class SpeakerAttnFn(torch.autograd.Function):
         dout = _f32c(dout, "SpeakerAttnFn dout")
         dqkv = torch.empty_like(qkv)
         with torch.cuda.device(qkv.device):
-            _check(lib().fseend_train_spk_attn_bwd(_ptr(qkv), _ptr(dout), n, S, _ptr(dqkv), _stream()))
-        return dqkv
+            _check(lib().fseend_train_spk_attn_bwd(_ptr(qkv), _ptr(dout), n, S, ctx.p, ctx.seed, _ptr(dqkv), _stream()))
+        return dqkv, None, None
+
+
+def _seed() -> int:
+    """A fresh 62-bit seed for one attention call, drawn from torch's CPU generator (reproducible under manual_seed)."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+def _drop(x: torch.Tensor, p: float, training: bool) -> torch.Tensor:
+    return torch.nn.functional.dropout(x, p, True) if training and p > 0 else x
 
 
 def _mha(sa: nn.MultiheadAttention, x: torch.Tensor, attend) -> torch.Tensor:
+    """attend(qkv, p, seed) -> context; p = the module's attention-probability dropout when it is in train mode."""
     qkv = LinearFn.apply(x, sa.in_proj_weight, sa.in_proj_bias, "none")
-    return LinearFn.apply(attend(qkv), sa.out_proj.weight, sa.out_proj.bias, "none")
+    p = float(sa.dropout) if sa.training else 0.0
+    ctx = attend(qkv, p, _seed() if p > 0 else 0)
+    return LinearFn.apply(ctx, sa.out_proj.weight, sa.out_proj.bias, "none")
 
 
 def _ffn(layer, x: torch.Tensor) -> torch.Tensor:
+    p = float(layer.dropout.p) if layer.training else 0.0
+    if p > 0:          # dropout sits between the two projections: the fused pair does not apply
+        h = _drop(LinearFn.apply(x, layer.linear1.weight, layer.linear1.bias, "relu"), p, True)
+        return LinearFn.apply(h, layer.linear2.weight, layer.linear2.bias, "none")
     return FfnFn.apply(x, layer.linear1.weight, layer.linear1.bias, layer.linear2.weight, layer.linear2.bias)
 
 
 def fusion_layer_forward(layer, x: torch.Tensor, mask_delay: int = 0) -> torch.Tensor:
-    """The reference's attractor-decoder layer, live path ``FS:fusion:356-376`` (post-norm, dropout 0), differentiable.
+    """The reference's attractor-decoder layer, live path ``FS:fusion:356-376`` (post-norm), differentiable.
 
     x: [B, T, S, 256].  Time attention runs over [B*S, T, 256] (causal), speaker attention over [B*T, S, 256] (no mask);
-    ``norm12`` is unused, as in the reference.  The two layout changes are torch copies."""
+    ``norm12`` is unused, as in the reference.  The two layout changes are torch copies; in train mode the residual
+    dropouts (dropout11 / dropout21 / dropout2, ``:380-399``) are torch's, the attention-probability dropout is the
+    kernels' own (hash mask)."""
     B, T, S, D = x.shape
+    tr = layer.training
     y = x.transpose(1, 2).reshape(B * S, T, D)
-    y = AddLayerNormFn.apply(_mha(layer.self_attn1, y, lambda qkv: CausalAttnFn.apply(qkv, mask_delay)), y,
-                             layer.norm11.weight, layer.norm11.bias, layer.norm11.eps)
+    a = _mha(layer.self_attn1, y, lambda qkv, p, seed: CausalAttnFn.apply(qkv, mask_delay, p, seed))
+    y = AddLayerNormFn.apply(_drop(a, layer.dropout11.p, tr), y, layer.norm11.weight, layer.norm11.bias, layer.norm11.eps)
     y = y.reshape(B, S, T, D).transpose(1, 2).reshape(B * T, S, D)
-    y = AddLayerNormFn.apply(_mha(layer.self_attn2, y, SpeakerAttnFn.apply), y, layer.norm21.weight, layer.norm21.bias,
-                             layer.norm21.eps)
-    y = AddLayerNormFn.apply(_ffn(layer, y), y, layer.norm22.weight, layer.norm22.bias, layer.norm22.eps)
+    a = _mha(layer.self_attn2, y, lambda qkv, p, seed: SpeakerAttnFn.apply(qkv, p, seed))
+    y = AddLayerNormFn.apply(_drop(a, layer.dropout21.p, tr), y, layer.norm21.weight, layer.norm21.bias, layer.norm21.eps)
+    y = AddLayerNormFn.apply(_drop(_ffn(layer, y), layer.dropout2.p, tr), y, layer.norm22.weight, layer.norm22.bias,
+                             layer.norm22.eps)
     return y.reshape(B, T, S, D)
 
 
 def encoder_layer_forward(layer: nn.TransformerEncoderLayer, x: torch.Tensor, mask_delay: int = 0) -> torch.Tensor:
-    """The reference's post-norm encoder layer (``FS:model:147``; dropout 0) on native kernels, differentiable.
+    """The reference's post-norm encoder layer (``FS:model:147``) on native kernels, differentiable.
 
     x: [n_seq, T, 256] (batch-first; the reference runs (T, B, 256) — the math is per sequence, the layout is ours).
-    ``layer`` only provides the parameters (reference names: self_attn.in_proj_*, self_attn.out_proj, linear1/2, norm1/2).
-    """
+    ``layer`` only provides the parameters (reference names: self_attn.in_proj_*, self_attn.out_proj, linear1/2, norm1/2)
+    and the dropout probabilities (dropout1 / dropout / dropout2 and the attention's own)."""
     if layer.norm_first:
         raise FseendError("encoder_layer_forward: the reference layer is post-norm")
-    o = _mha(layer.self_attn, x, lambda qkv: CausalAttnFn.apply(qkv, mask_delay))
-    x = AddLayerNormFn.apply(o, x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
-    f = _ffn(layer, x)
+    tr = layer.training
+    o = _mha(layer.self_attn, x, lambda qkv, p, seed: CausalAttnFn.apply(qkv, mask_delay, p, seed))
+    x = AddLayerNormFn.apply(_drop(o, layer.dropout1.p, tr), x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
+    f = _drop(_ffn(layer, x), layer.dropout2.p, tr)
     return AddLayerNormFn.apply(f, x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)

@@ -8,8 +8,10 @@ What runs where (DESIGN.md §7 has the table):
   * torch CUDA ops (interim, small): BatchNorm1d with batch statistics, the layout changes between the (B*S, T) and
     (B*T, S) views, the two L2 normalisations, the dot-product head, the embedding-consistency loss, dropout masks on
     the residual branches.
-Attention-probability dropout (inside nn.MultiheadAttention) is not implemented: construct the model with dropout=0.0
-for training through this path (it raises otherwise).
+Dropout (reference recipes train with 0.1): the residual / FFN dropouts are torch's functional dropout on the native
+kernels' outputs; the attention-probability dropout inside nn.MultiheadAttention is implemented in the attention kernels
+themselves (counter-based hash of (seed, sequence, head, query, key); the backward regenerates the mask).  The random
+streams differ from torch's, the distribution does not.
 """
 from __future__ import annotations
 
@@ -19,14 +21,6 @@ from torch.nn.utils.rnn import pad_sequence
 
 from .autograd import AddLayerNormFn, LinearFn, encoder_layer_forward, fusion_layer_forward
 from .native import FseendError
-
-
-def _check_dropout(model):
-    for m in model.modules():
-        if isinstance(m, torch.nn.MultiheadAttention) and m.dropout > 0 and model.training:
-            raise NotImplementedError(
-                "fseend_b200 training path: attention-probability dropout is not implemented — build the model with "
-                "dropout=0.0 (SURVEY §8f N1 is started, not complete)")
 
 
 def _require_device(dev):
@@ -39,7 +33,6 @@ def fs_forward_train(model, src, tgt, ilens):
     enc, dec = model.enc, model.dec
     dev, dt = model.cnn.weight.device, model.cnn.weight.dtype
     _require_device(dev)
-    _check_dropout(model)
     lens = [int(l) for l in ilens]
     n_speakers = [t.shape[1] for t in tgt]
     S = max(n_speakers)

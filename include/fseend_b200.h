@@ -304,17 +304,23 @@ size_t fseend_train_layernorm_workspace_bytes(int rows);
 int fseend_train_layernorm_bwd(const float* x, const float* g, const float* dy, int rows, float eps, float* dx, float* dg,
                                float* db, void* workspace, size_t ws_bytes, void* stream);
 /* Causal 4-head self-attention on projected qkv fp32 [n_seq][T][768] -> out fp32 [n_seq][T][256]; key j is visible to
- * query i iff j <= i + mask_delay (FS model file :152-155); lse fp32 [n_seq][4][T] is saved for the backward. */
-int fseend_train_attn_fwd(const float* qkv, int n_seq, int T, int mask_delay, float* out, float* lse, void* stream);
+ * query i iff j <= i + mask_delay (FS model file :152-155); lse fp32 [n_seq][4][T] is saved for the backward.
+ * dropout_p / seed: attention-probability dropout (nn.MultiheadAttention's `dropout`, on the softmax output, kept
+ * elements scaled by 1/(1-p)); the mask is a counter-based hash of (seed, sequence, head, query, key), so the backward
+ * regenerates it from the same (dropout_p, seed).  dropout_p = 0 disables it. */
+int fseend_train_attn_fwd(const float* qkv, int n_seq, int T, int mask_delay, float dropout_p, unsigned long long seed,
+                          float* out, float* lse, void* stream);
 /* dqkv fp32 [n_seq][T][768] from dout [n_seq][T][256]; dsum: scratch fp32 [n_seq][4][T]. */
 int fseend_train_attn_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int n_seq, int T,
-                          int mask_delay, float* dqkv, float* dsum, void* stream);
-
+                          int mask_delay, float dropout_p, unsigned long long seed, float* dqkv, float* dsum,
+                          void* stream);
 /* Speaker-axis attention (FS-EEND/nnet/modules/transformer_encoder_fusion.py:390 self_attn2: S x S per frame, no mask)
  * on projected qkv fp32 [n_frames][S][768] -> out fp32 [n_frames][S][256]; S <= 16.  The backward recomputes the
- * probabilities: dqkv fp32 [n_frames][S][768] from dout [n_frames][S][256]. */
-int fseend_train_spk_attn_fwd(const float* qkv, int n_frames, int S, float* out, void* stream);
-int fseend_train_spk_attn_bwd(const float* qkv, const float* dout, int n_frames, int S, float* dqkv, void* stream);
+ * probabilities: dqkv fp32 [n_frames][S][768] from dout [n_frames][S][256].  Dropout as above. */
+int fseend_train_spk_attn_fwd(const float* qkv, int n_frames, int S, float dropout_p, unsigned long long seed, float* out,
+                              void* stream);
+int fseend_train_spk_attn_bwd(const float* qkv, const float* dout, int n_frames, int S, float dropout_p,
+                              unsigned long long seed, float* dqkv, void* stream);
 
 #ifdef __cplusplus
 }

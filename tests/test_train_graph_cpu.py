@@ -38,11 +38,11 @@ class _Ffn:
 
 
 class _Causal:
-    apply = staticmethod(_attn)
+    apply = staticmethod(lambda qkv, delay, p=0.0, seed=0: _attn(qkv, delay))
 
 
 class _Spk:
-    apply = staticmethod(lambda qkv: _attn(qkv, 1 << 20))
+    apply = staticmethod(lambda qkv, p=0.0, seed=0: _attn(qkv, 1 << 20))
 
 
 @pytest.mark.parametrize("mask_delay", [0, 2])

@@ -271,11 +271,100 @@ def test_training_step_reduces_loss(built_lib):
     assert max((a - b).abs().max().item() for a, b in zip(y0, y1)) > 1e-3
 
 
-def test_training_rejects_attention_dropout(built_lib):
+def keep_mask(seed, shape, p):
+    """The kernels' dropout hash (csrc/train_attn.cu drop_hash) in torch integer arithmetic: True = kept."""
+    import numpy as np
+    n = 1
+    for d in shape:
+        n *= d
+    M = 0xFFFFFFFF
+    idx = torch.arange(n, dtype=torch.int64)
+    x = (idx & M) ^ (seed & M)
+    x = (x * 0x9E3779B1) & M
+    x = x ^ (x >> 15)
+    x = (x + (idx >> 32) * 0x85EBCA77 + (seed >> 32)) & M
+    x = (x * 0xC2B2AE3D) & M
+    x = x ^ (x >> 13)
+    x = (x * 0x27D4EB2F) & M
+    x = x ^ (x >> 16)
+    thresh = min(2 ** 32 - 1, int(float(np.float32(p)) * 4294967296.0))
+    return (x >= thresh).reshape(shape)
+
+
+def ref_attention_dropout(qkv, delay, keep, p):
+    n, T, _ = qkv.shape
+    q, k, v = (t.reshape(n, T, 4, 64).transpose(1, 2) for t in qkv.split(256, dim=-1))
+    s = (q * 0.125) @ k.transpose(-1, -2)
+    i = torch.arange(T, device=qkv.device)
+    s = s.masked_fill(i[None, :] > i[:, None] + delay, float("-inf"))
+    pr = torch.softmax(s, -1) * keep.to(qkv) / (1 - float(torch.tensor(p, dtype=torch.float32)))
+    return (pr @ v).transpose(1, 2).reshape(n, T, 256)
+
+
+@pytest.mark.parametrize("n,T,delay,p", [(2, 200, 0, 0.1), (1, 70, 3, 0.5)])
+def test_causal_attention_dropout(built_lib, n, T, delay, p):
+    """Attention-probability dropout: forward and backward against a torch reference that applies the SAME mask
+    (regenerated from the seed by the hash above); the keep rate matches 1 - p."""
+    from fseend_b200.autograd import CausalAttnFn
+    seed = 0x1234567 + (T << 33)
+    g = torch.Generator().manual_seed(T)
+    qkv = (1.5 * torch.randn(n, T, 768, generator=g)).cuda().requires_grad_()
+    do = torch.randn(n, T, 256, generator=g).cuda()
+    o = CausalAttnFn.apply(qkv, delay, p, seed)
+    o.backward(do)
+    keep = keep_mask(seed, (n, 4, T, T), p).cuda()
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    qr = qkv.detach().double().requires_grad_()
+    orf = ref_attention_dropout(qr, delay, keep, p)
+    orf.backward(do.double())
+    close(o, orf, "out")
+    close(qkv.grad, qr.grad, "dqkv")
+    o0 = CausalAttnFn.apply(qkv.detach(), delay, 0.0, seed)
+    assert (o0 - o.detach()).abs().max() > 1e-3            # dropout did change the output
+
+
+@pytest.mark.parametrize("n,S,p", [(300, 6, 0.1), (33, 10, 0.4)])
+def test_speaker_attention_dropout(built_lib, n, S, p):
+    from fseend_b200.autograd import SpeakerAttnFn
+    seed = 987654321012345
+    g = torch.Generator().manual_seed(n)
+    qkv = (1.5 * torch.randn(n, S, 768, generator=g)).cuda().requires_grad_()
+    do = torch.randn(n, S, 256, generator=g).cuda()
+    o = SpeakerAttnFn.apply(qkv, p, seed)
+    o.backward(do)
+    keep = keep_mask(seed, (n, 4, S, S), p).cuda()
+    qr = qkv.detach().double().requires_grad_()
+    orf = ref_attention_dropout(qr, S, keep, p)
+    orf.backward(do.double())
+    close(o, orf, "out")
+    close(qkv.grad, qr.grad, "dqkv")
+
+
+def test_training_with_reference_dropout(built_lib):
+    """The reference recipes train with dropout 0.1: the step runs, is reproducible under torch.manual_seed, differs
+    between seeds, and eval mode is unaffected."""
+    from fseend_b200.loss import standard_loss
     from oracle import fs_eend_oracle as O
     from nnet.model.onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import OnlineTransformerDADiarization
+    sd = O.random_state_dict(seed=4, enc_n_layers=1, dec_n_layers=1, trained_like=False)
     m = OnlineTransformerDADiarization(n_speakers=4, in_size=345, n_units=256, n_heads=4, enc_n_layers=1, dec_n_layers=1,
-                                       dropout=0.1, has_mask=True, max_seqlen=500, dec_dim_feedforward=2048).cuda().train()
-    src = [torch.randn(50, 345).cuda()]
-    with pytest.raises(NotImplementedError):
-        m(src, [torch.zeros(50, 2).cuda()], [50])
+                                       dropout=0.1, has_mask=True, max_seqlen=500, dec_dim_feedforward=2048)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    lens = [120, 90]
+    src = [s.cuda() for s in O.synthetic_features(2, 120, seed=8, lens=lens)[0]]
+    tgt = [(torch.rand(l, 3) < 0.3).float().cuda() for l in lens]
+
+    def run(seed):
+        torch.manual_seed(seed)
+        m.zero_grad()
+        out, emb_loss, _, _ = m(src, tgt, lens)
+        loss = standard_loss(out, tgt) + emb_loss
+        loss.backward()
+        return loss.item(), m.enc.encoder.weight.grad.clone()
+
+    l1, g1 = run(1)
+    l2, g2 = run(1)
+    l3, g3 = run(2)
+    assert l1 == l2 and torch.equal(g1, g2)
+    assert l1 != l3 and torch.isfinite(g3).all()

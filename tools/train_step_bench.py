@@ -49,11 +49,11 @@ class _Ffn:
 
 
 class _Causal:
-    apply = staticmethod(_attn)
+    apply = staticmethod(lambda qkv, delay, p=0.0, seed=0: _attn(qkv, delay))
 
 
 class _Spk:
-    apply = staticmethod(lambda qkv: _attn(qkv, 1 << 20))
+    apply = staticmethod(lambda qkv, p=0.0, seed=0: _attn(qkv, 1 << 20))
 
 
 def timed(fn, steps, warmup):
@@ -69,15 +69,8 @@ def timed(fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--frames", type=int, default=500)
-    ap.add_argument("--speakers", type=int, default=4)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--native-only", action="store_true")
-    a = ap.parse_args()
+def measure(batch=64, frames=500, speakers=4, steps=5, warmup=2, native_only=False):
+    """Returns the result dict (None with native_only: one native step for profilers)."""
     import fseend_b200.autograd as A
     import fseend_b200.train_graph as G
     from fseend_b200.loss import standard_loss
@@ -86,7 +79,7 @@ def main():
     m = OnlineTransformerDADiarization(n_speakers=4, in_size=345, n_units=256, n_heads=4, enc_n_layers=4, dec_n_layers=2,
                                        dropout=0.0, has_mask=True, max_seqlen=500, dec_dim_feedforward=2048).cuda().train()
     opt = torch.optim.Adam(m.parameters(), lr=1e-5)
-    B, T, S = a.batch, a.frames, a.speakers
+    B, T, S = batch, frames, speakers
     src = [torch.randn(T, 345, device="cuda") for _ in range(B)]
     tgt = [(torch.rand(T, S, device="cuda") < 0.3).float() for _ in range(B)]
     # the labels the training step hands to model / loss carry silence + "no speaker" columns: S + 2 classes
@@ -102,14 +95,16 @@ def main():
         opt.step()
         last["loss"] = loss
 
-    if a.native_only:
+    if native_only:
         step()
         torch.cuda.synchronize()
-        return
+        return None
+    tf32_was = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     state0 = {k: v.clone() for k, v in m.state_dict().items()}
-    t_native = timed(step, a.steps, a.warmup)
+    torch.cuda.reset_peak_memory_stats()
+    t_native = timed(step, steps, warmup)
     loss_native = last["loss"].item()
     peak_native = torch.cuda.max_memory_allocated() / 2**30
     # torch eager arm: same graph, stand-in ops
@@ -119,22 +114,43 @@ def main():
         mod.LinearFn, mod.AddLayerNormFn = _Lin, _AddLn
     A.CausalAttnFn, A.SpeakerAttnFn, A.FfnFn = _Causal, _Spk, _Ffn
     res = {}
-    for name, tf32 in (("torch_fp32", False), ("torch_tf32", True)):
-        m.load_state_dict(state0)
-        opt.state.clear()
-        torch.backends.cuda.matmul.allow_tf32 = tf32
-        torch.backends.cudnn.allow_tf32 = tf32
-        res[name] = timed(step, a.steps, a.warmup)
-        res[name + "_loss"] = last["loss"].item()
-    for (mod, n), v in saved.items():
-        setattr(mod, n, v)
-    frames = B * T
-    print(json.dumps({"what": "FS-EEND training step (fwd + loss + bwd + Adam)", "batch": B, "frames": T, "label_classes": S + 2,
-                      "native_ms": round(t_native, 2), "torch_fp32_ms": round(res["torch_fp32"], 2),
-                      "torch_tf32_ms": round(res["torch_tf32"], 2), "native_frames_per_s": round(frames / t_native * 1e3),
-                      "loss_after_steps": {"native": loss_native, "torch_fp32": res["torch_fp32_loss"],
-                                           "torch_tf32": res["torch_tf32_loss"]},
-                      "native_peak_mem_gib": round(peak_native, 2)}))
+    try:
+        for name, tf32 in (("torch_fp32", False), ("torch_tf32", True)):
+            m.load_state_dict(state0)
+            opt.state.clear()
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            res[name] = timed(step, steps, warmup)
+            res[name + "_loss"] = last["loss"].item()
+    finally:
+        for (mod, n), v in saved.items():
+            setattr(mod, n, v)
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32_was
+    n_frames = B * T
+    return {"workload": f"FS-EEND training step: fwd + standard_loss + emb loss + bwd + Adam, B={B} x T={T}, {S + 2} label classes, "
+                        "4 enc + 2 dec layers, dropout 0",
+            "status": "SURVEY 8f N1 STARTED: GEMMs / attention / LayerNorm forward+backward are this library's kernels; "
+                      "BatchNorm, L2 norms, head, emb loss, optimizer are torch ops",
+            "native_ms": round(t_native, 2), "native_frames_per_s": round(n_frames / t_native * 1e3),
+            "torch_eager_fp32_ms": round(res["torch_fp32"], 2), "torch_eager_tf32_ms": round(res["torch_tf32"], 2),
+            "loss_after_%d_steps" % (steps + warmup): {"native": loss_native, "torch_fp32": res["torch_fp32_loss"],
+                                                        "torch_tf32": res["torch_tf32_loss"]},
+            "native_peak_mem_gib": round(peak_native, 2),
+            "torch_arm": "same graph with F.linear / F.layer_norm / SDPA (what nn.TransformerEncoderLayer executes), same GPU"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=500)
+    ap.add_argument("--speakers", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--native-only", action="store_true")
+    a = ap.parse_args()
+    r = measure(a.batch, a.frames, a.speakers, a.steps, a.warmup, a.native_only)
+    if r is not None:
+        print(json.dumps(r))
 
 
 if __name__ == "__main__":
