@@ -11,8 +11,10 @@
 // inside a half-warp).  Backward is the standard recomputation form in two kernels (no atomics, fixed summation order):
 //   dq kernel  per query tile:  D = rowsum(dO * O);  for key tiles: P = exp(S - lse); dS = P (dO V^T - D) scale; dQ += dS K
 //   dkv kernel per key tile:    for query tiles:     dV += P^T dO;  dK += dS^T Q
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include <algorithm>
@@ -304,6 +306,8 @@ train_attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict
   }
 }
 
+#include "train_attn_tc.cuh"
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Speaker-axis attention backward (FS:fusion:390 self_attn2: S x S attention per frame, no mask).  One warp per
 // (frame, head): q / k / v / dO rows [S][64] staged in shared memory (row stride 65), the S x S probabilities and score
@@ -473,9 +477,37 @@ void set_attrs() {
     cudaFuncSetAttribute(train_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kTile * 4);
     cudaFuncSetAttribute(train_attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * kTile * 4);
     cudaFuncSetAttribute(train_attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * kTile * 4);
+    cudaFuncSetAttribute(tc::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kFwdSmem);
+    cudaFuncSetAttribute(tc::attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kDqSmem);
+    cudaFuncSetAttribute(tc::attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kDkvSmem);
     cudaFuncSetAttribute(train_spk_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSpkWarpFloats * 4);
     cudaFuncSetAttribute(train_spk_attn_fwd_drop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSpkWarpFloats * 4);
   }
+}
+// max |x| -> power-of-two scale (the gradient-scaling rule of train_ops.cu, target [16, 32): dP = dO V^T must stay inside
+// the fp16 range after the multiplication)
+__global__ void __launch_bounds__(256) attn_absmax_kernel(const float* __restrict__ x, size_t n4, unsigned int* __restrict__ slot) {
+  float m = 0.f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+}
+__global__ void attn_make_scale_kernel(const unsigned int* __restrict__ slot, float* __restrict__ sc) {
+  const float m = __uint_as_float(*slot);
+  float s = 1.f;
+  if (m > 0.f && m < 3e38f) s = exp2f(static_cast<float>(max(-100, min(100, 4 - ilogbf(m)))));
+  sc[0] = s;
+  sc[1] = 1.f / s;
+}
+
+// FSEEND_TRAIN_ATTN=0 selects the CUDA-core kernels (read per call: the tests run both)
+bool use_tensor_cores() {
+  const char* e = getenv("FSEEND_TRAIN_ATTN");
+  return !(e && e[0] == '0');
 }
 Dropout make_dropout(float p, unsigned long long seed) {
   if (!(p >= 0.f && p < 1.f)) throw std::invalid_argument("dropout probability must be in [0, 1)");
@@ -500,13 +532,17 @@ int fseend_train_attn_fwd(const float* qkv, int n_seq, int T, int mask_delay, fl
     if (!qkv || !out || !lse || n_seq < 1 || T < 1 || mask_delay < 0 || n_seq > 65535)
       throw std::invalid_argument("train_attn_fwd: bad arguments");
     set_attrs();
-    train_attn_fwd_kernel<<<dim3((T + 63) / 64, kHeads, n_seq), 256, 4 * kTile * 4, static_cast<cudaStream_t>(stream)>>>(
-        qkv, out, lse, T, mask_delay, 0.125f, make_dropout(dropout_p, seed));
+    const dim3 grid((T + 63) / 64, kHeads, n_seq);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (use_tensor_cores())
+      tc::attn_fwd_kernel<<<grid, 128, tc::kFwdSmem, st>>>(qkv, out, lse, T, mask_delay, 0.125f, make_dropout(dropout_p, seed));
+    else
+      train_attn_fwd_kernel<<<grid, 256, 4 * kTile * 4, st>>>(qkv, out, lse, T, mask_delay, 0.125f, make_dropout(dropout_p, seed));
     check_launch("train_attn_fwd");
   });
 }
 
-// dsum: scratch fp32 [n_seq][4][T]
+// dsum: scratch fp32 [n_seq][4][T] + 16 floats (row sums of dO * O; the gradient-scale slot behind them)
 int fseend_train_attn_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int n_seq, int T,
                           int mask_delay, float dropout_p, unsigned long long seed, float* dqkv, float* dsum, void* stream) {
   return aguard([&] {
@@ -516,8 +552,18 @@ int fseend_train_attn_bwd(const float* qkv, const float* out, const float* dout,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const dim3 grid((T + 63) / 64, kHeads, n_seq);
     const Dropout drop = make_dropout(dropout_p, seed);
-    train_attn_bwd_dq_kernel<<<grid, 256, 5 * kTile * 4, st>>>(qkv, out, dout, lse, dqkv, dsum, T, mask_delay, 0.125f, drop);
-    train_attn_bwd_dkv_kernel<<<grid, 256, 6 * kTile * 4, st>>>(qkv, dout, lse, dsum, dqkv, T, mask_delay, 0.125f, drop);
+    if (use_tensor_cores()) {
+      unsigned int* slot = reinterpret_cast<unsigned int*>(dsum + static_cast<size_t>(n_seq) * kHeads * T);
+      float* gsc = reinterpret_cast<float*>(slot) + 4;
+      if (cudaMemsetAsync(slot, 0, 4, st) != cudaSuccess) throw std::runtime_error("train_attn_bwd: memset failed");
+      attn_absmax_kernel<<<592, 256, 0, st>>>(dout, static_cast<size_t>(n_seq) * T * 64, slot);
+      attn_make_scale_kernel<<<1, 1, 0, st>>>(slot, gsc);
+      tc::attn_bwd_dq_kernel<<<grid, 128, tc::kDqSmem, st>>>(qkv, out, dout, lse, dqkv, dsum, T, mask_delay, 0.125f, drop, gsc);
+      tc::attn_bwd_dkv_kernel<<<grid, 128, tc::kDkvSmem, st>>>(qkv, dout, lse, dsum, dqkv, T, mask_delay, 0.125f, drop, gsc);
+    } else {
+      train_attn_bwd_dq_kernel<<<grid, 256, 5 * kTile * 4, st>>>(qkv, out, dout, lse, dqkv, dsum, T, mask_delay, 0.125f, drop);
+      train_attn_bwd_dkv_kernel<<<grid, 256, 6 * kTile * 4, st>>>(qkv, dout, lse, dsum, dqkv, T, mask_delay, 0.125f, drop);
+    }
     check_launch("train_attn_bwd");
   });
 }

@@ -182,7 +182,7 @@ class CausalAttnFn(torch.autograd.Function):
         n, T, _ = qkv.shape
         dout = _f32c(dout, "CausalAttnFn dout")
         dqkv = torch.empty_like(qkv)
-        dsum = torch.empty_like(lse)
+        dsum = torch.empty(lse.numel() + 16, device=lse.device, dtype=torch.float32)
         with torch.cuda.device(qkv.device):
             _check(lib().fseend_train_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), n, T, ctx.delay, ctx.p, ctx.seed,
                                                _ptr(dqkv), _ptr(dsum), _stream()))

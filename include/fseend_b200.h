@@ -310,7 +310,7 @@ int fseend_train_layernorm_bwd(const float* x, const float* g, const float* dy, 
  * regenerates it from the same (dropout_p, seed).  dropout_p = 0 disables it. */
 int fseend_train_attn_fwd(const float* qkv, int n_seq, int T, int mask_delay, float dropout_p, unsigned long long seed,
                           float* out, float* lse, void* stream);
-/* dqkv fp32 [n_seq][T][768] from dout [n_seq][T][256]; dsum: scratch fp32 [n_seq][4][T]. */
+/* dqkv fp32 [n_seq][T][768] from dout [n_seq][T][256]; dsum: scratch fp32 [n_seq * 4 * T + 16]. */
 int fseend_train_attn_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int n_seq, int T,
                           int mask_delay, float dropout_p, unsigned long long seed, float* dqkv, float* dsum,
                           void* stream);

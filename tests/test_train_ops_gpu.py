@@ -113,9 +113,12 @@ def ref_attention(qkv, delay):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(n, T, 256)
 
 
+@pytest.mark.parametrize("kernels", ["tensor", "cuda_core"])
 @pytest.mark.parametrize("n,T,delay", [(3, 500, 0), (2, 130, 3), (1, 64, 0), (2, 1, 0), (1, 257, 70)])
-def test_causal_attention_fwd_bwd(built_lib, n, T, delay):
+def test_causal_attention_fwd_bwd(built_lib, monkeypatch, n, T, delay, kernels):
+    """Both kernel families: mma.sync split-precision (default) and the fp32 CUDA-core form (FSEEND_TRAIN_ATTN=0)."""
     from fseend_b200.autograd import CausalAttnFn
+    monkeypatch.setenv("FSEEND_TRAIN_ATTN", "1" if kernels == "tensor" else "0")
     g = torch.Generator().manual_seed(n * 1000 + T)
     qkv = (1.5 * torch.randn(n, T, 768, generator=g)).cuda().requires_grad_()
     do = torch.randn(n, T, 256, generator=g).cuda()
@@ -301,11 +304,26 @@ def ref_attention_dropout(qkv, delay, keep, p):
     return (pr @ v).transpose(1, 2).reshape(n, T, 256)
 
 
+def test_causal_attention_tiny_gradients(built_lib):
+    """Upstream gradients as the training loss produces them (1e-7, far below the fp16 normal range): the tensor-core
+    backward rescales dO by a power of two before the operand split."""
+    from fseend_b200.autograd import CausalAttnFn
+    g = torch.Generator().manual_seed(77)
+    qkv = (1.5 * torch.randn(2, 300, 768, generator=g)).cuda().requires_grad_()
+    do = (1e-7 * torch.randn(2, 300, 256, generator=g) * torch.rand(2, 300, 1, generator=g) ** 4).cuda()
+    CausalAttnFn.apply(qkv, 0).backward(do)
+    qr = qkv.detach().double().requires_grad_()
+    ref_attention(qr, 0).backward(do.double())
+    close(qkv.grad, qr.grad, "dqkv")
+
+
+@pytest.mark.parametrize("kernels", ["tensor", "cuda_core"])
 @pytest.mark.parametrize("n,T,delay,p", [(2, 200, 0, 0.1), (1, 70, 3, 0.5)])
-def test_causal_attention_dropout(built_lib, n, T, delay, p):
+def test_causal_attention_dropout(built_lib, monkeypatch, n, T, delay, p, kernels):
     """Attention-probability dropout: forward and backward against a torch reference that applies the SAME mask
     (regenerated from the seed by the hash above); the keep rate matches 1 - p."""
     from fseend_b200.autograd import CausalAttnFn
+    monkeypatch.setenv("FSEEND_TRAIN_ATTN", "1" if kernels == "tensor" else "0")
     seed = 0x1234567 + (T << 33)
     g = torch.Generator().manual_seed(T)
     qkv = (1.5 * torch.randn(n, T, 768, generator=g)).cuda().requires_grad_()
