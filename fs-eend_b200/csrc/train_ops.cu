@@ -175,21 +175,35 @@ colsum_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, 
   const int c = blockIdx.y * 256 + threadIdx.x;
   if (c >= C) return;
   const int r0 = blockIdx.x * kRowsPerBlk, r1 = min(R, r0 + kRowsPerBlk);
-  float s = 0.f;
-  for (int r = r0; r < r1; ++r) {
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};        // four independent chains (rows r, r+1, r+2, r+3), combined in fixed order
+  auto term = [&](int r) {
     float v = a[static_cast<size_t>(r) * C + c];
     if (mask && mask[static_cast<size_t>(r) * C + c] <= 0.f) v = 0.f;
-    s += b ? v * b[static_cast<size_t>(r) * C + c] : v;
+    return b ? v * b[static_cast<size_t>(r) * C + c] : v;
+  };
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s4[j] += term(r + j);
   }
-  partial[static_cast<size_t>(blockIdx.x) * C + c] = s;
+  for (; r < r1; ++r) s4[0] += term(r);
+  partial[static_cast<size_t>(blockIdx.x) * C + c] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
 }
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int n_blk, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= C) return;
+  // 32 columns per block, 8 interleaved groups of partial rows per column, combined in fixed order (deterministic)
+  __shared__ double sm[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int k = 0; k < n_blk; ++k) s += static_cast<double>(partial[static_cast<size_t>(k) * C + c]);
-  out[c] = static_cast<float>(s);
+  if (c < C)
+    for (int k = grp; k < n_blk; k += 8) s += static_cast<double>(partial[static_cast<size_t>(k) * C + c]);
+  sm[grp][lane] = s;
+  __syncthreads();
+  if (grp == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) s += sm[j][lane];
+    out[c] = static_cast<float>(s);
+  }
 }
 
 // out = dy where y > 0 else 0   (ReLU backward on the saved output; only the stand-alone Linear(+ReLU) backward needs it —
@@ -439,7 +453,7 @@ int fseend_train_linear_bwd(const float* x, const float* w, const float* y, cons
     if (db) {
       const int nb = (rows + kRowsPerBlk - 1) / kRowsPerBlk;
       colsum_partial_kernel<<<dim3(nb, (N + 255) / 256), 256, 0, st>>>(dy, nullptr, nullptr, rows, N, part);
-      colsum_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(part, nb, N, db);
+      colsum_final_kernel<<<(N + 31) / 32, 256, 0, st>>>(part, nb, N, db);
     }
     if (dx) {
       // W^T planes [Kp][N] (rows >= K zero): one slice of N "rows"
@@ -531,9 +545,9 @@ int fseend_train_layernorm_bwd(const float* x, const float* g, const float* dy, 
     ln_bwd_row_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, g, dy, rows, eps, dx, xhat);
     const int nb = (rows + kRowsPerBlk - 1) / kRowsPerBlk;
     colsum_partial_kernel<<<dim3(nb, 1), 256, 0, st>>>(dy, xhat, nullptr, rows, 256, part);
-    colsum_final_kernel<<<1, 256, 0, st>>>(part, nb, 256, dg);
+    colsum_final_kernel<<<8, 256, 0, st>>>(part, nb, 256, dg);
     colsum_partial_kernel<<<dim3(nb, 1), 256, 0, st>>>(dy, nullptr, nullptr, rows, 256, part);
-    colsum_final_kernel<<<1, 256, 0, st>>>(part, nb, 256, db);
+    colsum_final_kernel<<<8, 256, 0, st>>>(part, nb, 256, db);
     TCHECK(cudaGetLastError());
   });
 }
