@@ -304,6 +304,163 @@ ln_fwd_row_kernel(const float* __restrict__ x, const float* __restrict__ r, cons
                                                               (v[6] - mean) * rstd * g1.z + b1.z, (v[7] - mean) * rstd * g1.w + b1.w);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// L2 normalisation of rows of 256 (FS:model:41,43: emb / ||emb||, attractors / ||attractors||; no eps, as the reference)
+// forward: y = x / ||x||, inv[row] = 1 / ||x||;  backward: dx = (dy - y (y . dy)) * inv
+__global__ void __launch_bounds__(256)
+l2norm_fwd_kernel(const float* __restrict__ x, int rows, float* __restrict__ y, float* __restrict__ inv) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xp = reinterpret_cast<const float4*>(x) + static_cast<size_t>(row) * 64;
+  const float4 a = xp[lane], b = xp[32 + lane];
+  float s = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float r = 1.f / sqrtf(s);
+  float4* yp = reinterpret_cast<float4*>(y) + static_cast<size_t>(row) * 64;
+  yp[lane] = make_float4(a.x * r, a.y * r, a.z * r, a.w * r);
+  yp[32 + lane] = make_float4(b.x * r, b.y * r, b.z * r, b.w * r);
+  if (lane == 0) inv[row] = r;
+}
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(const float* __restrict__ y, const float* __restrict__ inv, const float* __restrict__ dy, int rows,
+                  float* __restrict__ dx) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* yp = reinterpret_cast<const float4*>(y) + static_cast<size_t>(row) * 64;
+  const float4* dp = reinterpret_cast<const float4*>(dy) + static_cast<size_t>(row) * 64;
+  const float4 a = yp[lane], b = yp[32 + lane], da = dp[lane], db = dp[32 + lane];
+  float s = a.x * da.x + a.y * da.y + a.z * da.z + a.w * da.w + b.x * db.x + b.y * db.y + b.z * db.z + b.w * db.w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float r = inv[row];
+  float4* op = reinterpret_cast<float4*>(dx) + static_cast<size_t>(row) * 64;
+  op[lane] = make_float4((da.x - a.x * s) * r, (da.y - a.y * s) * r, (da.z - a.z * s) * r, (da.w - a.w * s) * r);
+  op[32 + lane] = make_float4((db.x - b.x * s) * r, (db.y - b.y * s) * r, (db.z - b.z * s) * r, (db.w - b.w * s) * r);
+}
+
+// Dot-product head (FS:model:60): y[f][s] = emb[f][:] . att[f][s][:], one warp per frame f.
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float* __restrict__ emb, const float* __restrict__ att, int frames, int S, float* __restrict__ y) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (f >= frames) return;
+  const float4* ep = reinterpret_cast<const float4*>(emb) + static_cast<size_t>(f) * 64;
+  const float4 a = ep[lane], b = ep[32 + lane];
+  for (int s = 0; s < S; ++s) {
+    const float4* ap = reinterpret_cast<const float4*>(att) + (static_cast<size_t>(f) * S + s) * 64;
+    const float4 c = ap[lane], d = ap[32 + lane];
+    float v = a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w + b.x * d.x + b.y * d.y + b.z * d.z + b.w * d.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) y[static_cast<size_t>(f) * S + s] = v;
+  }
+}
+// demb[f][:] = sum_s dy[f][s] att[f][s][:];  datt[f][s][:] = dy[f][s] emb[f][:]
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ emb, const float* __restrict__ att, const float* __restrict__ dy, int frames, int S,
+                float* __restrict__ demb, float* __restrict__ datt) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (f >= frames) return;
+  const float4* ep = reinterpret_cast<const float4*>(emb) + static_cast<size_t>(f) * 64;
+  const float4 a = ep[lane], b = ep[32 + lane];
+  float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+  for (int s = 0; s < S; ++s) {
+    const float g = dy[static_cast<size_t>(f) * S + s];
+    const float4* ap = reinterpret_cast<const float4*>(att) + (static_cast<size_t>(f) * S + s) * 64;
+    const float4 c = ap[lane], d = ap[32 + lane];
+    ga.x = fmaf(g, c.x, ga.x); ga.y = fmaf(g, c.y, ga.y); ga.z = fmaf(g, c.z, ga.z); ga.w = fmaf(g, c.w, ga.w);
+    gb.x = fmaf(g, d.x, gb.x); gb.y = fmaf(g, d.y, gb.y); gb.z = fmaf(g, d.z, gb.z); gb.w = fmaf(g, d.w, gb.w);
+    float4* op = reinterpret_cast<float4*>(datt) + (static_cast<size_t>(f) * S + s) * 64;
+    op[lane] = make_float4(g * a.x, g * a.y, g * a.z, g * a.w);
+    op[32 + lane] = make_float4(g * b.x, g * b.y, g * b.z, g * b.w);
+  }
+  float4* dp = reinterpret_cast<float4*>(demb) + static_cast<size_t>(f) * 64;
+  dp[lane] = ga;
+  dp[32 + lane] = gb;
+}
+
+// BatchNorm1d over the rows of x [rows][C] in training mode (FS:model:166 on the -1-padded batch): batch mean and
+// biased variance per feature from two-stage fixed-order column sums (second stage in double), then
+//   y = (x - mean) * rstd * gamma + beta          dx = gamma * rstd * (dy - mean(dy) - xhat * mean(dy * xhat))
+// stats[0..C) = mean, stats[C..2C) = biased variance (the caller updates the running statistics from them).
+__global__ void __launch_bounds__(256)
+bn_colstat_partial_kernel(const float* __restrict__ x, int R, int C, float* __restrict__ p1, float* __restrict__ p2) {
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= C) return;
+  const int r0 = blockIdx.x * kRowsPerBlk, r1 = min(R, r0 + kRowsPerBlk);
+  float s = 0.f, q = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float v = x[static_cast<size_t>(r) * C + c];
+    s += v;
+    q = fmaf(v, v, q);
+  }
+  p1[static_cast<size_t>(blockIdx.x) * C + c] = s;
+  p2[static_cast<size_t>(blockIdx.x) * C + c] = q;
+}
+__global__ void __launch_bounds__(256)
+bn_stat_final_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int n_blk, int R, int C, float* __restrict__ stats) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < n_blk; ++k) {
+    s += static_cast<double>(p1[static_cast<size_t>(k) * C + c]);
+    q += static_cast<double>(p2[static_cast<size_t>(k) * C + c]);
+  }
+  const double mean = s / R;
+  stats[c] = static_cast<float>(mean);
+  stats[C + c] = static_cast<float>(fmax(q / R - mean * mean, 0.0));
+}
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ g,
+                const float* __restrict__ b, size_t n, int C, float eps, float* __restrict__ y) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  y[i] = (x[i] - stats[c]) * (1.f / sqrtf(stats[C + c] + eps)) * g[c] + b[c];
+}
+// sums[0..C) = colsum(dy), sums[C..2C) = colsum(dy * xhat) (xhat recomputed from x and the saved statistics)
+__global__ void __launch_bounds__(256)
+bn_bwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ stats, int R, int C,
+                      float eps, float* __restrict__ p1, float* __restrict__ p2) {
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= C) return;
+  const float mean = stats[c], rstd = 1.f / sqrtf(stats[C + c] + eps);
+  const int r0 = blockIdx.x * kRowsPerBlk, r1 = min(R, r0 + kRowsPerBlk);
+  float s = 0.f, q = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float d = dy[static_cast<size_t>(r) * C + c];
+    s += d;
+    q = fmaf(d, (x[static_cast<size_t>(r) * C + c] - mean) * rstd, q);
+  }
+  p1[static_cast<size_t>(blockIdx.x) * C + c] = s;
+  p2[static_cast<size_t>(blockIdx.x) * C + c] = q;
+}
+__global__ void __launch_bounds__(256)
+bn_bwd_final_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int n_blk, int C, float* __restrict__ db,
+                    float* __restrict__ dg) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < n_blk; ++k) {
+    s += static_cast<double>(p1[static_cast<size_t>(k) * C + c]);
+    q += static_cast<double>(p2[static_cast<size_t>(k) * C + c]);
+  }
+  db[c] = static_cast<float>(s);
+  dg[c] = static_cast<float>(q);
+}
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ stats,
+                    const float* __restrict__ g, const float* __restrict__ db, const float* __restrict__ dg, size_t n, int R,
+                    int C, float eps, float* __restrict__ dx) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  const float rstd = 1.f / sqrtf(stats[C + c] + eps);
+  const float xhat = (x[i] - stats[c]) * rstd;
+  const float invR = 1.f / static_cast<float>(R);
+  dx[i] = g[c] * rstd * (dy[i] - db[c] * invR - xhat * dg[c] * invR);
+}
+
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 inline int pad64(int x) { return (x + 63) / 64 * 64; }
 inline int pad128(int x) { return (x + 127) / 128 * 128; }
@@ -548,6 +705,74 @@ int fseend_train_layernorm_bwd(const float* x, const float* g, const float* dy, 
     colsum_final_kernel<<<8, 256, 0, st>>>(part, nb, 256, dg);
     colsum_partial_kernel<<<dim3(nb, 1), 256, 0, st>>>(dy, nullptr, nullptr, rows, 256, part);
     colsum_final_kernel<<<8, 256, 0, st>>>(part, nb, 256, db);
+    TCHECK(cudaGetLastError());
+  });
+}
+
+// ---- L2 normalisation, head, BatchNorm (training)
+int fseend_train_l2norm_fwd(const float* x, int rows, float* y, float* inv_norm, void* stream) {
+  return tguard([&] {
+    if (!x || !y || !inv_norm || rows < 1) throw std::invalid_argument("l2norm_fwd: bad arguments");
+    l2norm_fwd_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, y, inv_norm);
+    TCHECK(cudaGetLastError());
+  });
+}
+int fseend_train_l2norm_bwd(const float* y, const float* inv_norm, const float* dy, int rows, float* dx, void* stream) {
+  return tguard([&] {
+    if (!y || !inv_norm || !dy || !dx || rows < 1) throw std::invalid_argument("l2norm_bwd: bad arguments");
+    l2norm_bwd_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, inv_norm, dy, rows, dx);
+    TCHECK(cudaGetLastError());
+  });
+}
+int fseend_train_head_fwd(const float* emb, const float* att, int frames, int S, float* y, void* stream) {
+  return tguard([&] {
+    if (!emb || !att || !y || frames < 1 || S < 1) throw std::invalid_argument("head_fwd: bad arguments");
+    head_fwd_kernel<<<(frames + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(emb, att, frames, S, y);
+    TCHECK(cudaGetLastError());
+  });
+}
+int fseend_train_head_bwd(const float* emb, const float* att, const float* dy, int frames, int S, float* demb, float* datt,
+                          void* stream) {
+  return tguard([&] {
+    if (!emb || !att || !dy || !demb || !datt || frames < 1 || S < 1) throw std::invalid_argument("head_bwd: bad arguments");
+    head_bwd_kernel<<<(frames + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(emb, att, dy, frames, S, demb, datt);
+    TCHECK(cudaGetLastError());
+  });
+}
+size_t fseend_train_batchnorm_workspace_bytes(int rows, int C) {
+  return 2 * align256((static_cast<size_t>(rows) / kRowsPerBlk + 1) * C * 4) + 1024;
+}
+// y = BatchNorm(x) with batch statistics; stats [2 * C] receives mean | biased variance
+int fseend_train_batchnorm_fwd(const float* x, const float* g, const float* b, int rows, int C, float eps, float* y,
+                               float* stats, void* workspace, size_t ws_bytes, void* stream) {
+  return tguard([&] {
+    if (!x || !g || !b || !y || !stats || !workspace || rows < 1 || C < 1) throw std::invalid_argument("batchnorm_fwd: bad arguments");
+    if (ws_bytes < fseend_train_batchnorm_workspace_bytes(rows, C)) throw std::invalid_argument("batchnorm_fwd: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nb = (rows + kRowsPerBlk - 1) / kRowsPerBlk;
+    float* p1 = static_cast<float*>(workspace);
+    float* p2 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align256(static_cast<size_t>(nb) * C * 4));
+    bn_colstat_partial_kernel<<<dim3(nb, (C + 255) / 256), 256, 0, st>>>(x, rows, C, p1, p2);
+    bn_stat_final_kernel<<<(C + 255) / 256, 256, 0, st>>>(p1, p2, nb, rows, C, stats);
+    const size_t n = static_cast<size_t>(rows) * C;
+    bn_apply_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, stats, g, b, n, C, eps, y);
+    TCHECK(cudaGetLastError());
+  });
+}
+int fseend_train_batchnorm_bwd(const float* x, const float* g, const float* stats, const float* dy, int rows, int C, float eps,
+                               float* dx, float* dg, float* db, void* workspace, size_t ws_bytes, void* stream) {
+  return tguard([&] {
+    if (!x || !g || !stats || !dy || !dg || !db || !workspace || rows < 1 || C < 1)      // dx may be null (input features)
+      throw std::invalid_argument("batchnorm_bwd: bad arguments");
+    if (ws_bytes < fseend_train_batchnorm_workspace_bytes(rows, C)) throw std::invalid_argument("batchnorm_bwd: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nb = (rows + kRowsPerBlk - 1) / kRowsPerBlk;
+    float* p1 = static_cast<float*>(workspace);
+    float* p2 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align256(static_cast<size_t>(nb) * C * 4));
+    bn_bwd_partial_kernel<<<dim3(nb, (C + 255) / 256), 256, 0, st>>>(x, dy, stats, rows, C, eps, p1, p2);
+    bn_bwd_final_kernel<<<(C + 255) / 256, 256, 0, st>>>(p1, p2, nb, C, db, dg);
+    const size_t n = static_cast<size_t>(rows) * C;
+    if (dx) bn_bwd_apply_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, dy, stats, g, db, dg, n, rows, C, eps, dx);
     TCHECK(cudaGetLastError());
   });
 }

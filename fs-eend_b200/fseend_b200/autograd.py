@@ -216,6 +216,108 @@ class SpeakerAttnFn(torch.autograd.Function):
         return dqkv, None, None
 
 
+class L2NormFn(torch.autograd.Function):
+    """y = x / ||x||_2 over the last dim (256), no eps (FS:model:41,43)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x2 = _f32c(x, "L2NormFn x").reshape(-1, 256)
+        y = torch.empty_like(x2)
+        inv = torch.empty(x2.shape[0], device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _check(lib().fseend_train_l2norm_fwd(_ptr(x2), x2.shape[0], _ptr(y), _ptr(inv), _stream()))
+        ctx.save_for_backward(y, inv)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        dy2 = _f32c(dy, "L2NormFn dy").reshape(-1, 256)
+        dx = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            _check(lib().fseend_train_l2norm_bwd(_ptr(y), _ptr(inv), _ptr(dy2), y.shape[0], _ptr(dx), _stream()))
+        return dx.view(dy.shape)
+
+
+class HeadFn(torch.autograd.Function):
+    """logits[b, t, s] = emb[b, t, :] . att[b, t, s, :]  (FS:model:60)."""
+
+    @staticmethod
+    def forward(ctx, emb, att):
+        emb, att = _f32c(emb, "HeadFn emb"), _f32c(att, "HeadFn att")
+        B, T, S, D = att.shape
+        if D != 256 or tuple(emb.shape) != (B, T, D):
+            raise FseendError("HeadFn: emb [B, T, 256], att [B, T, S, 256]")
+        y = torch.empty(B, T, S, device=emb.device, dtype=torch.float32)
+        with torch.cuda.device(emb.device):
+            _check(lib().fseend_train_head_fwd(_ptr(emb), _ptr(att), B * T, S, _ptr(y), _stream()))
+        ctx.save_for_backward(emb, att)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        emb, att = ctx.saved_tensors
+        B, T, S, _ = att.shape
+        dy = _f32c(dy, "HeadFn dy")
+        demb, datt = torch.empty_like(emb), torch.empty_like(att)
+        with torch.cuda.device(emb.device):
+            _check(lib().fseend_train_head_bwd(_ptr(emb), _ptr(att), _ptr(dy), B * T, S, _ptr(demb), _ptr(datt), _stream()))
+        return demb, datt
+
+
+class BatchNormTrainFn(torch.autograd.Function):
+    """nn.BatchNorm1d in training mode over the rows of x [..., C]: returns (y, batch mean, biased batch variance)."""
+
+    @staticmethod
+    def forward(ctx, x, g, b, eps: float):
+        Cn = x.shape[-1]
+        x2 = _f32c(x, "BatchNormTrainFn x").reshape(-1, Cn)
+        g, b = _f32c(g, "gamma"), _f32c(b, "beta")
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        stats = torch.empty(2 * Cn, device=x.device, dtype=torch.float32)
+        ws = _workspace(x.device, lib().fseend_train_batchnorm_workspace_bytes(rows, Cn))
+        with torch.cuda.device(x.device):
+            _check(lib().fseend_train_batchnorm_fwd(_ptr(x2), _ptr(g), _ptr(b), rows, Cn, float(eps), _ptr(y), _ptr(stats),
+                                                    _ptr(ws), ws.numel(), _stream()))
+        ctx.save_for_backward(x2, g, stats)
+        ctx.eps, ctx.shape = float(eps), x.shape
+        ctx.mark_non_differentiable(stats)
+        return y.view(x.shape), stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        x2, g, stats = ctx.saved_tensors
+        rows, Cn = x2.shape
+        dy2 = _f32c(dy, "BatchNormTrainFn dy").reshape(rows, Cn)
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dg, db = torch.empty_like(g), torch.empty_like(g)
+        ws = _workspace(x2.device, lib().fseend_train_batchnorm_workspace_bytes(rows, Cn))
+        with torch.cuda.device(x2.device):
+            _check(lib().fseend_train_batchnorm_bwd(_ptr(x2), _ptr(g), _ptr(stats), _ptr(dy2), rows, Cn, ctx.eps, _ptr(dx),
+                                                    _ptr(dg), _ptr(db), _ptr(ws), ws.numel(), _stream()))
+        return (None if dx is None else dx.view(ctx.shape)), dg, db, None
+
+
+def batch_norm_forward(bn: nn.BatchNorm1d, x: torch.Tensor) -> torch.Tensor:
+    """``bn(x.transpose(1, 2)).transpose(1, 2)`` for x [B, T, C] (FS:model:166).  Training mode: native kernels with batch
+    statistics; the running statistics are updated as nn.BatchNorm1d does (momentum, unbiased variance,
+    num_batches_tracked).  Eval mode inside a training graph (frozen statistics): torch's functional batch_norm."""
+    if not bn.training:
+        return torch.nn.functional.batch_norm(x.transpose(1, 2), bn.running_mean, bn.running_var, bn.weight, bn.bias, False,
+                                              0.0, bn.eps).transpose(1, 2).contiguous()
+    y, stats = BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.eps)
+    if bn.track_running_stats:
+        with torch.no_grad():
+            Cn = x.shape[-1]
+            rows = x.numel() // Cn
+            bn.num_batches_tracked += 1
+            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.running_mean.mul_(1 - mom).add_(stats[:Cn], alpha=mom)
+            bn.running_var.mul_(1 - mom).add_(stats[Cn:] * (rows / max(rows - 1, 1)), alpha=mom)
+    return y
+
+
 def _seed() -> int:
     """A fresh 62-bit seed for one attention call, drawn from torch's CPU generator (reproducible under manual_seed)."""
     return int(torch.randint(0, 2 ** 62, (1,)).item())

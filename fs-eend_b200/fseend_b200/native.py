@@ -52,7 +52,9 @@ EXPORTS = [
     "fseend_p32_linear_destroy", "fseend_p32_linear_apply", "fseend_op_p32_retention",
     "fseend_train_linear_workspace_bytes", "fseend_train_linear_fwd", "fseend_train_linear_bwd", "fseend_train_add_layernorm_fwd",
     "fseend_train_layernorm_workspace_bytes", "fseend_train_layernorm_bwd", "fseend_train_attn_fwd", "fseend_train_attn_bwd",
-    "fseend_train_spk_attn_fwd", "fseend_train_spk_attn_bwd",
+    "fseend_train_spk_attn_fwd", "fseend_train_spk_attn_bwd", "fseend_train_l2norm_fwd", "fseend_train_l2norm_bwd",
+    "fseend_train_head_fwd", "fseend_train_head_bwd", "fseend_train_batchnorm_workspace_bytes", "fseend_train_batchnorm_fwd",
+    "fseend_train_batchnorm_bwd",
 ]
 
 
@@ -198,6 +200,20 @@ def lib() -> C.CDLL:
     L.fseend_train_spk_attn_fwd.argtypes = [vp, ip, ip, fp, C.c_ulonglong, vp, vp]
     L.fseend_train_spk_attn_bwd.restype = ip
     L.fseend_train_spk_attn_bwd.argtypes = [vp, vp, ip, ip, fp, C.c_ulonglong, vp, vp]
+    L.fseend_train_l2norm_fwd.restype = ip
+    L.fseend_train_l2norm_fwd.argtypes = [vp, ip, vp, vp, vp]
+    L.fseend_train_l2norm_bwd.restype = ip
+    L.fseend_train_l2norm_bwd.argtypes = [vp, vp, vp, ip, vp, vp]
+    L.fseend_train_head_fwd.restype = ip
+    L.fseend_train_head_fwd.argtypes = [vp, vp, ip, ip, vp, vp]
+    L.fseend_train_head_bwd.restype = ip
+    L.fseend_train_head_bwd.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp]
+    L.fseend_train_batchnorm_workspace_bytes.restype = sz
+    L.fseend_train_batchnorm_workspace_bytes.argtypes = [ip, ip]
+    L.fseend_train_batchnorm_fwd.restype = ip
+    L.fseend_train_batchnorm_fwd.argtypes = [vp, vp, vp, ip, ip, fp, vp, vp, vp, sz, vp]
+    L.fseend_train_batchnorm_bwd.restype = ip
+    L.fseend_train_batchnorm_bwd.argtypes = [vp, vp, vp, vp, ip, ip, fp, vp, vp, vp, vp, sz, vp]
     _lib = L
     return L
 

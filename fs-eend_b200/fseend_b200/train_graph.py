@@ -5,9 +5,10 @@ What runs where (DESIGN.md §7 has the table):
   * native kernels, forward AND backward (fseend_b200.autograd): every Linear (input projection, QKV / out projections,
     FFNs, the k=19 Conv1d as one GEMM over unfolded frames, the attractor ``convert``), every residual + LayerNorm, the
     causal time attention of encoder and decoder, the speaker-axis attention — >99 % of the step's FLOPs;
-  * torch CUDA ops (interim, small): BatchNorm1d with batch statistics, the layout changes between the (B*S, T) and
-    (B*T, S) views, the two L2 normalisations, the dot-product head, the embedding-consistency loss, dropout masks on
-    the residual branches.
+    also native: BatchNorm1d with batch statistics, the two L2 normalisations, the dot-product head;
+  * torch CUDA ops (interim, small): the layout changes between the (B*S, T) and (B*T, S) views, the frame unfolding
+    of the Conv1d, the length mask, the embedding-consistency loss (three batched matmuls), dropout masks on the
+    residual branches, the optimizer.
 Dropout (reference recipes train with 0.1): the residual / FFN dropouts are torch's functional dropout on the native
 kernels' outputs; the attention-probability dropout inside nn.MultiheadAttention is implemented in the attention kernels
 themselves (counter-based hash of (seed, sequence, head, query, key); the backward regenerates the mask).  The random
@@ -19,7 +20,8 @@ import torch
 import torch.nn.functional as F
 from torch.nn.utils.rnn import pad_sequence
 
-from .autograd import AddLayerNormFn, LinearFn, encoder_layer_forward, fusion_layer_forward
+from .autograd import (AddLayerNormFn, HeadFn, L2NormFn, LinearFn, batch_norm_forward, encoder_layer_forward,
+                       fusion_layer_forward)
 from .native import FseendError
 
 
@@ -39,7 +41,7 @@ def fs_forward_train(model, src, tgt, ilens):
     # ---- encoder, reference :162-188
     x = pad_sequence([s.to(device=dev, dtype=dt) for s in src], batch_first=True, padding_value=-1.0)
     B, T, _ = x.shape
-    x = enc.bn(x.transpose(1, 2)).transpose(1, 2).contiguous()              # batch statistics in train mode (torch)
+    x = batch_norm_forward(enc.bn, x)                                        # batch statistics incl. the -1 padding rows
     h = LinearFn.apply(x, enc.encoder.weight, enc.encoder.bias, "none")
     h = AddLayerNormFn.apply(h, None, enc.encoder_norm.weight, enc.encoder_norm.bias, enc.encoder_norm.eps)
     delay = enc.mask_delay if enc.has_mask else T
@@ -55,7 +57,7 @@ def fs_forward_train(model, src, tgt, ilens):
     Tout = cols.shape[1]
     emb = LinearFn.apply(cols.reshape(B, Tout, D * K), model.cnn.weight.reshape(model.cnn.out_channels, D * K),
                          model.cnn.bias, "none")
-    emb = emb / torch.norm(emb, dim=-1, keepdim=True)
+    emb = L2NormFn.apply(emb)
     # ---- attractor decoder, reference :112-118: convert([emb ; pe_s]) = emb Wc[:, :D]^T + (pe_s Wc[:, D:]^T + b)
     Wc = dec.convert.weight
     pe = dec.pos_enc.pe[0, :S].to(dt)
@@ -64,7 +66,7 @@ def fs_forward_train(model, src, tgt, ilens):
     att = a0[:, :, None, :] + pp[None, None]
     for layer in dec.attractor_decoder.layers:
         att = fusion_layer_forward(layer, att, dec.mask_delay)
-    att = att / torch.norm(att, dim=-1, keepdim=True)
+    att = L2NormFn.apply(att)
     # ---- embedding-consistency loss, reference :46-57 (torch; the (B, T, T) maps are 64 MB each at B=64, T=500)
     attn_map = emb @ emb.transpose(-1, -2)
     n = torch.norm(emb, dim=-1, keepdim=True)
@@ -74,7 +76,7 @@ def fs_forward_train(model, src, tgt, ilens):
     label_map = (tp @ tp.transpose(-1, -2)) / (tn @ tn.transpose(-1, -2) + 1e-6)
     emb_consis_loss = F.mse_loss(attn_map, label_map)
     # ---- head, reference :60-64
-    y = (emb[:, :, None, :] * att).sum(-1)
+    y = HeadFn.apply(emb, att)
     output = [o[:l, :ns] for o, l, ns in zip(y, lens, n_speakers)]
     embs = [e[:l] for e, l in zip(emb, lens)]
     atts = [a[:l, 1:ns] for a, l, ns in zip(att, lens, n_speakers)]

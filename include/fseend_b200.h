@@ -322,6 +322,24 @@ int fseend_train_spk_attn_fwd(const float* qkv, int n_frames, int S, float dropo
 int fseend_train_spk_attn_bwd(const float* qkv, const float* dout, int n_frames, int S, float dropout_p,
                               unsigned long long seed, float* dqkv, void* stream);
 
+/* Row kernels of the training graph (csrc/train_ops.cu), fp32:
+ *  l2norm: y = x / ||x||_2 over rows of 256 (FS model file :41,:43, no eps), inv_norm[rows] saved for the backward
+ *          dx = (dy - y (y . dy)) * inv_norm;
+ *  head:   y[f][s] = emb[f][:] . att[f][s][:] (:60) and its two gradients;
+ *  batchnorm: nn.BatchNorm1d in training mode over x [rows][C] (:166; the -1 padding rows are part of the batch, as in
+ *          the reference): stats[2C] = batch mean | biased variance (the caller updates running_mean / running_var),
+ *          backward dx, dgamma, dbeta. */
+int fseend_train_l2norm_fwd(const float* x, int rows, float* y, float* inv_norm, void* stream);
+int fseend_train_l2norm_bwd(const float* y, const float* inv_norm, const float* dy, int rows, float* dx, void* stream);
+int fseend_train_head_fwd(const float* emb, const float* att, int frames, int S, float* y, void* stream);
+int fseend_train_head_bwd(const float* emb, const float* att, const float* dy, int frames, int S, float* demb, float* datt,
+                          void* stream);
+size_t fseend_train_batchnorm_workspace_bytes(int rows, int C);
+int fseend_train_batchnorm_fwd(const float* x, const float* g, const float* b, int rows, int C, float eps, float* y,
+                               float* stats, void* workspace, size_t ws_bytes, void* stream);
+int fseend_train_batchnorm_bwd(const float* x, const float* g, const float* stats, const float* dy, int rows, int C,
+                               float eps, float* dx, float* dg, float* db, void* workspace, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

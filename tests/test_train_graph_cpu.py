@@ -37,6 +37,18 @@ class _Ffn:
         return F.linear(torch.relu(F.linear(x, w1, b1)), w2, b2)
 
 
+class _L2:
+    apply = staticmethod(lambda x: x / torch.norm(x, dim=-1, keepdim=True))
+
+
+class _Head:
+    apply = staticmethod(lambda emb, att: (emb[:, :, None, :] * att).sum(-1))
+
+
+def _bn(bn, x):
+    return bn(x.transpose(1, 2)).transpose(1, 2).contiguous()
+
+
 class _Causal:
     apply = staticmethod(lambda qkv, delay, p=0.0, seed=0: _attn(qkv, delay))
 
@@ -56,6 +68,9 @@ def test_train_graph_wiring_matches_oracle_autograd(monkeypatch, mask_delay):
     monkeypatch.setattr(A, "FfnFn", _Ffn)
     monkeypatch.setattr(A, "CausalAttnFn", _Causal)
     monkeypatch.setattr(A, "SpeakerAttnFn", _Spk)
+    monkeypatch.setattr(G, "L2NormFn", _L2)
+    monkeypatch.setattr(G, "HeadFn", _Head)
+    monkeypatch.setattr(G, "batch_norm_forward", _bn)
     monkeypatch.setattr(G, "_require_device", lambda dev: None)
     sd = O.random_state_dict(seed=11, enc_n_layers=1, dec_n_layers=1)
     m = OnlineTransformerDADiarization(n_speakers=4, in_size=345, n_units=256, n_heads=4, enc_n_layers=1, dec_n_layers=1,

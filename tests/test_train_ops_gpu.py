@@ -386,3 +386,89 @@ def test_training_with_reference_dropout(built_lib):
     l3, g3 = run(2)
     assert l1 == l2 and torch.equal(g1, g2)
     assert l1 != l3 and torch.isfinite(g3).all()
+
+
+def test_l2norm_head_batchnorm_fwd_bwd(built_lib):
+    from fseend_b200.autograd import BatchNormTrainFn, HeadFn, L2NormFn
+    g = torch.Generator().manual_seed(21)
+    # L2 normalisation
+    x = (3 * torch.randn(5, 37, 256, generator=g)).cuda().requires_grad_()
+    dy = torch.randn(5, 37, 256, generator=g).cuda()
+    y = L2NormFn.apply(x)
+    y.backward(dy)
+    xr = x.detach().double().requires_grad_()
+    yr = xr / torch.norm(xr, dim=-1, keepdim=True)
+    yr.backward(dy.double())
+    close(y, yr, "l2 y")
+    close(x.grad, xr.grad, "l2 dx")
+    # head
+    emb = torch.randn(3, 50, 256, generator=g).cuda().requires_grad_()
+    att = torch.randn(3, 50, 6, 256, generator=g).cuda().requires_grad_()
+    dl = torch.randn(3, 50, 6, generator=g).cuda()
+    lg = HeadFn.apply(emb, att)
+    lg.backward(dl)
+    er, ar = emb.detach().double().requires_grad_(), att.detach().double().requires_grad_()
+    lr = (er[:, :, None, :] * ar).sum(-1)
+    lr.backward(dl.double())
+    close(lg, lr, "head y")
+    close(emb.grad, er.grad, "head demb")
+    close(att.grad, ar.grad, "head datt")
+    # BatchNorm, training mode, C = 345 (not a multiple of 4), rows not a multiple of the block
+    xb = (2 * torch.randn(7, 300, 345, generator=g) + 0.5).cuda().requires_grad_()
+    gam = (1 + 0.2 * torch.randn(345, generator=g)).cuda().requires_grad_()
+    bet = (0.1 * torch.randn(345, generator=g)).cuda().requires_grad_()
+    dyb = torch.randn(7, 300, 345, generator=g).cuda()
+    yb, stats = BatchNormTrainFn.apply(xb, gam, bet, 1e-5)
+    yb.backward(dyb)
+    xr, gr, br = (t.detach().double().requires_grad_() for t in (xb, gam, bet))
+    ybr = torch.nn.functional.batch_norm(xr.reshape(-1, 345), None, None, gr, br, True, 0.1, 1e-5).reshape(7, 300, 345)
+    ybr.backward(dyb.double())
+    close(yb, ybr, "bn y")
+    close(stats[:345], xr.detach().reshape(-1, 345).mean(0), "bn mean")
+    close(stats[345:], xr.detach().reshape(-1, 345).var(0, unbiased=False), "bn var")
+    close(xb.grad, xr.grad, "bn dx", rel=1e-4)
+    close(gam.grad, gr.grad, "bn dgamma")
+    close(bet.grad, br.grad, "bn dbeta")
+
+
+def test_training_batchnorm_train_mode_matches_torch_graph(built_lib, monkeypatch):
+    """The whole step with BatchNorm in training mode (batch statistics over the -1-padded batch, running statistics
+    updated) against the same graph built from plain torch ops in float64 on the GPU (the stand-ins of
+    tests/test_train_graph_cpu.py, which that file pins against the oracle)."""
+    import copy
+    import fseend_b200.autograd as A
+    import fseend_b200.train_graph as G
+    import test_train_graph_cpu as S
+    from fseend_b200.loss import standard_loss
+    from oracle import fs_eend_oracle as O
+    sd = O.random_state_dict(seed=12, enc_n_layers=1, dec_n_layers=1)
+    m = _train_model(sd, 1, 1)
+    ref = copy.deepcopy(m).double()
+    lens, n_spks = [130, 88, 61], [3, 2, 3]
+    src, _ = O.synthetic_features(3, 130, seed=5, lens=lens)
+    g = torch.Generator().manual_seed(6)
+    tgt = [(torch.rand(l, n, generator=g) < 0.4).float().cuda() for l, n in zip(lens, n_spks)]
+    out, el, _, _ = m([s.cuda() for s in src], tgt, lens)
+    (standard_loss(out, tgt) + el).backward()
+    with monkeypatch.context() as mp:
+        for mod in (A, G):
+            mp.setattr(mod, "LinearFn", S._Lin)
+            mp.setattr(mod, "AddLayerNormFn", S._AddLn)
+        mp.setattr(A, "FfnFn", S._Ffn)
+        mp.setattr(A, "CausalAttnFn", type("C", (), {"apply": staticmethod(lambda qkv, d, p=0.0, seed=0: ref_attention(qkv, d))}))
+        mp.setattr(A, "SpeakerAttnFn", type("P", (), {"apply": staticmethod(lambda qkv, p=0.0, seed=0: ref_attention(qkv, 1 << 20))}))
+        mp.setattr(G, "L2NormFn", S._L2)
+        mp.setattr(G, "HeadFn", S._Head)
+        mp.setattr(G, "batch_norm_forward", S._bn)
+        out_r, el_r, _, _ = G.fs_forward_train(ref, [s.cuda().double() for s in src], [t.double() for t in tgt], lens)
+        (G.standard_loss_train(out_r, [t.double() for t in tgt]) + el_r).backward()
+    for o, r in zip(out, out_r):
+        close(o, r, "logits", rel=1e-4)
+    close(m.enc.bn.running_mean, ref.enc.bn.running_mean, "running_mean")
+    close(m.enc.bn.running_var, ref.enc.bn.running_var, "running_var")
+    assert int(m.enc.bn.num_batches_tracked) == int(ref.enc.bn.num_batches_tracked) == 1
+    for (name, p), (_, pr) in zip(m.named_parameters(), ref.named_parameters()):
+        if pr.grad is None:
+            assert p.grad is None, name
+            continue
+        close(p.grad, pr.grad, name, rel=3e-4)

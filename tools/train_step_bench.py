@@ -48,6 +48,18 @@ class _Ffn:
         return F.linear(torch.relu(F.linear(x, w1, b1)), w2, b2)
 
 
+class _L2:
+    apply = staticmethod(lambda x: x / torch.norm(x, dim=-1, keepdim=True))
+
+
+class _Head:
+    apply = staticmethod(lambda emb, att: (emb[:, :, None, :] * att).sum(-1))
+
+
+def _bn(bn, x):
+    return bn(x.transpose(1, 2)).transpose(1, 2).contiguous()
+
+
 class _Causal:
     apply = staticmethod(lambda qkv, delay, p=0.0, seed=0: _attn(qkv, delay))
 
@@ -110,9 +122,12 @@ def measure(batch=64, frames=500, speakers=4, steps=5, warmup=2, native_only=Fal
     # torch eager arm: same graph, stand-in ops
     saved = {(mod, n): getattr(mod, n) for mod in (A, G) for n in ("LinearFn", "AddLayerNormFn")}
     saved[(A, "CausalAttnFn")], saved[(A, "SpeakerAttnFn")], saved[(A, "FfnFn")] = A.CausalAttnFn, A.SpeakerAttnFn, A.FfnFn
+    for n_ in ("L2NormFn", "HeadFn", "batch_norm_forward"):
+        saved[(G, n_)] = getattr(G, n_)
     for mod in (A, G):
         mod.LinearFn, mod.AddLayerNormFn = _Lin, _AddLn
     A.CausalAttnFn, A.SpeakerAttnFn, A.FfnFn = _Causal, _Spk, _Ffn
+    G.L2NormFn, G.HeadFn, G.batch_norm_forward = _L2, _Head, _bn
     res = {}
     try:
         for name, tf32 in (("torch_fp32", False), ("torch_tf32", True)):
@@ -129,8 +144,8 @@ def measure(batch=64, frames=500, speakers=4, steps=5, warmup=2, native_only=Fal
     n_frames = B * T
     return {"workload": f"FS-EEND training step: fwd + standard_loss + emb loss + bwd + Adam, B={B} x T={T}, {S + 2} label classes, "
                         "4 enc + 2 dec layers, dropout 0",
-            "status": "SURVEY 8f N1 STARTED: GEMMs / attention / LayerNorm forward+backward are this library's kernels; "
-                      "BatchNorm, L2 norms, head, emb loss, optimizer are torch ops",
+            "status": "SURVEY 8f N1 STARTED: GEMMs / attention / LayerNorm / BatchNorm / L2 norms / head forward+backward are this "
+                      "library's kernels; emb loss, layout copies, residual dropout and the optimizer are torch ops",
             "native_ms": round(t_native, 2), "native_frames_per_s": round(n_frames / t_native * 1e3),
             "torch_eager_fp32_ms": round(res["torch_fp32"], 2), "torch_eager_tf32_ms": round(res["torch_tf32"], 2),
             "loss_after_%d_steps" % (steps + warmup): {"native": loss_native, "torch_fp32": res["torch_fp32_loss"],
