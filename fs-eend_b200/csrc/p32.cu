@@ -521,6 +521,169 @@ p32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_
 }
 
 // =====================================================================================================================
+// TMA-fed form: A arrives as pre-split fp16 hi / lo planes [rows][K] (row-major, one 2-D tensor map each) — no register
+// producers, so the per-k-block cost is the 12 MMAs plus the fold.  Used by the training products (train_ops.cu), whose
+// operands are split by one elementwise pass that also applies the power-of-two gradient scale.  ncu on the register-fed
+// persistent kernel (profiles/r02c_train_gemm_ncu.txt): tensor pipe 14-22 % active, the producer warps need ~2000+ clk per
+// k-block against 768 clk of MMAs.
+//   warp 0 lane 0 : TMA for A_hi, A_lo, W_hi, W_lo of every k-block (3-stage ring, 192 KB)
+//   warp 1        : MMA issuer, four 128-column TMEM accumulators (fresh per k-block)
+//   warps 4-11    : fold + epilogue (the tile goes out through a 64-row staging tile, two passes)
+// One sequence, one tap.  kMask: out = mask > 0 ? v : 0 (ReLU backward in the epilogue); out_scale_dev as in the train variant.
+constexpr int kTStages = 3;
+constexpr int kTHalfRows = 64;
+constexpr int kPlanesSmem = kTStages * kStageBytes + kTHalfRows * kPLdT * 4 + 1024;
+constexpr int kTThreads = 12 * 32;
+
+template <int kAct>
+__global__ void __launch_bounds__(kTThreads, 1)
+p32_gemm_planes_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                       const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
+                       const P32GemmParams p, const int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kTStages];
+  __shared__ __align__(8) uint64_t empty_bar[kTStages];
+  __shared__ __align__(8) uint64_t acc_full[kPAcc];
+  __shared__ __align__(8) uint64_t acc_empty[kPAcc];
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* tile_s = reinterpret_cast<float*>(smem + kTStages * kStageBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kTStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < kPAcc; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 256);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmAhi);
+    tma_prefetch_desc(&tmAlo);
+    tma_prefetch_desc(&tmWhi);
+    tma_prefetch_desc(&tmWlo);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int n_tiles_n = p.N / BN;
+  const int KB = p.k_blocks;
+  const int n_local = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const uint32_t G = static_cast<uint32_t>(n_local > 0 ? n_local : 0) * KB;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (uint32_t gi = 0; gi < G; ++gi) {
+        const int s = gi % kTStages;
+        mbar_wait(&empty_bar[s], ((gi / kTStages) & 1) ^ 1, 91);
+        const int tile = blockIdx.x + (gi / KB) * gridDim.x, kb = gi % KB;
+        const int t0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+        uint8_t* st = smem + s * kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[s], 4 * kTileBytes);
+        tma_load_2d(st, &tmAhi, &full_bar[s], kb * BK, t0);                 // rows beyond the tensor are zero-filled
+        tma_load_2d(st + kTileBytes, &tmAlo, &full_bar[s], kb * BK, t0);
+        tma_load_2d(st + 2 * kTileBytes, &tmWhi, &full_bar[s], kb * BK, n0);
+        tma_load_2d(st + 3 * kTileBytes, &tmWlo, &full_bar[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN, false);
+    for (uint32_t g = 0; g < G; ++g) {
+      const int s = g % kTStages, buf = g % kPAcc;
+      mbar_wait(&full_bar[s], (g / kTStages) & 1, 92);
+      mbar_wait(&acc_empty[buf], ((g / kPAcc) & 1) ^ 1, 93);
+      tc_fence_after();
+      const uint32_t sb = smem_u32(smem + s * kStageBytes);
+      const uint64_t dAhi = smem_desc_sw128(sb), dAlo = smem_desc_sw128(sb + kTileBytes);
+      const uint64_t dWhi = smem_desc_sw128(sb + 2 * kTileBytes), dWlo = smem_desc_sw128(sb + 3 * kTileBytes);
+      const uint32_t d = tmem_base + buf * 128;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          umma_f16(d, dAlo + 2 * kk, dWhi + 2 * kk, idesc, kk > 0 ? 1u : 0u);
+          umma_f16(d, dAhi + 2 * kk, dWlo + 2 * kk, idesc, 1u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) umma_f16(d, dAhi + 2 * kk, dWhi + 2 * kk, idesc, 1u);
+        umma_commit(&empty_bar[s]);
+        umma_commit(&acc_full[buf]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3, half = (warp - 4) >> 2;
+    const int r = wq * 32 + lane;
+    const uint32_t t_addr = (static_cast<uint32_t>(wq * 32) << 16) + half * 64;
+    const int ew = warp - 4;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int t0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+      float acc[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      for (int kb = 0; kb < KB; ++kb, ++g) {
+        const int buf = g % kPAcc;
+        mbar_wait(&acc_full[buf], (g / kPAcc) & 1, 94);
+        tc_fence_after();
+        uint32_t ra[32], rb[32];
+        tmem_ld32(tmem_base + buf * 128 + t_addr, ra);
+        tmem_ld32(tmem_base + buf * 128 + t_addr + 32, rb);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          acc[j] += __uint_as_float(ra[j]);
+          acc[32 + j] += __uint_as_float(rb[j]);
+        }
+      }
+      const int col = n0 + 4 * lane;
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      const float wsc = p.w_inv_scale * (p.out_scale_dev ? __ldg(p.out_scale_dev) : 1.f), alpha = p.alpha;
+#pragma unroll 1
+      for (int hp = 0; hp < 2; ++hp) {                  // rows hp * 64 .. + 64 through the staging tile
+        named_bar_sync(1, 256);                         // the previous pass' rows have been read out
+        if ((wq >> 1) == hp) {
+          float* trow = tile_s + (r - hp * kTHalfRows) * kPLdT + half * 64;
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) *reinterpret_cast<float4*>(trow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        }
+        named_bar_sync(1, 256);
+        for (int rr = ew; rr < kTHalfRows; rr += 8) {
+          const int t = t0 + hp * kTHalfRows + rr;
+          if (t >= p.rows_per_seq) break;
+          const size_t orow = static_cast<size_t>(t);
+          const float4 a = *reinterpret_cast<const float4*>(tile_s + rr * kPLdT + 4 * lane);
+          float4 v;
+          v.x = alpha * act_apply<kAct>(fmaf(a.x, wsc, bb.x));
+          v.y = alpha * act_apply<kAct>(fmaf(a.y, wsc, bb.y));
+          v.z = alpha * act_apply<kAct>(fmaf(a.z, wsc, bb.z));
+          v.w = alpha * act_apply<kAct>(fmaf(a.w, wsc, bb.w));
+          if (p.residual) {
+            const float4 rs = *reinterpret_cast<const float4*>(p.residual + orow * p.ldr + col);
+            v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w;
+          }
+          if (p.out_mask) {
+            const float4 mk = __ldg(reinterpret_cast<const float4*>(p.out_mask + orow * p.ldo + col));
+            v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+          }
+          *reinterpret_cast<float4*>(p.out + orow * p.ldo + col) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================================
 // A-stationary persistent form for K <= 256, one tap, N >= 256 (QKV(G) projections, FFN up-projections, speaker-attention
 // in-projection: most launches of the parity path).  ncu on the persistent kernel above (r02_final_p32persist.txt): 844 M
 // warp-instructions for one decoder FFN up-projection, i.e. ~900 issue cycles per k-block against 768 clk of MMAs — the A
@@ -1587,6 +1750,24 @@ void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P
   if (p.act == P32_RELU) p32_gemm_kernel<P32_RELU><<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
   else if (p.act == P32_SWISH) p32_gemm_kernel<P32_SWISH><<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
   else p32_gemm_kernel<P32_NONE><<<grid, 256, kGemmSmem, st>>>(tmWhi, tmWlo, p);
+}
+
+
+void launch_p32_gemm_planes(const CUtensorMap& tmAhi, const CUtensorMap& tmAlo, const CUtensorMap& tmWhi,
+                            const CUtensorMap& tmWlo, const P32GemmParams& p, cudaStream_t st) {
+  static PerDeviceOnce once;
+  static int num_sms = 148;
+  if (once.first()) {
+    cudaFuncSetAttribute(p32_gemm_planes_kernel<P32_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlanesSmem);
+    cudaFuncSetAttribute(p32_gemm_planes_kernel<P32_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlanesSmem);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int n_tiles = ((p.rows_per_seq + BM - 1) / BM) * (p.N / BN);
+  const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+  if (p.act == P32_RELU) p32_gemm_planes_kernel<P32_RELU><<<grid, kTThreads, kPlanesSmem, st>>>(tmAhi, tmAlo, tmWhi, tmWlo, p, n_tiles);
+  else p32_gemm_planes_kernel<P32_NONE><<<grid, kTThreads, kPlanesSmem, st>>>(tmAhi, tmAlo, tmWhi, tmWlo, p, n_tiles);
 }
 
 bool launch_p32_rowvec(const __half* whi, const __half* wlo, const P32GemmParams& p, cudaStream_t st) {

@@ -67,6 +67,11 @@ struct P32GemmParams {
 // tmWhi / tmWlo: 2-D (K, taps*N) fp16, box (64, 128), 128B swizzle
 void launch_p32_gemm(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo, const P32GemmParams& p, cudaStream_t st);
 
+// TMA-fed form for pre-split A: tmAhi / tmAlo: 2-D (K, rows) fp16, box (64, 128), 128B swizzle; one sequence, one tap,
+// act none / ReLU; honours bias, alpha, w_inv_scale, residual, out_scale_dev, out_mask.
+void launch_p32_gemm_planes(const CUtensorMap& tmAhi, const CUtensorMap& tmAlo, const CUtensorMap& tmWhi,
+                            const CUtensorMap& tmWlo, const P32GemmParams& p, cudaStream_t st);
+
 // The same product for at most 16 output rows (the per-frame streaming steps: 1 .. B * S rows): with so few rows the
 // GEMM is a weight-streaming matrix-vector product — L2-bandwidth bound, tensor cores idle either way — so it runs on
 // CUDA cores: every warp owns two output columns, lanes split K, the weights (fp16 hi [+ lo] planes, [taps*N][K]

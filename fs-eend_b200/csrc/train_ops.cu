@@ -57,16 +57,33 @@ __device__ __forceinline__ void split1(float x, __half& h, __half& l) {
   l = __float2half_rn(x - __half2float(h));
 }
 
-// src fp32 [R][C] -> hi / lo fp16 planes [R][Cp] (columns >= C zero), values multiplied by `scale`
+// src fp32 [R][C] -> hi / lo fp16 planes [R][Cp] (columns >= C zero), values multiplied by scale * (*scale_dev)
 __global__ void split_planes_kernel(const float* __restrict__ src, int R, int C, int Cp, float scale,
-                                    __half* __restrict__ hi, __half* __restrict__ lo) {
+                                    const float* __restrict__ scale_dev, __half* __restrict__ hi, __half* __restrict__ lo) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<size_t>(R) * Cp) return;
   const int r = static_cast<int>(i / Cp), c = static_cast<int>(i % Cp);
+  const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.f);
   __half h, l;
-  split1(c < C ? src[static_cast<size_t>(r) * C + c] * scale : 0.f, h, l);
+  split1(c < C ? src[static_cast<size_t>(r) * C + c] * sc : 0.f, h, l);
   hi[i] = h;
   lo[i] = l;
+}
+// the same for C == Cp, C % 4 == 0: four elements per thread
+__global__ void __launch_bounds__(256)
+split_planes4_kernel(const float* __restrict__ src, size_t n4, float scale, const float* __restrict__ scale_dev,
+                     __half* __restrict__ hi, __half* __restrict__ lo) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.f);
+  const float4 v = reinterpret_cast<const float4*>(src)[i];
+  __half h[4], l[4];
+  split1(v.x * sc, h[0], l[0]);
+  split1(v.y * sc, h[1], l[1]);
+  split1(v.z * sc, h[2], l[2]);
+  split1(v.w * sc, h[3], l[3]);
+  reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<const uint2*>(h);
+  reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<const uint2*>(l);
 }
 
 // src fp32 [R][C] -> fp16 hi / lo planes of its transpose, laid out per K-slice: plane[(r / ks) * Cp + c][r % ks] for
@@ -498,33 +515,23 @@ inline WgradPlan wgrad_plan(int rows, int K, int N) {
   return pl;
 }
 
+// fp32 [R][C] -> fp16 hi / lo planes [R][Cp]
+void split_rows(const float* src, int R, int C, int Cp, float scale, const float* scale_dev, __half* hi, __half* lo,
+                cudaStream_t st) {
+  if (C == Cp && C % 4 == 0) {
+    const size_t n4 = static_cast<size_t>(R) * C / 4;
+    split_planes4_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(src, n4, scale, scale_dev, hi, lo);
+  } else {
+    const size_t n = static_cast<size_t>(R) * Cp;
+    split_planes_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(src, R, C, Cp, scale, scale_dev, hi, lo);
+  }
+}
+
 CUtensorMap plane_map(const void* base, int rows, int K) {
   uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows)};
   uint64_t str[1] = {static_cast<uint64_t>(K)};
   uint32_t box[2] = {64, 128};
   return make_tmap_f16(base, 2, dims, str, box);
-}
-
-void run_gemm(const float* A, int lda, int rows, int kdim, const __half* hi, const __half* lo, int n_out, const float* bias,
-              int act, float inv_scale, float* out, int ldo, cudaStream_t st) {
-  // out[rows][n_out] = act(inv_scale * A[rows][kdim] planes[n_out][kdim]^T + bias)
-  P32GemmParams p{};
-  p.A = A;
-  p.lda = lda;
-  p.a_seq_rows = rows;
-  p.rows_per_seq = rows;
-  p.n_seq = 1;
-  p.k_blocks = kdim / 64;
-  p.taps = 1;
-  p.N = n_out;
-  p.bias = bias;
-  p.act = act;
-  p.alpha = 1.f;
-  p.w_inv_scale = inv_scale;
-  p.out = out;
-  p.ldo = ldo;
-  const CUtensorMap th = plane_map(hi, n_out, kdim), tl = plane_map(lo, n_out, kdim);
-  launch_p32_gemm(th, tl, p, st);
 }
 
 }  // namespace
@@ -537,10 +544,12 @@ extern "C" {
 // Workspace (bytes) of fseend_train_linear_fwd / _bwd for a [rows][K] x [N][K]^T layer.
 size_t fseend_train_linear_workspace_bytes(int rows, int K, int N) {
   const size_t Kp = pad64(K), Np = pad128(N), Kp128 = pad128(K);
-  const size_t fwd = 2 * align256(Np * Kp * 2) + align256(static_cast<size_t>(rows) * Kp * 4);
+  const size_t rows_p = pad128(rows);            // A planes are declared to TMA with whole 128-row boxes
+  const size_t fwd = 2 * align256(Np * Kp * 2) + 2 * align256(rows_p * Kp * 2);
   const WgradPlan pl = wgrad_plan(rows, K, N);
   const size_t bwd = 256                                                        // max slot + scale pair
                      + 2 * align256(Kp128 * Np * 2)                             // W^T planes [K][N]
+                     + 2 * align256(rows_p * Np * 2)                            // dY planes (scaled) for the dgrad
                      + align256(static_cast<size_t>(rows) * Kp128 * 4)          // dX padded
                      + 2 * align256(static_cast<size_t>(pl.n_slices) * pl.n_out * pl.ks * 2)   // small operand's planes
                      + align256(static_cast<size_t>(pl.n_slices) * pl.M * pl.n_out * 4)        // split-K partial products
@@ -561,19 +570,26 @@ int fseend_train_linear_fwd(const float* x, int rows, int K, const float* w, int
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     __half* hi = reinterpret_cast<__half*>(ws);
     __half* lo = reinterpret_cast<__half*>(ws + align256(static_cast<size_t>(Np) * Kp * 2));
-    float* xp = reinterpret_cast<float*>(ws + 2 * align256(static_cast<size_t>(Np) * Kp * 2));
-    const size_t nw = static_cast<size_t>(Np) * Kp;
-    TCHECK(cudaMemsetAsync(hi, 0, nw * 2, st));
-    TCHECK(cudaMemsetAsync(lo, 0, nw * 2, st));
-    split_planes_kernel<<<static_cast<unsigned>((static_cast<size_t>(N) * Kp + 255) / 256), 256, 0, st>>>(w, N, K, Kp, kWScale, hi, lo);
-    const float* xa = x;
-    if (Kp != K) {      // pad the activation columns (the GEMM reads K in blocks of 64 with 16-byte loads)
-      TCHECK(cudaMemsetAsync(xp, 0, static_cast<size_t>(rows) * Kp * 4, st));
-      TCHECK(cudaMemcpy2DAsync(xp, static_cast<size_t>(Kp) * 4, x, static_cast<size_t>(K) * 4, static_cast<size_t>(K) * 4, rows,
-                               cudaMemcpyDeviceToDevice, st));
-      xa = xp;
-    }
-    run_gemm(xa, Kp, rows, Kp, hi, lo, Np, bias, act, 1.f / kWScale, y, N, st);
+    __half* xhi = reinterpret_cast<__half*>(ws + 2 * align256(static_cast<size_t>(Np) * Kp * 2));
+    __half* xlo = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(xhi) + align256(static_cast<size_t>(pad128(rows)) * Kp * 2));
+    split_rows(w, N, K, Kp, kWScale, nullptr, hi, lo, st);
+    split_rows(x, rows, K, Kp, 1.f, nullptr, xhi, xlo, st);      // activations as planes: both operands arrive by TMA
+    P32GemmParams p{};
+    p.rows_per_seq = rows;
+    p.a_seq_rows = rows;
+    p.n_seq = 1;
+    p.k_blocks = Kp / 64;
+    p.taps = 1;
+    p.N = Np;
+    p.bias = bias;
+    p.act = act;
+    p.alpha = 1.f;
+    p.w_inv_scale = 1.f / kWScale;
+    p.out = y;
+    p.ldo = N;
+    // rows of the planes beyond `rows` (up to the next multiple of 128) are never written: they only feed output rows that
+    // are not stored
+    launch_p32_gemm_planes(plane_map(xhi, pad128(rows), Kp), plane_map(xlo, pad128(rows), Kp), plane_map(hi, Np, Kp), plane_map(lo, Np, Kp), p, st);
     TCHECK(cudaGetLastError());
   });
 }
@@ -603,6 +619,8 @@ int fseend_train_linear_bwd(const float* x, const float* w, const float* y, cons
     __half* wt_hi = reinterpret_cast<__half*>(take(static_cast<size_t>(Kp) * N * 2));
     __half* wt_lo = reinterpret_cast<__half*>(take(static_cast<size_t>(Kp) * N * 2));
     float* dxp = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * Kp * 4));
+    __half* dy_hi = reinterpret_cast<__half*>(take(static_cast<size_t>(pad128(rows)) * N * 2));
+    __half* dy_lo = reinterpret_cast<__half*>(take(static_cast<size_t>(pad128(rows)) * N * 2));
     const size_t plane_elems = static_cast<size_t>(pl.n_slices) * pl.n_out * pl.ks;
     __half* sp_hi = reinterpret_cast<__half*>(take(plane_elems * 2));
     __half* sp_lo = reinterpret_cast<__half*>(take(plane_elems * 2));
@@ -629,11 +647,10 @@ int fseend_train_linear_bwd(const float* x, const float* w, const float* y, cons
       // W^T planes [Kp][N] (rows >= K zero): one slice of N "rows"
       transpose_split_kernel<<<dim3(N / 32, Kp / 32), 256, 0, st>>>(w, nullptr, N, K, N, Kp, kWScale, nullptr, wt_hi, wt_lo);
       float* out = (Kp == K) ? dx : dxp;
+      split_rows(dy, rows, N, N, 1.f, sc, dy_hi, dy_lo, st);          // scaled gradient planes
       P32GemmParams p{};
-      p.A = dy;
-      p.lda = N;
-      p.a_seq_rows = rows;
       p.rows_per_seq = rows;
+      p.a_seq_rows = rows;
       p.n_seq = 1;
       p.k_blocks = N / 64;
       p.taps = 1;
@@ -642,10 +659,9 @@ int fseend_train_linear_bwd(const float* x, const float* w, const float* y, cons
       p.w_inv_scale = 1.f / kWScale;
       p.out = out;
       p.ldo = Kp;
-      p.a_scale_dev = sc;
       p.out_scale_dev = sc + 1;
       p.out_mask = relu_input ? x : nullptr;            // Kp == K here (checked above): same layout as out
-      launch_p32_gemm(plane_map(wt_hi, Kp, N), plane_map(wt_lo, Kp, N), p, st);
+      launch_p32_gemm_planes(plane_map(dy_hi, pad128(rows), N), plane_map(dy_lo, pad128(rows), N), plane_map(wt_hi, Kp, N), plane_map(wt_lo, Kp, N), p, st);
       if (Kp != K)
         TCHECK(cudaMemcpy2DAsync(dx, static_cast<size_t>(K) * 4, dxp, static_cast<size_t>(Kp) * 4, static_cast<size_t>(K) * 4, rows,
                                  cudaMemcpyDeviceToDevice, st));
