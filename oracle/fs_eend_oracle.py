@@ -453,3 +453,10 @@ def synthetic_features(B: int, T: int, in_size: int = 345, seed: int = 777, lens
     g = torch.Generator().manual_seed(seed)
     lens = list(lens) if lens is not None else [T] * B
     return [torch.randn(l, in_size, generator=g) for l in lens], lens
+
+
+def synthetic_labels(seed: int, lens: Sequence[int], n_spks: Sequence[int], p: float = 0.35) -> List[Tensor]:
+    """0/1 speaker-activity matrices (T_i, n_spk_i) for the training-step goldens (tests/golden/make_golden_train.py)."""
+    g = torch.Generator().manual_seed(seed + 1)
+    return [(torch.rand(l, n, generator=g) < p).float() for l, n in zip(lens, n_spks)]
+

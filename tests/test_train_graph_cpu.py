@@ -105,3 +105,71 @@ def test_train_graph_wiring_matches_oracle_autograd(monkeypatch, mask_delay):
         assert (p.grad - r).abs().max() <= 1e-10 * (1 + r.abs().max()), name
         n_checked += 1
     assert n_checked >= 30
+
+
+TRAIN_CASES = {
+    # must match tests/golden/make_golden_train.py
+    "train_e2d1": (21, 2, 1, [140, 101, 77], [4, 3, 4], 0, 0),
+    "train_e1d2_delay": (22, 1, 2, [90, 64], [3, 5], 2, 1),
+}
+
+
+def load_train_golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "fs_train_grads.json")) as f:
+        return json.load(f)
+
+
+def check_against_reference_grads(m, rec, bce, emb_loss, out, rel):
+    """Loss values, logits checksum, BatchNorm running statistics and every parameter gradient (norm + 24 sampled
+    elements) against the REAL reference's autograd (tests/golden/fs_train_grads.json)."""
+    assert abs(float(bce) - rec["bce"]) <= rel * abs(rec["bce"])
+    assert abs(float(emb_loss) - rec["emb_loss"]) <= rel * abs(rec["emb_loss"])
+    assert abs(float(sum(o.detach().double().sum() for o in out)) - rec["logit_sum"]) <= rel * rec["logit_abs_sum"]
+    assert abs(float(m.enc.bn.running_mean.sum()) - rec["running_mean_sum"]) <= rel * (1 + abs(rec["running_mean_sum"]))
+    assert abs(float(m.enc.bn.running_var.sum()) - rec["running_var_sum"]) <= rel * (1 + abs(rec["running_var_sum"]))
+    n = 0
+    for name, p in m.named_parameters():
+        g = rec["grads"][name]
+        if g is None:
+            assert p.grad is None, name
+            continue
+        flat = p.grad.detach().double().reshape(-1).cpu()
+        assert abs(float(flat.norm()) - g["norm"]) <= rel * g["norm"] + 1e-12, name
+        got = flat[torch.tensor(g["idx"])]
+        want = torch.tensor(g["val"], dtype=torch.float64)
+        assert (got - want).abs().max().item() <= rel * g["max_abs"] + 1e-12, name
+        n += 1
+    assert n >= 40
+
+
+@pytest.mark.parametrize("case", list(TRAIN_CASES))
+def test_train_graph_matches_real_reference_autograd(monkeypatch, case):
+    """The train graph's wiring (torch stand-ins for the kernels, float64, BatchNorm in training mode) against gradients
+    produced by the real reference model + its own standard_loss (goldens): equal to rounding."""
+    import fseend_b200.autograd as A
+    import fseend_b200.train_graph as G
+    from nnet.model.onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import OnlineTransformerDADiarization
+    for mod in (A, G):
+        monkeypatch.setattr(mod, "LinearFn", _Lin)
+        monkeypatch.setattr(mod, "AddLayerNormFn", _AddLn)
+    monkeypatch.setattr(A, "FfnFn", _Ffn)
+    monkeypatch.setattr(A, "CausalAttnFn", _Causal)
+    monkeypatch.setattr(A, "SpeakerAttnFn", _Spk)
+    monkeypatch.setattr(G, "L2NormFn", _L2)
+    monkeypatch.setattr(G, "HeadFn", _Head)
+    monkeypatch.setattr(G, "batch_norm_forward", _bn)
+    monkeypatch.setattr(G, "_require_device", lambda dev: None)
+    wseed, ne, nd, lens, n_spks, md, ld = TRAIN_CASES[case]
+    sd = O.random_state_dict(seed=wseed, enc_n_layers=ne, dec_n_layers=nd)
+    m = OnlineTransformerDADiarization(n_speakers=4, in_size=345, n_units=256, n_heads=4, enc_n_layers=ne, dec_n_layers=nd,
+                                       dropout=0.0, has_mask=True, max_seqlen=500, dec_dim_feedforward=2048, mask_delay=md)
+    m.load_state_dict(sd)
+    m = m.double().train()
+    src, _ = O.synthetic_features(len(lens), max(lens), seed=wseed, lens=lens)
+    tgt = [t.double() for t in O.synthetic_labels(wseed, lens, n_spks)]
+    out, el, _, _ = G.fs_forward_train(m, [s.double() for s in src], tgt, lens)
+    bce = G.standard_loss_train(out, tgt, ld)
+    (bce + el).backward()
+    check_against_reference_grads(m, load_train_golden()[case], bce, el, out, rel=1e-9)
