@@ -612,6 +612,101 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------ training arm (--train)
+def run_train(args):
+    """one FS-EEND training step — forward, standard_loss + emb loss, backward through this library's
+    kernels, gradient all-reduce (torch DistributedDataParallel over NCCL, 39.9 MB of fp32 gradients), Adam — at the
+    BASELINE config-1 shape per GPU (weak scaling).  Prints ONE JSON line; `allreduce.exposed_ms` is the step time with the
+    collective minus the step time under `no_sync()` (what the all-reduce adds after overlap with the backward)."""
+    import contextlib
+    import torch
+    import torch.distributed as dist
+    from fseend_b200.loss import standard_loss
+    from nnet.model.onl_tfm_enc_1dcnn_enc_linear_non_autoreg_pos_enc_l2norm import OnlineTransformerDADiarization
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.manual_seed(0)
+    model = OnlineTransformerDADiarization(
+        n_speakers=4, in_size=DIN, n_units=D, n_heads=H, enc_n_layers=ENC_L, dec_n_layers=DEC_L, dropout=0.1,
+        has_mask=True, max_seqlen=T, dec_dim_feedforward=FF).cuda().train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-5)
+    g = torch.Generator(device="cuda").manual_seed(777 + rank)
+    n_spk = 4
+    src = [torch.randn(T, DIN, device="cuda", generator=g) for _ in range(B)]
+    act = [(torch.rand(T, n_spk, device="cuda", generator=g) < 0.3).float() for _ in range(B)]
+    lab = [torch.cat([1 - t.max(-1, keepdim=True)[0], t, torch.zeros(T, 1, device="cuda")], -1) for t in act]   # + silence, + none
+    lens = [T] * B
+    n_grad = sum(p.numel() for p in model.parameters() if p.requires_grad)
+
+    def step(sync=True):
+        ctx = contextlib.nullcontext() if (sync or world == 1) else net.no_sync()
+        with ctx:
+            opt.zero_grad(set_to_none=True)
+            out, emb_loss, _, _ = net(src, lab, lens)
+            loss = standard_loss(out, lab) + emb_loss
+            loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, sync):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loss = step(sync)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), loss
+
+    steps = min(args.steps, 50)
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, loss = timed(steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_nosync = None
+    if world > 1:
+        for _ in range(2):
+            step(False)
+        ms_nosync, _ = timed(steps, False)
+    if rank == 0:
+        frames = world * B * T
+        line = {"metric": "training_frames_per_second", "value": frames * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (split fp16 hi+lo tensor-core operands, fp32 accumulate)",
+                "data": "synthetic",
+                "config": {"workload": f"FS-EEND training step, {B} chunks x {T} frames per GPU, {n_spk} speakers + 2 label columns, "
+                                       "4 enc + 2 dec layers, dropout 0.1, Adam; inputs resident in HBM",
+                           "parallelism": f"dp{world}" if world > 1 else "single"},
+                "status": "SURVEY 8f N1 started: GEMM / attention / LayerNorm / BatchNorm / L2 / head forward+backward native; "
+                          "emb loss, layout copies, residual dropout, optimizer and the DDP bucketing are torch's",
+                "allreduce": None if world == 1 else {
+                    "bytes": 4 * n_grad, "collective": "NCCL all-reduce issued by torch DDP (25 MB buckets, overlapped with backward)",
+                    "ms_per_step_without_sync": ms_nosync / steps, "exposed_ms": (ms - ms_nosync) / steps},
+                "loss": float(loss.detach()), "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -620,10 +715,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the LS-EEND / streaming secondary workloads")
+    ap.add_argument("--train", action="store_true", help="measure the training step (forward + backward + all-reduce + Adam) instead")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.train:
+        run_train(args)
     else:
         run_ours(args)
 
