@@ -388,7 +388,21 @@ def secondary_measurements(dev):
     try:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import train_step_bench
-        out["fs_train_step_B64_T500"] = train_step_bench.measure(steps=3, warmup=2)
+        rec = train_step_bench.measure(steps=3, warmup=2)
+        # CPU figure beside it: the oracle restatement's forward + both losses + torch-autograd backward on the host cores
+        # (float32, 4 chunks x 500 frames, 6 label classes; BatchNorm on running statistics; no optimizer step)
+        sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and not k.endswith(".pe"))
+              for k, v in FO.random_state_dict(seed=0).items()}
+        csrc, clens = FO.synthetic_features(4, T)
+        ctgt = FO.synthetic_labels(3, clens, [6] * 4)
+        t0 = time.perf_counter()
+        o, el, _, _ = FO.forward(sd, csrc, ctgt, clens, FO.Cfg())
+        bce = sum(torch.nn.functional.binary_cross_entropy_with_logits(y, t) * len(y) for y, t in zip(o, ctgt)) / sum(clens)
+        (bce + el).backward()
+        cpu_s = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": 4 * T / cpu_s, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                               "sample": f"4 chunks x {T} frames, oracle forward + torch autograd backward, fp32, {cpu_threads} threads, {cpu_s:.1f} s"}
+        out["fs_train_step_B64_T500"] = rec
     except Exception as e:  # the headline must not depend on the secondary training measurement
         out["fs_train_step_B64_T500"] = {"error": repr(e)[:300]}
     return out
