@@ -136,22 +136,23 @@ __device__ __forceinline__ float half_warp_sum(float v) {
 }
 
 __global__ void __launch_bounds__(256)
-train_attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ lse, int T, int delay,
+train_attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ lse, int T, int S_in, int delay,
                       float scale, const Dropout drop) {
   extern __shared__ __align__(16) float sm[];
   float *Qs = sm, *Ks = sm + kTile, *Vs = sm + 2 * kTile, *Ps = sm + 3 * kTile;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int i0 = blockIdx.x * 64, h = blockIdx.y, n = blockIdx.z;
-  const float* base = qkv + static_cast<size_t>(n) * T * 768 + h * 64;
-  load_tile(Qs, base, i0, T, 768);
+  const size_t r0g = static_cast<size_t>(n / S_in) * T * S_in + (n % S_in);      // see train_attn_tc.cuh
+  const float* base = qkv + r0g * 768 + h * 64;
+  load_tile(Qs, base, i0, T, 768 * S_in);
   float o[4][4] = {}, m[4], l[4] = {};
 #pragma unroll
   for (int i = 0; i < 4; ++i) m[i] = -INFINITY;
   const int jlast = min(T - 1, i0 + 63 + delay);
   for (int j0 = 0; j0 <= jlast; j0 += 64) {
     __syncthreads();
-    load_tile(Ks, base + 256, j0, T, 768);
-    load_tile(Vs, base + 512, j0, T, 768);
+    load_tile(Ks, base + 256, j0, T, 768 * S_in);
+    load_tile(Vs, base + 512, j0, T, 768 * S_in);
     __syncthreads();
     float s[4][4] = {};
     mm_nt(Qs, Ks, ty, tx, s);
@@ -189,22 +190,23 @@ train_attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, fl
     if (row >= T) continue;
     const float inv = 1.f / l[i];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[(static_cast<size_t>(n) * T + row) * 256 + h * 64 + tx + 16 * j] = o[i][j] * inv;
+    for (int j = 0; j < 4; ++j) out[(r0g + static_cast<size_t>(row) * S_in) * 256 + h * 64 + tx + 16 * j] = o[i][j] * inv;
     if (tx == 0) lse[(static_cast<size_t>(n) * kHeads + h) * T + row] = m[i] + logf(l[i]);
   }
 }
 
 __global__ void __launch_bounds__(256)
 train_attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ out, const float* __restrict__ dout,
-                         const float* __restrict__ lse, float* __restrict__ dqkv, float* __restrict__ dsum, int T,
+                         const float* __restrict__ lse, float* __restrict__ dqkv, float* __restrict__ dsum, int T, int S_in,
                          int delay, float scale, const Dropout drop) {
   extern __shared__ __align__(16) float sm[];
   float *Qs = sm, *dOs = sm + kTile, *Ks = sm + 2 * kTile, *Vs = sm + 3 * kTile, *Ps = sm + 4 * kTile;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int i0 = blockIdx.x * 64, h = blockIdx.y, n = blockIdx.z;
-  const float* base = qkv + static_cast<size_t>(n) * T * 768 + h * 64;
-  load_tile(Qs, base, i0, T, 768);
-  load_tile(dOs, dout + static_cast<size_t>(n) * T * 256 + h * 64, i0, T, 256);
+  const size_t r0g = static_cast<size_t>(n / S_in) * T * S_in + (n % S_in);      // see train_attn_tc.cuh
+  const float* base = qkv + r0g * 768 + h * 64;
+  load_tile(Qs, base, i0, T, 768 * S_in);
+  load_tile(dOs, dout + r0g * 256 + h * 64, i0, T, 256 * S_in);
   __syncthreads();
   float D[4], L[4], dq[4][4] = {};
 #pragma unroll
@@ -214,7 +216,7 @@ train_attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
     if (row < T) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        d = fmaf(out[(static_cast<size_t>(n) * T + row) * 256 + h * 64 + tx + 16 * j], dOs[(ty + 16 * i) * kLD + tx + 16 * j], d);
+        d = fmaf(out[(r0g + static_cast<size_t>(row) * S_in) * 256 + h * 64 + tx + 16 * j], dOs[(ty + 16 * i) * kLD + tx + 16 * j], d);
     }
     D[i] = half_warp_sum(d);
     L[i] = row < T ? lse[(static_cast<size_t>(n) * kHeads + h) * T + row] : 0.f;
@@ -223,8 +225,8 @@ train_attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
   const int jlast = min(T - 1, i0 + 63 + delay);
   for (int j0 = 0; j0 <= jlast; j0 += 64) {
     __syncthreads();
-    load_tile(Ks, base + 256, j0, T, 768);
-    load_tile(Vs, base + 512, j0, T, 768);
+    load_tile(Ks, base + 256, j0, T, 768 * S_in);
+    load_tile(Vs, base + 512, j0, T, 768 * S_in);
     __syncthreads();
     float s[4][4] = {}, dp[4][4] = {};
     mm_nt(Qs, Ks, ty, tx, s);
@@ -249,27 +251,28 @@ train_attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
     const int row = i0 + ty + 16 * i;
     if (row >= T) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dqkv[(static_cast<size_t>(n) * T + row) * 768 + h * 64 + tx + 16 * j] = dq[i][j];
+    for (int j = 0; j < 4; ++j) dqkv[(r0g + static_cast<size_t>(row) * S_in) * 768 + h * 64 + tx + 16 * j] = dq[i][j];
   }
 }
 
 __global__ void __launch_bounds__(256)
 train_attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dout, const float* __restrict__ lse,
-                          const float* __restrict__ dsum, float* __restrict__ dqkv, int T, int delay, float scale,
+                          const float* __restrict__ dsum, float* __restrict__ dqkv, int T, int S_in, int delay, float scale,
                           const Dropout drop) {
   extern __shared__ __align__(16) float sm[];
   float *Ks = sm, *Vs = sm + kTile, *Qs = sm + 2 * kTile, *dOs = sm + 3 * kTile, *Ps = sm + 4 * kTile, *dSs = sm + 5 * kTile;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int j0 = blockIdx.x * 64, h = blockIdx.y, n = blockIdx.z;
-  const float* base = qkv + static_cast<size_t>(n) * T * 768 + h * 64;
-  load_tile(Ks, base + 256, j0, T, 768);
-  load_tile(Vs, base + 512, j0, T, 768);
+  const size_t r0g = static_cast<size_t>(n / S_in) * T * S_in + (n % S_in);      // see train_attn_tc.cuh
+  const float* base = qkv + r0g * 768 + h * 64;
+  load_tile(Ks, base + 256, j0, T, 768 * S_in);
+  load_tile(Vs, base + 512, j0, T, 768 * S_in);
   float dk[4][4] = {}, dv[4][4] = {};
   const size_t stat = (static_cast<size_t>(n) * kHeads + h) * T;
   for (int i0 = max(0, j0 - delay) / 64 * 64; i0 < T; i0 += 64) {
     __syncthreads();
-    load_tile(Qs, base, i0, T, 768);
-    load_tile(dOs, dout + static_cast<size_t>(n) * T * 256 + h * 64, i0, T, 256);
+    load_tile(Qs, base, i0, T, 768 * S_in);
+    load_tile(dOs, dout + r0g * 256 + h * 64, i0, T, 256 * S_in);
     __syncthreads();
     float s[4][4] = {}, dp[4][4] = {};
     mm_nt(Qs, Ks, ty, tx, s);
@@ -299,7 +302,7 @@ train_attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict
     if (key >= T) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const size_t o = (static_cast<size_t>(n) * T + key) * 768 + h * 64 + tx + 16 * j;
+      const size_t o = (r0g + static_cast<size_t>(key) * S_in) * 768 + h * 64 + tx + 16 * j;
       dqkv[o + 256] = dk[i][j];
       dqkv[o + 512] = dv[i][j];
     }
@@ -526,27 +529,29 @@ using namespace fseend;
 
 extern "C" {
 
-int fseend_train_attn_fwd(const float* qkv, int n_seq, int T, int mask_delay, float dropout_p, unsigned long long seed,
-                          float* out, float* lse, void* stream) {
+int fseend_train_attn_fwd(const float* qkv, int n_seq, int T, int seq_inner, int mask_delay, float dropout_p,
+                          unsigned long long seed, float* out, float* lse, void* stream) {
   return aguard([&] {
-    if (!qkv || !out || !lse || n_seq < 1 || T < 1 || mask_delay < 0 || n_seq > 65535)
+    if (!qkv || !out || !lse || n_seq < 1 || T < 1 || mask_delay < 0 || n_seq > 65535 || seq_inner < 1 || n_seq % seq_inner)
       throw std::invalid_argument("train_attn_fwd: bad arguments");
     set_attrs();
     const dim3 grid((T + 63) / 64, kHeads, n_seq);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (use_tensor_cores())
-      tc::attn_fwd_kernel<<<grid, 128, tc::kFwdSmem, st>>>(qkv, out, lse, T, mask_delay, 0.125f, make_dropout(dropout_p, seed));
+      tc::attn_fwd_kernel<<<grid, 128, tc::kFwdSmem, st>>>(qkv, out, lse, T, seq_inner, mask_delay, 0.125f, make_dropout(dropout_p, seed));
     else
-      train_attn_fwd_kernel<<<grid, 256, 4 * kTile * 4, st>>>(qkv, out, lse, T, mask_delay, 0.125f, make_dropout(dropout_p, seed));
+      train_attn_fwd_kernel<<<grid, 256, 4 * kTile * 4, st>>>(qkv, out, lse, T, seq_inner, mask_delay, 0.125f, make_dropout(dropout_p, seed));
     check_launch("train_attn_fwd");
   });
 }
 
 // dsum: scratch fp32 [n_seq][4][T] + 16 floats (row sums of dO * O; the gradient-scale slot behind them)
 int fseend_train_attn_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int n_seq, int T,
-                          int mask_delay, float dropout_p, unsigned long long seed, float* dqkv, float* dsum, void* stream) {
+                          int seq_inner, int mask_delay, float dropout_p, unsigned long long seed, float* dqkv, float* dsum,
+                          void* stream) {
   return aguard([&] {
-    if (!qkv || !out || !dout || !lse || !dqkv || !dsum || n_seq < 1 || T < 1 || mask_delay < 0 || n_seq > 65535)
+    if (!qkv || !out || !dout || !lse || !dqkv || !dsum || n_seq < 1 || T < 1 || mask_delay < 0 || n_seq > 65535 ||
+        seq_inner < 1 || n_seq % seq_inner)
       throw std::invalid_argument("train_attn_bwd: bad arguments");
     set_attrs();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -558,11 +563,11 @@ int fseend_train_attn_bwd(const float* qkv, const float* out, const float* dout,
       if (cudaMemsetAsync(slot, 0, 4, st) != cudaSuccess) throw std::runtime_error("train_attn_bwd: memset failed");
       attn_absmax_kernel<<<592, 256, 0, st>>>(dout, static_cast<size_t>(n_seq) * T * 64, slot);
       attn_make_scale_kernel<<<1, 1, 0, st>>>(slot, gsc);
-      tc::attn_bwd_dq_kernel<<<grid, 128, tc::kDqSmem, st>>>(qkv, out, dout, lse, dqkv, dsum, T, mask_delay, 0.125f, drop, gsc);
-      tc::attn_bwd_dkv_kernel<<<grid, 128, tc::kDkvSmem, st>>>(qkv, dout, lse, dsum, dqkv, T, mask_delay, 0.125f, drop, gsc);
+      tc::attn_bwd_dq_kernel<<<grid, 128, tc::kDqSmem, st>>>(qkv, out, dout, lse, dqkv, dsum, T, seq_inner, mask_delay, 0.125f, drop, gsc);
+      tc::attn_bwd_dkv_kernel<<<grid, 128, tc::kDkvSmem, st>>>(qkv, dout, lse, dsum, dqkv, T, seq_inner, mask_delay, 0.125f, drop, gsc);
     } else {
-      train_attn_bwd_dq_kernel<<<grid, 256, 5 * kTile * 4, st>>>(qkv, out, dout, lse, dqkv, dsum, T, mask_delay, 0.125f, drop);
-      train_attn_bwd_dkv_kernel<<<grid, 256, 6 * kTile * 4, st>>>(qkv, dout, lse, dsum, dqkv, T, mask_delay, 0.125f, drop);
+      train_attn_bwd_dq_kernel<<<grid, 256, 5 * kTile * 4, st>>>(qkv, out, dout, lse, dqkv, dsum, T, seq_inner, mask_delay, 0.125f, drop);
+      train_attn_bwd_dkv_kernel<<<grid, 256, 6 * kTile * 4, st>>>(qkv, dout, lse, dsum, dqkv, T, seq_inner, mask_delay, 0.125f, drop);
     }
     check_launch("train_attn_bwd");
   });

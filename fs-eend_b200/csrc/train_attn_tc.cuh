@@ -127,21 +127,23 @@ __device__ __forceinline__ float quad_sum(float v) {
 // forward: grid (q tiles, heads, sequences), 128 threads; warp w owns query rows i0 + 16 w .. + 16
 constexpr int kFwdSmem = 6 * TILE_H * 2;
 __global__ void __launch_bounds__(128)
-attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ lse, int T, int delay,
+attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ lse, int T, int S_in, int delay,
                 float scale, const Dropout drop) {
   extern __shared__ __align__(16) __half smh[];
   __half *Qh = smh, *Ql = Qh + TILE_H, *Kh = Ql + TILE_H, *Kl = Kh + TILE_H, *Vth = Kl + TILE_H, *Vtl = Vth + TILE_H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int i0 = blockIdx.x * 64, h = blockIdx.y, n = blockIdx.z, r0 = warp * 16;
-  const float* base = qkv + static_cast<size_t>(n) * T * 768 + h * 64;
-  load_split(Qh, Ql, base, i0, T, 768, scale);          // the 64^-1/2 scale is a power of two: folded into q exactly
+  // sequence n of an interleaved batch [n_seq / S_in][T][S_in][.]: frame t lives at row r0g + t * S_in (S_in = 1: plain [n][T])
+  const size_t r0g = static_cast<size_t>(n / S_in) * T * S_in + (n % S_in);
+  const float* base = qkv + r0g * 768 + h * 64;
+  load_split(Qh, Ql, base, i0, T, 768 * S_in, scale);          // the 64^-1/2 scale is a power of two: folded into q exactly
   float o[8][4] = {}, m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
   const int row[2] = {i0 + r0 + g, i0 + r0 + g + 8};
   const int jlast = min(T - 1, i0 + 63 + delay);
   for (int j0 = 0; j0 <= jlast; j0 += 64) {
     __syncthreads();
-    load_split(Kh, Kl, base + 256, j0, T, 768, 1.f);
-    load_split_t(Vth, Vtl, base + 512, j0, T, 768, 1.f);
+    load_split(Kh, Kl, base + 256, j0, T, 768 * S_in, 1.f);
+    load_split_t(Vth, Vtl, base + 512, j0, T, 768 * S_in, 1.f);
     __syncthreads();
     float s[8][4] = {};
     warp_mm_nt(Qh, Ql, r0, Kh, Kl, g, t, s);
@@ -185,7 +187,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* _
   for (int a = 0; a < 2; ++a) {
     if (row[a] >= T) continue;
     const float inv = 1.f / l[a];
-    float* op = out + (static_cast<size_t>(n) * T + row[a]) * 256 + h * 64 + 2 * t;
+    float* op = out + (r0g + static_cast<size_t>(row[a]) * S_in) * 256 + h * 64 + 2 * t;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
       *reinterpret_cast<float2*>(op + nt * 8) = make_float2(o[nt][2 * a] * inv, o[nt][2 * a + 1] * inv);
@@ -198,28 +200,31 @@ attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* _
 constexpr int kDqSmem = 10 * TILE_H * 2 + 64 * 4;
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ out, const float* __restrict__ dout,
-                   const float* __restrict__ lse, float* __restrict__ dqkv, float* __restrict__ dsum, int T, int delay,
-                   float scale, const Dropout drop, const float* __restrict__ gsc) {
+                   const float* __restrict__ lse, float* __restrict__ dqkv, float* __restrict__ dsum, int T, int S_in,
+                   int delay, float scale, const Dropout drop, const float* __restrict__ gsc) {
   extern __shared__ __align__(16) __half smh[];
   __half *Qh = smh, *Ql = Qh + TILE_H, *dOh = Ql + TILE_H, *dOl = dOh + TILE_H, *Kh = dOl + TILE_H, *Kl = Kh + TILE_H;
   __half *Kth = Kl + TILE_H, *Ktl = Kth + TILE_H, *Vh = Ktl + TILE_H, *Vl = Vh + TILE_H;
   float* Ds = reinterpret_cast<float*>(Vl + TILE_H);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int i0 = blockIdx.x * 64, h = blockIdx.y, n = blockIdx.z, r0 = warp * 16;
-  const float* base = qkv + static_cast<size_t>(n) * T * 768 + h * 64;
-  const float* dob = dout + static_cast<size_t>(n) * T * 256 + h * 64;
+  // sequence n of an interleaved batch [n_seq / S_in][T][S_in][.]: frame t lives at row r0g + t * S_in (S_in = 1: plain [n][T])
+  const size_t r0g = static_cast<size_t>(n / S_in) * T * S_in + (n % S_in);
+  const float* base = qkv + r0g * 768 + h * 64;
+  const float* dob = dout + r0g * 256 + h * 64;
   const size_t stat = (static_cast<size_t>(n) * kHeads + h) * T;
   // gradients are ~1e-6 (fp16-subnormal): dO is multiplied by a power of two (max |dO| -> [16, 32)) before the split,
   // every quantity derived from it (D, dP, dS) carries the factor, the result is multiplied by its inverse
   const float gscale = __ldg(gsc), ginv = __ldg(gsc + 1);
-  load_split(Qh, Ql, base, i0, T, 768, scale);
-  load_split(dOh, dOl, dob, i0, T, 256, gscale);
+  load_split(Qh, Ql, base, i0, T, 768 * S_in, scale);
+  load_split(dOh, dOl, dob, i0, T, 256 * S_in, gscale);
   for (int rr = 0; rr < 16; ++rr) {                      // D = rowsum(dO * O), one row per iteration, lanes over d
     const int rw = i0 + r0 + rr;
     float d = 0.f;
     if (rw < T) {
-      const float* op = out + (static_cast<size_t>(n) * T + rw) * 256 + h * 64;
-      d = op[lane] * dob[static_cast<size_t>(rw) * 256 + lane] + op[lane + 32] * dob[static_cast<size_t>(rw) * 256 + lane + 32];
+      const float* op = out + (r0g + static_cast<size_t>(rw) * S_in) * 256 + h * 64;
+      const float* dp = dob + static_cast<size_t>(rw) * 256 * S_in;
+      d = op[lane] * dp[lane] + op[lane + 32] * dp[lane + 32];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
@@ -239,9 +244,9 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
   const int jlast = min(T - 1, i0 + 63 + delay);
   for (int j0 = 0; j0 <= jlast; j0 += 64) {
     __syncthreads();
-    load_split(Kh, Kl, base + 256, j0, T, 768, 1.f);
-    load_split_t(Kth, Ktl, base + 256, j0, T, 768, 1.f);
-    load_split(Vh, Vl, base + 512, j0, T, 768, 1.f);
+    load_split(Kh, Kl, base + 256, j0, T, 768 * S_in, 1.f);
+    load_split_t(Kth, Ktl, base + 256, j0, T, 768 * S_in, 1.f);
+    load_split(Vh, Vl, base + 512, j0, T, 768 * S_in, 1.f);
     __syncthreads();
     float s[8][4] = {}, dp[8][4] = {};
     warp_mm_nt(Qh, Ql, r0, Kh, Kl, g, t, s);
@@ -266,7 +271,7 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
     if (row[a] >= T) continue;
-    float* op = dqkv + (static_cast<size_t>(n) * T + row[a]) * 768 + h * 64 + 2 * t;
+    float* op = dqkv + (r0g + static_cast<size_t>(row[a]) * S_in) * 768 + h * 64 + 2 * t;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
       *reinterpret_cast<float2*>(op + nt * 8) = make_float2(dq[nt][2 * a] * ginv, dq[nt][2 * a + 1] * ginv);
@@ -279,7 +284,7 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
 constexpr int kDkvSmem = 12 * TILE_H * 2 + 2 * 64 * 4;
 __global__ void __launch_bounds__(128)
 attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dout, const float* __restrict__ lse,
-                    const float* __restrict__ dsum, float* __restrict__ dqkv, int T, int delay, float scale,
+                    const float* __restrict__ dsum, float* __restrict__ dqkv, int T, int S_in, int delay, float scale,
                     const Dropout drop, const float* __restrict__ gsc) {
   extern __shared__ __align__(16) __half smh[];
   __half *Kh = smh, *Kl = Kh + TILE_H, *Vh = Kl + TILE_H, *Vl = Vh + TILE_H, *Qh = Vl + TILE_H, *Ql = Qh + TILE_H;
@@ -288,20 +293,22 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dou
   float* Ds = Ls + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int j0 = blockIdx.x * 64, h = blockIdx.y, n = blockIdx.z, r0 = warp * 16;
-  const float* base = qkv + static_cast<size_t>(n) * T * 768 + h * 64;
-  const float* dob = dout + static_cast<size_t>(n) * T * 256 + h * 64;
+  // sequence n of an interleaved batch [n_seq / S_in][T][S_in][.]: frame t lives at row r0g + t * S_in (S_in = 1: plain [n][T])
+  const size_t r0g = static_cast<size_t>(n / S_in) * T * S_in + (n % S_in);
+  const float* base = qkv + r0g * 768 + h * 64;
+  const float* dob = dout + r0g * 256 + h * 64;
   const size_t stat = (static_cast<size_t>(n) * kHeads + h) * T;
   const float gscale = __ldg(gsc), ginv = __ldg(gsc + 1);
-  load_split(Kh, Kl, base + 256, j0, T, 768, 1.f);
-  load_split(Vh, Vl, base + 512, j0, T, 768, 1.f);
+  load_split(Kh, Kl, base + 256, j0, T, 768 * S_in, 1.f);
+  load_split(Vh, Vl, base + 512, j0, T, 768 * S_in, 1.f);
   const int key[2] = {j0 + r0 + g, j0 + r0 + g + 8};
   float dk[8][4] = {}, dv[8][4] = {};
   for (int i0 = max(0, j0 - delay) / 64 * 64; i0 < T; i0 += 64) {
     __syncthreads();
-    load_split(Qh, Ql, base, i0, T, 768, scale);
-    load_split_t(Qth, Qtl, base, i0, T, 768, scale);
-    load_split(dOh, dOl, dob, i0, T, 256, gscale);
-    load_split_t(dOth, dOtl, dob, i0, T, 256, gscale);
+    load_split(Qh, Ql, base, i0, T, 768 * S_in, scale);
+    load_split_t(Qth, Qtl, base, i0, T, 768 * S_in, scale);
+    load_split(dOh, dOl, dob, i0, T, 256 * S_in, gscale);
+    load_split_t(dOth, dOtl, dob, i0, T, 256 * S_in, gscale);
     if (threadIdx.x < 64) {
       const int q = i0 + threadIdx.x;
       Ls[threadIdx.x] = q < T ? lse[stat + q] : 0.f;
@@ -340,7 +347,7 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dou
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
     if (key[a] >= T) continue;
-    float* op = dqkv + (static_cast<size_t>(n) * T + key[a]) * 768 + h * 64 + 2 * t;
+    float* op = dqkv + (r0g + static_cast<size_t>(key[a]) * S_in) * 768 + h * 64 + 2 * t;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       *reinterpret_cast<float2*>(op + 256 + nt * 8) = make_float2(dk[nt][2 * a] * ginv, dk[nt][2 * a + 1] * ginv);

@@ -159,33 +159,37 @@ class AddLayerNormFn(torch.autograd.Function):
 
 
 class CausalAttnFn(torch.autograd.Function):
-    """qkv [n_seq, T, 768] (already projected, q | k | v) -> [n_seq, T, 256]; key j visible to query i iff j <= i + delay."""
+    """Causal 4-head attention on projected qkv (q | k | v); key j visible to query i iff j <= i + delay.
+
+    qkv [n_seq, T, 768] -> [n_seq, T, 256], or the attractor decoder's interleaved layout qkv [B, T, S, 768] ->
+    [B, T, S, 256], where every (b, s) is a sequence over T read with row stride S (no transposed copy)."""
 
     @staticmethod
     def forward(ctx, qkv, mask_delay: int = 0, dropout_p: float = 0.0, seed: int = 0):
         qkv = _f32c(qkv, "CausalAttnFn qkv")
-        if qkv.dim() != 3 or qkv.shape[-1] != 768:
-            raise FseendError("CausalAttnFn: qkv must be [n_seq, T, 768]")
-        n, T, _ = qkv.shape
-        out = torch.empty(n, T, 256, device=qkv.device, dtype=torch.float32)
+        if qkv.dim() not in (3, 4) or qkv.shape[-1] != 768:
+            raise FseendError("CausalAttnFn: qkv must be [n_seq, T, 768] or [B, T, S, 768]")
+        inner = qkv.shape[2] if qkv.dim() == 4 else 1
+        n, T = qkv.shape[0] * inner, qkv.shape[1]
+        out = torch.empty(*qkv.shape[:-1], 256, device=qkv.device, dtype=torch.float32)
         lse = torch.empty(n, 4, T, device=qkv.device, dtype=torch.float32)
         with torch.cuda.device(qkv.device):
-            _check(lib().fseend_train_attn_fwd(_ptr(qkv), n, T, int(mask_delay), float(dropout_p), int(seed), _ptr(out),
+            _check(lib().fseend_train_attn_fwd(_ptr(qkv), n, T, inner, int(mask_delay), float(dropout_p), int(seed), _ptr(out),
                                                _ptr(lse), _stream()))
         ctx.save_for_backward(qkv, out, lse)
-        ctx.delay, ctx.p, ctx.seed = int(mask_delay), float(dropout_p), int(seed)
+        ctx.delay, ctx.p, ctx.seed, ctx.inner = int(mask_delay), float(dropout_p), int(seed), inner
         return out
 
     @staticmethod
     def backward(ctx, dout):
         qkv, out, lse = ctx.saved_tensors
-        n, T, _ = qkv.shape
+        n, _, T = lse.shape
         dout = _f32c(dout, "CausalAttnFn dout")
         dqkv = torch.empty_like(qkv)
         dsum = torch.empty(lse.numel() + 16, device=lse.device, dtype=torch.float32)
         with torch.cuda.device(qkv.device):
-            _check(lib().fseend_train_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), n, T, ctx.delay, ctx.p, ctx.seed,
-                                               _ptr(dqkv), _ptr(dsum), _stream()))
+            _check(lib().fseend_train_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), n, T, ctx.inner, ctx.delay, ctx.p,
+                                               ctx.seed, _ptr(dqkv), _ptr(dsum), _stream()))
         return dqkv, None, None, None
 
 
@@ -346,16 +350,18 @@ def _ffn(layer, x: torch.Tensor) -> torch.Tensor:
 def fusion_layer_forward(layer, x: torch.Tensor, mask_delay: int = 0) -> torch.Tensor:
     """The reference's attractor-decoder layer, live path ``FS:fusion:356-376`` (post-norm), differentiable.
 
-    x: [B, T, S, 256].  Time attention runs over [B*S, T, 256] (causal), speaker attention over [B*T, S, 256] (no mask);
-    ``norm12`` is unused, as in the reference.  The two layout changes are torch copies; in train mode the residual
+    x: [B, T, S, 256].  Time attention runs per (b, s) over T (causal), speaker attention per (b, t) over S (no mask);
+    ``norm12`` is unused, as in the reference.  There are no layout copies (the reference transposes twice per layer,
+    ``:358-365``); in train mode the residual
     dropouts (dropout11 / dropout21 / dropout2, ``:380-399``) are torch's, the attention-probability dropout is the
     kernels' own (hash mask)."""
     B, T, S, D = x.shape
     tr = layer.training
-    y = x.transpose(1, 2).reshape(B * S, T, D)
-    a = _mha(layer.self_attn1, y, lambda qkv, p, seed: CausalAttnFn.apply(qkv, mask_delay, p, seed))
-    y = AddLayerNormFn.apply(_drop(a, layer.dropout11.p, tr), y, layer.norm11.weight, layer.norm11.bias, layer.norm11.eps)
-    y = y.reshape(B, S, T, D).transpose(1, 2).reshape(B * T, S, D)
+    # every op but the two attention cores is row-wise, so the tensor stays [B, T, S, D] throughout: the time attention
+    # reads sequence (b, s) in place with row stride S, the speaker attention sees [B * T, S, .] as a view
+    a = _mha(layer.self_attn1, x, lambda qkv, p, seed: CausalAttnFn.apply(qkv, mask_delay, p, seed))
+    y = AddLayerNormFn.apply(_drop(a, layer.dropout11.p, tr), x, layer.norm11.weight, layer.norm11.bias, layer.norm11.eps)
+    y = y.reshape(B * T, S, D)
     a = _mha(layer.self_attn2, y, lambda qkv, p, seed: SpeakerAttnFn.apply(qkv, p, seed))
     y = AddLayerNormFn.apply(_drop(a, layer.dropout21.p, tr), y, layer.norm21.weight, layer.norm21.bias, layer.norm21.eps)
     y = AddLayerNormFn.apply(_drop(_ffn(layer, y), layer.dropout2.p, tr), y, layer.norm22.weight, layer.norm22.bias,

@@ -193,9 +193,9 @@ def lib() -> C.CDLL:
     L.fseend_train_layernorm_bwd.restype = ip
     L.fseend_train_layernorm_bwd.argtypes = [vp, vp, vp, ip, fp, vp, vp, vp, vp, sz, vp]
     L.fseend_train_attn_fwd.restype = ip
-    L.fseend_train_attn_fwd.argtypes = [vp, ip, ip, ip, fp, C.c_ulonglong, vp, vp, vp]
+    L.fseend_train_attn_fwd.argtypes = [vp, ip, ip, ip, ip, fp, C.c_ulonglong, vp, vp, vp]
     L.fseend_train_attn_bwd.restype = ip
-    L.fseend_train_attn_bwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, fp, C.c_ulonglong, vp, vp, vp]
+    L.fseend_train_attn_bwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, fp, C.c_ulonglong, vp, vp, vp]
     L.fseend_train_spk_attn_fwd.restype = ip
     L.fseend_train_spk_attn_fwd.argtypes = [vp, ip, ip, fp, C.c_ulonglong, vp, vp]
     L.fseend_train_spk_attn_bwd.restype = ip

@@ -307,12 +307,15 @@ int fseend_train_layernorm_bwd(const float* x, const float* g, const float* dy, 
  * query i iff j <= i + mask_delay (FS model file :152-155); lse fp32 [n_seq][4][T] is saved for the backward.
  * dropout_p / seed: attention-probability dropout (nn.MultiheadAttention's `dropout`, on the softmax output, kept
  * elements scaled by 1/(1-p)); the mask is a counter-based hash of (seed, sequence, head, query, key), so the backward
- * regenerates it from the same (dropout_p, seed).  dropout_p = 0 disables it. */
-int fseend_train_attn_fwd(const float* qkv, int n_seq, int T, int mask_delay, float dropout_p, unsigned long long seed,
-                          float* out, float* lse, void* stream);
+ * regenerates it from the same (dropout_p, seed).  dropout_p = 0 disables it.
+ * seq_inner: 1 for the plain layout above; S for an interleaved batch [n_seq / S][T][S][768] -> [n_seq / S][T][S][256] (the
+ * attractor decoder's (B, T, S, D) tensor, whose time attention runs per (b, s) — FS-EEND/nnet/modules/merge_tfm_encoder.py
+ * :358-365 transposes instead): sequence n = b * S + s is read and written in place with row stride S, no layout copy. */
+int fseend_train_attn_fwd(const float* qkv, int n_seq, int T, int seq_inner, int mask_delay, float dropout_p,
+                          unsigned long long seed, float* out, float* lse, void* stream);
 /* dqkv fp32 [n_seq][T][768] from dout [n_seq][T][256]; dsum: scratch fp32 [n_seq * 4 * T + 16]. */
 int fseend_train_attn_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int n_seq, int T,
-                          int mask_delay, float dropout_p, unsigned long long seed, float* dqkv, float* dsum,
+                          int seq_inner, int mask_delay, float dropout_p, unsigned long long seed, float* dqkv, float* dsum,
                           void* stream);
 /* Speaker-axis attention (FS-EEND/nnet/modules/transformer_encoder_fusion.py:390 self_attn2: S x S per frame, no mask)
  * on projected qkv fp32 [n_frames][S][768] -> out fp32 [n_frames][S][256]; S <= 16.  The backward recomputes the

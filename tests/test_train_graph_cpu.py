@@ -13,9 +13,19 @@ def _attn(qkv, delay):
     n, T, _ = qkv.shape
     q, k, v = (t.reshape(n, T, 4, 64).transpose(1, 2) for t in qkv.split(256, dim=-1))
     s = (q * 0.125) @ k.transpose(-1, -2)
-    i = torch.arange(T)
+    i = torch.arange(T, device=qkv.device)
     s = s.masked_fill(i[None, :] > i[:, None] + delay, float("-inf"))
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(n, T, 256)
+
+
+
+def _causal4(qkv, delay):
+    """[n, T, 768] or the decoder's interleaved [B, T, S, 768] (sequence (b, s) over T)."""
+    if qkv.dim() == 3:
+        return _attn(qkv, delay)
+    B, T, S, _ = qkv.shape
+    o = _attn(qkv.transpose(1, 2).reshape(B * S, T, 768), delay)
+    return o.reshape(B, S, T, 256).transpose(1, 2)
 
 
 class _Lin:
@@ -50,7 +60,7 @@ def _bn(bn, x):
 
 
 class _Causal:
-    apply = staticmethod(lambda qkv, delay, p=0.0, seed=0: _attn(qkv, delay))
+    apply = staticmethod(lambda qkv, delay, p=0.0, seed=0: _causal4(qkv, delay))
 
 
 class _Spk:

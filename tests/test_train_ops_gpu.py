@@ -304,6 +304,25 @@ def ref_attention_dropout(qkv, delay, keep, p):
     return (pr @ v).transpose(1, 2).reshape(n, T, 256)
 
 
+@pytest.mark.parametrize("kernels", ["tensor", "cuda_core"])
+def test_causal_attention_interleaved_layout(built_lib, monkeypatch, kernels):
+    """The attractor decoder's [B, T, S, 768] tensor read in place (sequence (b, s) with row stride S), with dropout: equal
+    to the plain layout on the transposed copy, forward and backward, same mask (sequence index b * S + s)."""
+    from fseend_b200.autograd import CausalAttnFn
+    monkeypatch.setenv("FSEEND_TRAIN_ATTN", "1" if kernels == "tensor" else "0")
+    g = torch.Generator().manual_seed(31)
+    B, T, S = 2, 150, 3
+    q4 = (1.5 * torch.randn(B, T, S, 768, generator=g)).cuda().requires_grad_()
+    do4 = torch.randn(B, T, S, 256, generator=g).cuda()
+    o4 = CausalAttnFn.apply(q4, 1, 0.2, 4242)
+    o4.backward(do4)
+    q3 = q4.detach().transpose(1, 2).reshape(B * S, T, 768).contiguous().requires_grad_()
+    o3 = CausalAttnFn.apply(q3, 1, 0.2, 4242)
+    o3.backward(do4.transpose(1, 2).reshape(B * S, T, 256).contiguous())
+    assert torch.equal(o4.detach().transpose(1, 2).reshape(B * S, T, 256), o3.detach())
+    assert torch.equal(q4.grad.transpose(1, 2).reshape(B * S, T, 768), q3.grad)
+
+
 def test_causal_attention_tiny_gradients(built_lib):
     """Upstream gradients as the training loss produces them (1e-7, far below the fp16 normal range): the tensor-core
     backward rescales dO by a power of two before the operand split."""
@@ -455,7 +474,7 @@ def test_training_batchnorm_train_mode_matches_torch_graph(built_lib, monkeypatc
             mp.setattr(mod, "LinearFn", S._Lin)
             mp.setattr(mod, "AddLayerNormFn", S._AddLn)
         mp.setattr(A, "FfnFn", S._Ffn)
-        mp.setattr(A, "CausalAttnFn", type("C", (), {"apply": staticmethod(lambda qkv, d, p=0.0, seed=0: ref_attention(qkv, d))}))
+        mp.setattr(A, "CausalAttnFn", S._Causal)
         mp.setattr(A, "SpeakerAttnFn", type("P", (), {"apply": staticmethod(lambda qkv, p=0.0, seed=0: ref_attention(qkv, 1 << 20))}))
         mp.setattr(G, "L2NormFn", S._L2)
         mp.setattr(G, "HeadFn", S._Head)

@@ -29,6 +29,16 @@ def _attn(qkv, delay):
     return o.transpose(1, 2).reshape(n, T, 256)
 
 
+
+def _causal4(qkv, delay):
+    """[n, T, 768] or the decoder's interleaved [B, T, S, 768] (sequence (b, s) over T)."""
+    if qkv.dim() == 3:
+        return _attn(qkv, delay)
+    B, T, S, _ = qkv.shape
+    o = _attn(qkv.transpose(1, 2).reshape(B * S, T, 768), delay)
+    return o.reshape(B, S, T, 256).transpose(1, 2)
+
+
 class _Lin:
     @staticmethod
     def apply(x, w, b, act):
@@ -61,7 +71,7 @@ def _bn(bn, x):
 
 
 class _Causal:
-    apply = staticmethod(lambda qkv, delay, p=0.0, seed=0: _attn(qkv, delay))
+    apply = staticmethod(lambda qkv, delay, p=0.0, seed=0: _causal4(qkv, delay))
 
 
 class _Spk:
