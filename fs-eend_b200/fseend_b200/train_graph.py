@@ -6,8 +6,7 @@ What runs where (DESIGN.md §7 has the table):
     FFNs, the k=19 Conv1d as one GEMM over unfolded frames, the attractor ``convert``), every residual + LayerNorm, the
     causal time attention of encoder and decoder, the speaker-axis attention — >99 % of the step's FLOPs;
     also native: BatchNorm1d with batch statistics, the two L2 normalisations, the dot-product head;
-  * torch CUDA ops (interim, small): the layout changes between the (B*S, T) and (B*T, S) views, the frame unfolding
-    of the Conv1d, the length mask, the embedding-consistency loss (three batched matmuls), dropout masks on the
+  * torch CUDA ops (interim, small): the frame unfolding of the Conv1d, the length mask, the embedding-consistency loss (three batched matmuls), dropout masks on the
     residual branches, the optimizer.
 Dropout (reference recipes train with 0.1): the residual / FFN dropouts are torch's functional dropout on the native
 kernels' outputs; the attention-probability dropout inside nn.MultiheadAttention is implemented in the attention kernels
